@@ -1,0 +1,403 @@
+// Cell list build + fixed-radius search (count / fill) + exclusive scans.
+// Replaces open3d build_spatial_hash_table / fixed_radius_search as called from
+// utils/convolutions.py:354-358 of the reference.  HBM-bound integer/byte work: coalesced float4 candidate
+// reads from the cell-major copy of the points, warp-ballot compaction for ordered, coalesced CSR writes.
+#include "common.cuh"
+
+namespace dmcf {
+
+static constexpr int kScanThreads = 512;
+static constexpr int kScanItems = 4;
+static constexpr int kScanTile = kScanThreads * kScanItems;
+
+// ---------------------------------------------------------------------------------------------------------
+// exclusive scan (int32 in -> T out), three small kernels; out has n+1 entries.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) k_scan_local(const int32_t* __restrict__ in, int64_t n,
+                                                               T* __restrict__ out, int64_t* __restrict__ tile_sums) {
+    __shared__ int64_t warp_sums[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int32_t v[kScanItems];
+    int64_t local = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        local += v[i];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = (lane < kScanThreads / 32) ? warp_sums[lane] : 0;
+        int64_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = wi - w;  // exclusive warp offsets
+        if (lane == kScanThreads / 32 - 1) tile_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    int64_t run = warp_sums[warp] + incl - local;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (base + i < n) out[base + i] = (T)run;
+        run += v[i];
+    }
+}
+
+// single block: exclusive scan of the tile sums in place
+__global__ void __launch_bounds__(1024) k_scan_tiles(int64_t* __restrict__ tile_sums, int64_t n_tiles) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t start = 0; start < n_tiles; start += 1024) {
+        int64_t i = start + threadIdx.x;
+        int64_t v = (i < n_tiles) ? tile_sums[i] : 0;
+        int64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = warp_sums[lane];
+            int64_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - w;
+        }
+        __syncthreads();
+        const int64_t carry = carry_s;
+        const int64_t excl = carry + warp_sums[warp] + incl - v;
+        if (i < n_tiles) tile_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + v;
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) k_scan_add(T* __restrict__ out, int64_t n,
+                                                             const int64_t* __restrict__ tile_sums) {
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    const int64_t off = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+        if (base + i < n) out[base + i] = (T)(out[base + i] + off);
+}
+
+// total: out[n] = out[n-1] + in[n-1]
+template <typename T>
+__global__ void k_scan_total(const int32_t* __restrict__ in, int64_t n, T* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[n] = (n > 0) ? (T)(out[n - 1] + in[n - 1]) : (T)0;
+}
+
+template <typename T>
+static int exclusive_scan(const int32_t* in, int64_t n, T* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    DMCF_REQUIRE(n >= 0, "scan: negative length");
+    const int64_t n_tiles = ceil_div(n, kScanTile);
+    if ((size_t)(n_tiles > 0 ? n_tiles : 1) * sizeof(int64_t) > ws_bytes)
+        return set_error(DMCF_ERR_WORKSPACE, "scan: workspace %zu < %zu", ws_bytes, (size_t)n_tiles * 8);
+    int64_t* tile_sums = (int64_t*)ws;
+    if (n_tiles > 0) {
+        k_scan_local<T><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(in, n, out, tile_sums);
+        DMCF_LAUNCH_CHECK("k_scan_local");
+        if (n_tiles > 1) {
+            k_scan_tiles<<<1, 1024, 0, st>>>(tile_sums, n_tiles);
+            DMCF_LAUNCH_CHECK("k_scan_tiles");
+            k_scan_add<T><<<(unsigned)n_tiles, kScanThreads, 0, st>>>(out, n, tile_sums);
+            DMCF_LAUNCH_CHECK("k_scan_add");
+        }
+    }
+    k_scan_total<T><<<1, 32, 0, st>>>(in, n, out);
+    DMCF_LAUNCH_CHECK("k_scan_total");
+    return DMCF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cell list
+// ---------------------------------------------------------------------------------------------------------
+struct GridView {
+    float ox, oy, oz, inv_cell;
+    int nx, ny, nz, n_points;
+    const int32_t* cell_start;
+    const int32_t* sorted_index;
+    const float4* sorted_pos;
+};
+
+__device__ __forceinline__ int cell_of_point(const GridView& g, float x, float y, float z) {
+    const int cx = cell_coord(x, g.ox, g.inv_cell, g.nx);
+    const int cy = cell_coord(y, g.oy, g.inv_cell, g.ny);
+    const int cz = cell_coord(z, g.oz, g.inv_cell, g.nz);
+    return (cz * g.ny + cy) * g.nx + cx;
+}
+
+__global__ void __launch_bounds__(256) k_cell_hist(GridView g, const float* __restrict__ pts, int32_t* __restrict__ cell_of,
+                                                     int32_t* __restrict__ cell_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n_points) return;
+    const int c = cell_of_point(g, pts[3 * (int64_t)i], pts[3 * (int64_t)i + 1], pts[3 * (int64_t)i + 2]);
+    cell_of[i] = c;
+    atomicAdd(&cell_count[c], 1);
+}
+
+__global__ void __launch_bounds__(256) k_cell_scatter(int n, const int32_t* __restrict__ cell_of,
+                                                        const int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_fill,
+                                                        int32_t* __restrict__ sorted_index) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell_of[i];
+    const int slot = atomicAdd(&cell_fill[c], 1);
+    sorted_index[cell_start[c] + slot] = i;
+}
+
+// one thread per cell: order the ids of the cell ascending so that the layout (and every neighbour row
+// built from it) is deterministic and independent of atomic arrival order.
+__global__ void __launch_bounds__(256) k_cell_sort(int64_t n_cells, const int32_t* __restrict__ cell_start,
+                                                     int32_t* __restrict__ sorted_index) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const int s = cell_start[c], e = cell_start[c + 1];
+    const int m = e - s;
+    if (m < 2) return;
+    int32_t* a = sorted_index + s;
+    if (m <= 48) {
+        for (int i = 1; i < m; ++i) {
+            const int32_t v = a[i];
+            int j = i - 1;
+            while (j >= 0 && a[j] > v) {
+                a[j + 1] = a[j];
+                --j;
+            }
+            a[j + 1] = v;
+        }
+        return;
+    }
+    // heap sort for crowded cells (clamped border cells, degenerate inputs)
+    for (int start = m / 2 - 1; start >= 0; --start) {
+        int root = start;
+        const int32_t v = a[root];
+        while (true) {
+            int child = 2 * root + 1;
+            if (child >= m) break;
+            if (child + 1 < m && a[child + 1] > a[child]) ++child;
+            if (a[child] <= v) break;
+            a[root] = a[child];
+            root = child;
+        }
+        a[root] = v;
+    }
+    for (int end = m - 1; end > 0; --end) {
+        const int32_t v = a[end];
+        a[end] = a[0];
+        int root = 0;
+        while (true) {
+            int child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && a[child + 1] > a[child]) ++child;
+            if (a[child] <= v) break;
+            a[root] = a[child];
+            root = child;
+        }
+        a[root] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cell_gather_pos(int n, const float* __restrict__ pts,
+                                                           const int32_t* __restrict__ sorted_index, float4* __restrict__ sorted_pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = sorted_index[i];
+    sorted_pos[i] = make_float4(pts[3 * (int64_t)id], pts[3 * (int64_t)id + 1], pts[3 * (int64_t)id + 2], __int_as_float(id));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// radius queries: one warp per query, lanes stride over the contiguous candidate run of each (z,y) row.
+// ---------------------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_frs(GridView g, const float* __restrict__ queries, int64_t n_queries, float radius, float thr,
+                                               int ignore_query_point, const int64_t* __restrict__ row_splits, int64_t capacity,
+                                               int32_t* __restrict__ counts, int32_t* __restrict__ nbr_index,
+                                               float* __restrict__ nbr_dist, int32_t* __restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int64_t q = warp0; q < n_queries; q += n_warps) {
+        const float qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
+        const float rp = radius * 1.0001f;
+        const float px = rp + fabsf(qx) * 1e-6f, py = rp + fabsf(qy) * 1e-6f, pz = rp + fabsf(qz) * 1e-6f;
+        const int x0 = cell_coord(qx - px, g.ox, g.inv_cell, g.nx), x1 = cell_coord(qx + px, g.ox, g.inv_cell, g.nx);
+        const int y0 = cell_coord(qy - py, g.oy, g.inv_cell, g.ny), y1 = cell_coord(qy + py, g.oy, g.inv_cell, g.ny);
+        const int z0 = cell_coord(qz - pz, g.oz, g.inv_cell, g.nz), z1 = cell_coord(qz + pz, g.oz, g.inv_cell, g.nz);
+        int count = 0;
+        int64_t base = 0;
+        if (FILL) base = row_splits[q];
+        for (int z = z0; z <= z1; ++z) {
+            for (int y = y0; y <= y1; ++y) {
+                const int64_t crow = ((int64_t)z * g.ny + y) * g.nx;
+                const int s = __ldg(g.cell_start + crow + x0);
+                const int e = __ldg(g.cell_start + crow + x1 + 1);
+                for (int i0 = s; i0 < e; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool hit = false;
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float d2 = 0.f;
+                    if (i < e) {
+                        p = __ldg(g.sorted_pos + i);
+                        d2 = dist2_exact(p.x - qx, p.y - qy, p.z - qz);
+                        hit = d2 <= thr;
+                        if (ignore_query_point && p.x == qx && p.y == qy && p.z == qz) hit = false;
+                    }
+                    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+                    if (FILL) {
+                        if (hit) {
+                            const int64_t pos = base + count + __popc(ballot & lt_mask);
+                            if (pos < capacity) {
+                                nbr_index[pos] = __float_as_int(p.w);
+                                if (nbr_dist) nbr_dist[pos] = d2;
+                            } else if (overflow) {
+                                *overflow = 1;
+                            }
+                        }
+                    }
+                    count += __popc(ballot);
+                }
+            }
+        }
+        if (!FILL && lane == 0) counts[q] = count;
+    }
+}
+
+static int make_view(const dmcf_grid* grid, GridView* v) {
+    DMCF_REQUIRE(grid != nullptr, "grid is NULL");
+    DMCF_REQUIRE(grid->dims[0] > 0 && grid->dims[1] > 0 && grid->dims[2] > 0, "grid dims must be positive");
+    DMCF_REQUIRE((int64_t)grid->dims[0] * grid->dims[1] * grid->dims[2] < (int64_t)1 << 31, "grid has too many cells");
+    DMCF_REQUIRE(grid->inv_cell > 0.0f && grid->inv_cell == grid->inv_cell, "grid inv_cell must be positive");
+    DMCF_REQUIRE(grid->n_points >= 0, "grid n_points negative");
+    DMCF_REQUIRE(grid->cell_start && (grid->n_points == 0 || (grid->sorted_index && grid->sorted_pos)), "grid buffers are NULL");
+    DMCF_REQUIRE(((uintptr_t)grid->sorted_pos & 15) == 0, "grid sorted_pos must be 16-byte aligned");
+    v->ox = grid->origin[0]; v->oy = grid->origin[1]; v->oz = grid->origin[2];
+    v->inv_cell = grid->inv_cell;
+    v->nx = grid->dims[0]; v->ny = grid->dims[1]; v->nz = grid->dims[2];
+    v->n_points = grid->n_points;
+    v->cell_start = grid->cell_start;
+    v->sorted_index = grid->sorted_index;
+    v->sorted_pos = (const float4*)grid->sorted_pos;
+    return DMCF_OK;
+}
+
+}  // namespace dmcf
+
+using namespace dmcf;
+
+extern "C" size_t dmcf_scan_workspace_bytes(int64_t n) {
+    int64_t t = ceil_div(n > 0 ? n : 1, kScanTile);
+    return align_up((size_t)t * sizeof(int64_t), 256);
+}
+
+extern "C" int dmcf_exclusive_scan_i32_i64(const int32_t* in, int64_t n, int64_t* out, void* ws, size_t ws_bytes, void* stream) {
+    DMCF_REQUIRE(out && (n == 0 || in) && ws, "scan: NULL buffer");
+    return exclusive_scan<int64_t>(in, n, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dmcf_exclusive_scan_i32_i32(const int32_t* in, int64_t n, int32_t* out, void* ws, size_t ws_bytes, void* stream) {
+    DMCF_REQUIRE(out && (n == 0 || in) && ws, "scan: NULL buffer");
+    return exclusive_scan<int32_t>(in, n, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t dmcf_grid_workspace_bytes(int64_t n_points, int64_t n_cells) {
+    // cell_of[n] + cell_count[n_cells] + scan tiles
+    return align_up((size_t)(n_points > 0 ? n_points : 1) * 4, 256) + align_up((size_t)(n_cells > 0 ? n_cells : 1) * 4, 256) +
+           dmcf_scan_workspace_bytes(n_cells);
+}
+
+extern "C" int dmcf_grid_build(const float* points, dmcf_grid* grid, void* workspace, size_t workspace_bytes, void* stream) {
+    GridView g;
+    int rc = make_view(grid, &g);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = grid->n_points;
+    const int64_t n_cells = (int64_t)g.nx * g.ny * g.nz;
+    DMCF_REQUIRE(n == 0 || points, "grid_build: points is NULL");
+    DMCF_REQUIRE(workspace != nullptr, "grid_build: workspace is NULL");
+    if (workspace_bytes < dmcf_grid_workspace_bytes(n, n_cells))
+        return set_error(DMCF_ERR_WORKSPACE, "grid_build: workspace %zu < %zu", workspace_bytes, dmcf_grid_workspace_bytes(n, n_cells));
+    char* ws = (char*)workspace;
+    int32_t* cell_of = (int32_t*)ws;
+    ws += align_up((size_t)(n > 0 ? n : 1) * 4, 256);
+    int32_t* cell_count = (int32_t*)ws;
+    ws += align_up((size_t)n_cells * 4, 256);
+    void* scan_ws = ws;
+    rc = check_cuda(cudaMemsetAsync(cell_count, 0, (size_t)n_cells * 4, st), "memset cell_count");
+    if (rc) return rc;
+    if (n > 0) {
+        k_cell_hist<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g, points, cell_of, cell_count);
+        DMCF_LAUNCH_CHECK("k_cell_hist");
+    }
+    rc = exclusive_scan<int32_t>(cell_count, n_cells, grid->cell_start, scan_ws, dmcf_scan_workspace_bytes(n_cells), st);
+    if (rc) return rc;
+    if (n > 0) {
+        rc = check_cuda(cudaMemsetAsync(cell_count, 0, (size_t)n_cells * 4, st), "memset cell_fill");
+        if (rc) return rc;
+        k_cell_scatter<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, cell_of, grid->cell_start, cell_count, grid->sorted_index);
+        DMCF_LAUNCH_CHECK("k_cell_scatter");
+        k_cell_sort<<<(unsigned)ceil_div(n_cells, 256), 256, 0, st>>>(n_cells, grid->cell_start, grid->sorted_index);
+        DMCF_LAUNCH_CHECK("k_cell_sort");
+        k_cell_gather_pos<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, points, grid->sorted_index, (float4*)grid->sorted_pos);
+        DMCF_LAUNCH_CHECK("k_cell_gather_pos");
+    }
+    return DMCF_OK;
+}
+
+static unsigned frs_blocks(int64_t n_queries) {
+    int64_t want = ceil_div(n_queries, 8);  // 8 warps per block
+    int64_t cap = 148 * 32;                 // persistent-ish: a multiple of the SM count
+    return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+extern "C" int dmcf_frs_count(const dmcf_grid* grid, const float* queries, int64_t n_queries, float radius,
+                              int ignore_query_point, int32_t* counts, void* stream) {
+    GridView g;
+    int rc = make_view(grid, &g);
+    if (rc) return rc;
+    DMCF_REQUIRE(n_queries >= 0 && (n_queries == 0 || (queries && counts)), "frs_count: NULL buffer");
+    DMCF_REQUIRE(radius >= 0.0f, "frs_count: negative radius");
+    if (n_queries == 0) return DMCF_OK;
+    k_frs<false><<<frs_blocks(n_queries), 256, 0, (cudaStream_t)stream>>>(g, queries, n_queries, radius, radius * radius,
+                                                                            ignore_query_point, nullptr, 0, counts, nullptr, nullptr, nullptr);
+    DMCF_LAUNCH_CHECK("k_frs<count>");
+    return DMCF_OK;
+}
+
+extern "C" int dmcf_frs_fill(const dmcf_grid* grid, const float* queries, int64_t n_queries, float radius,
+                             int ignore_query_point, const int64_t* row_splits, int64_t capacity,
+                             int32_t* neighbors_index, float* neighbors_distance, int32_t* overflow_flag, void* stream) {
+    GridView g;
+    int rc = make_view(grid, &g);
+    if (rc) return rc;
+    DMCF_REQUIRE(n_queries >= 0 && (n_queries == 0 || (queries && row_splits)), "frs_fill: NULL buffer");
+    DMCF_REQUIRE(capacity >= 0 && (capacity == 0 || neighbors_index), "frs_fill: NULL neighbors_index");
+    if (n_queries == 0) return DMCF_OK;
+    k_frs<true><<<frs_blocks(n_queries), 256, 0, (cudaStream_t)stream>>>(g, queries, n_queries, radius, radius * radius,
+                                                                           ignore_query_point, row_splits, capacity, nullptr,
+                                                                           neighbors_index, neighbors_distance, overflow_flag);
+    DMCF_LAUNCH_CHECK("k_frs<fill>");
+    return DMCF_OK;
+}

@@ -1,0 +1,311 @@
+"""Torch-tensor front end of the C ABI (include/dmcf_b200.h): the ops DMCF reaches through ``open3d.ml.tf``.
+
+Mirrors the reference's op surface for the hot path:
+  * ``fixed_radius_search``  <- ml3d.layers.FixedRadiusSearch (utils/convolutions.py:207-210, 354-358)
+  * ``continuous_conv``      <- ml3d.ops.continuous_conv       (utils/convolutions.py:414-431)
+  * ``reduce_subarrays_sum`` <- o3dml.ops.reduce_subarrays_sum (models/pbf_model.py:450-453)
+  * ``dense``                <- tf.keras.layers.Dense           (models/pbf_model.py:140-152)
+Every function takes CUDA float32 tensors, enqueues on the current torch stream and raises on anything else:
+there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, DmcfError, Grid, check
+
+MAPPINGS = {"identity": 0, "ball_to_cube_radial": 1, "ball_to_cube_volume_preserving": 2}
+INTERPOLATIONS = {"linear": 0, "linear_border": 1, "nearest_neighbor": 2}
+WINDOWS = {None: 0, "poly6": 1, "cubic": 2, "linear": 3, "peak": 4, "cubic_grad": 5}
+
+NeighborSearchResult = namedtuple("NeighborSearchResult",
+                                  ["neighbors_index", "neighbors_row_splits", "neighbors_distance"])
+
+MAX_CELLS = 1 << 24
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _req(t, name, dtype=torch.float32, dim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise DmcfError(f"{name} must be a CUDA tensor: dmcf_b200 has no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise ValueError(f"{name} must have rank {dim}, got shape {tuple(t.shape)}")
+    return t
+
+
+def _rows(t, name):
+    """2-D tensor whose rows are contiguous; returns (tensor, row stride in elements)."""
+    _req(t, name, dim=2)
+    if t.stride(1) != 1 and t.shape[1] > 1:
+        t = t.contiguous()
+    if t.shape[0] > 1 and t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0)))
+
+
+def _pos(t, name):
+    _req(t, name, dim=2)
+    if t.shape[1] != 3:
+        raise ValueError(f"{name} must have shape [N,3], got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+class CellList:
+    """Uniform cell list over a point set (the reference's ``build_spatial_hash_table`` result)."""
+
+    def __init__(self, points, cell_size, origin=None, dims=None):
+        lib = _lib.load()
+        points = _pos(points, "points")
+        n = points.shape[0]
+        if n >= 2 ** 31:
+            raise DmcfError("too many points")
+        cell_size = float(cell_size)
+        if not cell_size > 0:
+            raise ValueError("cell_size must be positive")
+        if origin is None or dims is None:
+            if n > 0:
+                lo = points.amin(dim=0)
+                hi = points.amax(dim=0)
+                lohi = torch.stack([lo, hi]).cpu()  # one host sync per build; pass origin/dims to avoid it
+                lo, hi = lohi[0].tolist(), lohi[1].tolist()
+            else:
+                lo, hi = [0.0] * 3, [0.0] * 3
+            while True:
+                dims = [int((hi[a] - lo[a]) / cell_size) + 1 for a in range(3)]
+                if dims[0] * dims[1] * dims[2] <= MAX_CELLS:
+                    break
+                cell_size *= 1.26
+            origin = lo
+        self.points = points
+        self.cell_size = cell_size
+        self.n_cells = int(dims[0]) * int(dims[1]) * int(dims[2])
+        dev = points.device
+        self.cell_start = torch.empty(self.n_cells + 1, dtype=torch.int32, device=dev)
+        self.sorted_index = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        self.sorted_pos = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+        g = Grid()
+        g.origin[:] = [float(v) for v in origin]
+        g.inv_cell = 1.0 / cell_size
+        g.dims[:] = [int(v) for v in dims]
+        g.n_points = n
+        g.cell_start = self.cell_start.data_ptr()
+        g.sorted_index = self.sorted_index.data_ptr()
+        g.sorted_pos = self.sorted_pos.data_ptr()
+        self.grid = g
+        ws_bytes = lib.dmcf_grid_workspace_bytes(n, self.n_cells)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.dmcf_grid_build(_p(points), C.byref(g), _p(ws), ws_bytes, _stream()))
+
+
+def exclusive_scan(counts, out_dtype=torch.int64):
+    lib = _lib.load()
+    _req(counts, "counts", torch.int32, 1)
+    counts = counts.contiguous()
+    n = counts.shape[0]
+    out = torch.empty(n + 1, dtype=out_dtype, device=counts.device)
+    ws_bytes = lib.dmcf_scan_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=counts.device)
+    fn = lib.dmcf_exclusive_scan_i32_i64 if out_dtype == torch.int64 else lib.dmcf_exclusive_scan_i32_i32
+    check(fn(_p(counts), n, _p(out), _p(ws), ws_bytes, _stream()))
+    return out
+
+
+def neighbor_counts(points, queries, radius, ignore_query_point=False, cell_list=None):
+    """Per-query neighbour count (== reduce_subarrays_sum(ones, row_splits), models/pbf_model.py:450-453)."""
+    lib = _lib.load()
+    queries = _pos(queries, "queries")
+    if cell_list is None:
+        cell_list = CellList(points, max(float(radius), 1e-30))
+    counts = torch.empty(queries.shape[0], dtype=torch.int32, device=queries.device)
+    check(lib.dmcf_frs_count(C.byref(cell_list.grid), _p(queries), queries.shape[0], float(radius),
+                             int(bool(ignore_query_point)), _p(counts), _stream()))
+    return counts, cell_list
+
+
+def fixed_radius_search(points, queries, radius, ignore_query_point=False, return_distances=True, cell_list=None,
+                        metric="L2"):
+    """CSR neighbour lists within ``radius`` (L2, inclusive).  Same outputs as the reference layer:
+    neighbors_index int32 [P], neighbors_row_splits int64 [Nq+1], neighbors_distance float32 [P] (squared)."""
+    if metric != "L2":
+        raise NotImplementedError("only the L2 metric is supported (DMCF never uses another one)")
+    lib = _lib.load()
+    points = _pos(points, "points")
+    queries = _pos(queries, "queries")
+    radius = float(radius)
+    counts, cell_list = neighbor_counts(points, queries, radius, ignore_query_point, cell_list)
+    row_splits = exclusive_scan(counts, torch.int64)
+    nq = queries.shape[0]
+    total = int(row_splits[-1].item())  # data-dependent output size: the one host sync of the op
+    index = torch.empty(total, dtype=torch.int32, device=queries.device)
+    dist = torch.empty(total if return_distances else 0, dtype=torch.float32, device=queries.device)
+    if total > 0:
+        check(lib.dmcf_frs_fill(C.byref(cell_list.grid), _p(queries), nq, radius, int(bool(ignore_query_point)),
+                                _p(row_splits), total, _p(index), _p(dist) if return_distances else None, None,
+                                _stream()))
+    return NeighborSearchResult(index, row_splits, dist)
+
+
+def reduce_subarrays_sum_ones(row_splits):
+    """reduce_subarrays_sum(ones_like(index), row_splits) as used at models/pbf_model.py:450-453."""
+    return (row_splits[1:] - row_splits[:-1]).to(torch.float32)
+
+
+def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_features, inp_importance,
+                    neighbors_index, neighbors_importance, neighbors_row_splits, align_corners=True,
+                    coordinate_mapping="ball_to_cube_radial", normalize=False, interpolation="linear",
+                    max_temp_mem_MB=64, *, window=None, window_fac=1.0, relu_input=False, feat_scale=1.0,
+                    ascc=False, skip_self=False, nbr_range=None, bias=None, dense_inp=None, dense_cin=0,
+                    residual=None, out=None, accumulate=False, kernel_size=None):
+    """``ml3d.ops.continuous_conv`` (kwargs as assembled at utils/convolutions.py:414-429) plus keyword-only fused
+    extras (see include/dmcf_b200.h).  ``filters`` is [kz,ky,kx,Cin,Cout] or, with a fused Dense, the flattened
+    [(kz*ky*kx*Cin + dense_cin), Cout] matrix together with ``kernel_size``."""
+    lib = _lib.load()
+    _req(filters, "filters")
+    if filters.dim() == 5:
+        kz, ky, kx, cin, cout = filters.shape
+    else:
+        if kernel_size is None or filters.dim() != 2:
+            raise ValueError("flattened filters need kernel_size=[kz,ky,kx]")
+        kz, ky, kx = (int(v) for v in kernel_size)
+        cout = filters.shape[1]
+        cin = (filters.shape[0] - dense_cin) // (kz * ky * kx)
+        if cin * kz * ky * kx + dense_cin != filters.shape[0]:
+            raise ValueError("flattened filter rows do not match kernel_size/dense_cin")
+    filters = filters.contiguous()
+    out_positions = _pos(out_positions, "out_positions")
+    inp_positions = _pos(inp_positions, "inp_positions")
+    inp_features, inp_stride = _rows(inp_features, "inp_features")
+    if inp_features.shape[1] != cin:
+        raise ValueError(f"inp_features has {inp_features.shape[1]} channels, filter expects {cin}")
+    if inp_features.shape[0] != inp_positions.shape[0]:
+        raise ValueError("inp_features and inp_positions disagree on the number of points")
+    n_out, n_inp = out_positions.shape[0], inp_positions.shape[0]
+    ext = torch.as_tensor(extents).reshape(-1)
+    if ext.numel() != 1:
+        raise NotImplementedError("per-point extents (RadiusSearch path) are not reachable from DMCF models")
+    extent = float(ext[0])
+    _req(neighbors_index, "neighbors_index", torch.int32, 1)
+    _req(neighbors_row_splits, "neighbors_row_splits", torch.int64, 1)
+    if neighbors_row_splits.shape[0] != n_out + 1:
+        raise ValueError("neighbors_row_splits must have n_out+1 entries")
+    if inp_importance is not None and inp_importance.numel() == 0:
+        inp_importance = None
+    if neighbors_importance is not None and neighbors_importance.numel() == 0:
+        neighbors_importance = None
+    if inp_importance is not None:
+        _req(inp_importance, "inp_importance", dim=1)
+    if neighbors_importance is not None:
+        _req(neighbors_importance, "neighbors_importance", dim=1)
+        if neighbors_importance.shape[0] != neighbors_index.shape[0]:
+            raise ValueError("neighbors_importance and neighbors_index differ in length")
+    d = ConvDesc()
+    d.kernel_size[:] = [kz, ky, kx]
+    d.cin, d.cout = cin, cout
+    d.mapping = MAPPINGS[coordinate_mapping]
+    d.interpolation = INTERPOLATIONS[interpolation]
+    d.align_corners = int(bool(align_corners))
+    d.normalize = int(bool(normalize))
+    d.window = WINDOWS[window]
+    d.window_fac = float(window_fac)
+    d.extent = extent
+    off = [0.0, 0.0, 0.0] if offset is None else [float(v) for v in torch.as_tensor(offset).reshape(-1).tolist()]
+    d.offset[:] = off
+    d.relu_input = int(bool(relu_input))
+    d.feat_scale = float(feat_scale)
+    d.ascc = int(bool(ascc))
+    d.skip_self = int(bool(skip_self))
+    d.nbr_lo, d.nbr_hi = (0, 0) if nbr_range is None else (int(nbr_range[0]), int(nbr_range[1]))
+    d.dense_cin = int(dense_cin)
+    d.accumulate = int(bool(accumulate))
+    dense_stride = 0
+    if dense_cin:
+        dense_inp, dense_stride = _rows(dense_inp, "dense_inp")
+    res_stride = 0
+    if residual is not None:
+        residual, res_stride = _rows(residual, "residual")
+    if bias is not None:
+        _req(bias, "bias", dim=1)
+        bias = bias.contiguous()
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate needs an out tensor")
+        out = torch.empty((n_out, cout), dtype=torch.float32, device=out_positions.device)
+    _req(out, "out", dim=2)
+    if out.shape[0] != n_out or out.shape[1] != cout or out.stride(1) != 1:
+        raise ValueError("out has the wrong shape / layout")
+    out_stride = out.stride(0) if n_out > 1 else max(cout, out.stride(0))
+    neighbors_index = neighbors_index.contiguous()
+    neighbors_row_splits = neighbors_row_splits.contiguous()
+    check(lib.dmcf_cconv_forward(C.byref(d), _p(filters), _p(out_positions), n_out, _p(inp_positions),
+                                 _p(inp_features), inp_stride, n_inp, _p(inp_importance),
+                                 _p(neighbors_index), _p(neighbors_row_splits),
+                                 _p(neighbors_importance), _p(bias), _p(dense_inp) if dense_cin else None,
+                                 dense_stride, _p(residual), res_stride, _p(out), out_stride, _stream()))
+    return out
+
+
+def dense(x, kernel, bias=None, relu_input=False, out=None):
+    """Keras Dense (linear): g(x) @ kernel[Cin,Cout] + bias."""
+    lib = _lib.load()
+    x, xs = _rows(x, "x")
+    _req(kernel, "kernel", dim=2)
+    kernel = kernel.contiguous()
+    cin, cout = kernel.shape
+    if x.shape[1] != cin:
+        raise ValueError("x / kernel channel mismatch")
+    n = x.shape[0]
+    if out is None:
+        out = torch.empty((n, cout), dtype=torch.float32, device=x.device)
+    _req(out, "out", dim=2)
+    if out.shape[0] != n or out.shape[1] != cout or out.stride(1) != 1:
+        raise ValueError("out has the wrong shape / layout")
+    out_stride = out.stride(0) if n > 1 else max(cout, out.stride(0))
+    if bias is not None:
+        bias = _req(bias, "bias", dim=1).contiguous()
+    check(lib.dmcf_dense_forward(_p(x), n, cin, xs, _p(kernel), _p(bias), cout, int(bool(relu_input)), _p(out),
+                                 out_stride, _stream()))
+    return out
+
+
+def integrate(pos, vel, acc, gravity, dt):
+    """models/pbf_model.py:234-240."""
+    lib = _lib.load()
+    pos, vel = _pos(pos, "pos"), _pos(vel, "vel")
+    acc = None if acc is None else _pos(acc, "acc")
+    g = (C.c_float * 3)(*[float(v) for v in gravity])
+    pos2, vel2 = torch.empty_like(pos), torch.empty_like(vel)
+    check(lib.dmcf_integrate(_p(pos), _p(vel), _p(acc), g, float(dt), pos.shape[0], _p(pos2), _p(vel2), _stream()))
+    return pos2, vel2
+
+
+def correct(pos, pos2, net, out_scale, dt):
+    """models/pbf_model.py:466-487 (channel expansion, out_scale, position correction, velocity update)."""
+    lib = _lib.load()
+    pos, pos2 = _pos(pos, "pos"), _pos(pos2, "pos2")
+    net, ns = _rows(net, "net")
+    if net.shape[0] < pos.shape[0]:
+        raise ValueError("net has fewer rows than particles")
+    s = (C.c_float * 3)(*[float(v) for v in out_scale])
+    pos_new, vel_new = torch.empty_like(pos), torch.empty_like(pos)
+    check(lib.dmcf_correct(_p(pos), _p(pos2), _p(net), ns, net.shape[1], s, float(dt), pos.shape[0], _p(pos_new),
+                           _p(vel_new), _stream()))
+    return pos_new, vel_new
+
+
+def launch_count():
+    return int(_lib.load().dmcf_launch_count())

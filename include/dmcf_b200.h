@@ -1,0 +1,157 @@
+/* dmcf_b200.h -- C ABI of libdmcf_b200.so: the B200 (sm_100a) replacement for the native ops DMCF's per-step
+ * particle hot path calls through TensorFlow's custom-op ABI.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout, tum-pbs/DMCF):
+ *   - open3d.ml.tf.layers.FixedRadiusSearch -> ops build_spatial_hash_table + fixed_radius_search
+ *         constructed at utils/convolutions.py:207-210, called at utils/convolutions.py:354-358,
+ *         utils/tools/losses.py:296-298, 339-341
+ *   - open3d.ml.tf.ops.continuous_conv     called at utils/convolutions.py:431, 454, 1054 with the kwargs
+ *         assembled at utils/convolutions.py:414-429
+ *   - open3d.ml.tf.ops.reduce_subarrays_sum called at models/pbf_model.py:450-453
+ *   - tf.keras.layers.Dense (per-particle) models/pbf_model.py:140-152, models/hrnet.py:63-66
+ *   - grid_pos (tf.unique based lattice sampling) utils/tools/losses.py:136-181
+ *   - integrate / correct elementwise steps  models/pbf_model.py:234-250, 466-487
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns every buffer
+ *     (the library never allocates or frees device memory);
+ *   - every entry point takes the CUDA stream to enqueue on (a cudaStream_t passed as void*), never
+ *     synchronises the device and is CUDA-graph capturable unless stated otherwise;
+ *   - return value 0 = success; otherwise an error code, message via dmcf_last_error() (thread local);
+ *   - positions are float32 [n,3] row-major; features float32 row-major with an explicit row stride
+ *     (in floats); neighbour lists are CSR: int32 index [P], int64 row_splits [n_out+1].
+ */
+#ifndef DMCF_B200_H
+#define DMCF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMCF_B200_VERSION 100
+
+enum dmcf_status {
+    DMCF_OK = 0,
+    DMCF_ERR_INVALID = 1,   /* bad argument (the reference raises InvalidArgument from OP_REQUIRES) */
+    DMCF_ERR_UNSUPPORTED = 2,
+    DMCF_ERR_WORKSPACE = 3, /* workspace too small */
+    DMCF_ERR_CUDA = 4       /* a CUDA runtime call failed */
+};
+
+enum dmcf_mapping { DMCF_MAP_IDENTITY = 0, DMCF_MAP_BALL_TO_CUBE_RADIAL = 1, DMCF_MAP_BALL_TO_CUBE_VOLUME_PRESERVING = 2 };
+enum dmcf_interp { DMCF_INTERP_LINEAR = 0, DMCF_INTERP_LINEAR_BORDER = 1, DMCF_INTERP_NEAREST = 2 };
+/* window functions of utils/tools/losses.py:8-44 on q = d^2/r^2 */
+enum dmcf_window { DMCF_WIN_NONE = 0, DMCF_WIN_POLY6 = 1, DMCF_WIN_CUBIC = 2, DMCF_WIN_LINEAR = 3, DMCF_WIN_PEAK = 4, DMCF_WIN_CUBIC_GRAD = 5 };
+
+int dmcf_version(void);
+const char* dmcf_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches claim) */
+int64_t dmcf_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Cell list ("spatial hash table" of the reference: open3d build_spatial_hash_table).
+ * A uniform grid anchored at `origin` with cubic cells of edge 1/inv_cell and dims[] cells per axis;
+ * points outside are clamped into the border cells, so any origin/dims is *correct* (tight ones are fast).
+ * After dmcf_grid_build:  cell_start[c]..cell_start[c+1] delimit cell c (linear id (z*dims[1]+y)*dims[0]+x)
+ * in sorted_index (original point ids, ascending inside a cell => deterministic) and sorted_pos
+ * (x,y,z,bitcast(original id)) laid out cell-major for coalesced candidate reads.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dmcf_grid {
+    float origin[3];
+    float inv_cell;
+    int32_t dims[3];
+    int32_t n_points;
+    int32_t* cell_start;   /* [dims[0]*dims[1]*dims[2] + 1] */
+    int32_t* sorted_index; /* [n_points] */
+    float* sorted_pos;     /* [n_points,4], 16-byte aligned */
+} dmcf_grid;
+
+size_t dmcf_grid_workspace_bytes(int64_t n_points, int64_t n_cells);
+int dmcf_grid_build(const float* points, dmcf_grid* grid, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * fixed_radius_search (utils/convolutions.py:354-358): L2 metric, inclusive d^2 <= r*r evaluated in float32
+ * as (dx*dx + dy*dy) + dz*dz without FMA contraction; ignore_query_point drops points whose position equals
+ * the query position.  Two phases because P is data dependent:
+ *   dmcf_frs_count  -> counts[n_queries] (this IS reduce_subarrays_sum of ones, models/pbf_model.py:450-453)
+ *   dmcf_exclusive_scan_i32_i64 -> row_splits[n_queries+1]   (row_splits[n_queries] = P)
+ *   dmcf_frs_fill   -> neighbors_index[P] (original point ids), neighbors_distance[P] (squared; may be NULL)
+ * Row order: cells ascending (z,y,x), ascending point id inside a cell.
+ * ------------------------------------------------------------------------------------------------- */
+int dmcf_frs_count(const dmcf_grid* grid, const float* queries, int64_t n_queries, float radius,
+                   int ignore_query_point, int32_t* counts, void* stream);
+int dmcf_frs_fill(const dmcf_grid* grid, const float* queries, int64_t n_queries, float radius,
+                  int ignore_query_point, const int64_t* row_splits, int64_t capacity,
+                  int32_t* neighbors_index, float* neighbors_distance, int32_t* overflow_flag, void* stream);
+
+size_t dmcf_scan_workspace_bytes(int64_t n);
+/* out[0]=0, out[i]=sum(in[0..i)), out has n+1 entries */
+int dmcf_exclusive_scan_i32_i64(const int32_t* in, int64_t n, int64_t* out, void* workspace, size_t workspace_bytes, void* stream);
+int dmcf_exclusive_scan_i32_i32(const int32_t* in, int64_t n, int32_t* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * continuous_conv forward (utils/convolutions.py:414-431) with the layer glue DMCF wraps around it fused in:
+ *   out[o,:] (+)= sum_n a_n s_n W(x_n - y_o)^T g(f_n)  [/ sum_n a_n]  + [g'(c_o) Wd] + bias + residual[o,:]
+ *   g(f) = feat_scale * (relu_input ? max(f,0) : f)  (+ g(f_o) if `ascc`: the fused form of the
+ *   antisymmetric layer's second pass, utils/convolutions.py:433-458)
+ *   a_n  = neighbors_importance[n] if given, else window(d^2/r^2) (utils/convolutions.py:359-379), else 1
+ *   W(.) = trilinear lookup in `filters` [kz,ky,kx,cin,cout] after the coordinate mapping
+ *   g'(c_o) Wd = fused per-particle Dense on dense_inp (models/hrnet.py:94-96): filters then holds
+ *   (kz*ky*kx*cin + dense_cin) rows, the Dense kernel [dense_cin,cout] appended after the conv filter.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dmcf_conv_desc {
+    int32_t kernel_size[3]; /* kz, ky, kx of the EFFECTIVE filter (after antisymmetric mirroring) */
+    int32_t cin, cout;
+    int32_t mapping;        /* enum dmcf_mapping */
+    int32_t interpolation;  /* enum dmcf_interp */
+    int32_t align_corners;
+    int32_t normalize;
+    int32_t window;         /* enum dmcf_window, used only when neighbors_importance == NULL */
+    float window_fac;
+    float extent;           /* filter diameter = 2*radius (scalar extents only) */
+    float offset[3];        /* x,y,z */
+    int32_t relu_input;
+    float feat_scale;
+    int32_t ascc;           /* add the centre feature to every neighbour feature (needs out set == inp set) */
+    int32_t skip_self;      /* drop neighbours whose position equals the out position (lets one CSR that
+                               contains self serve ignore_query_point layers) */
+    int32_t nbr_lo, nbr_hi; /* keep only neighbours with nbr_lo <= index < nbr_hi; feature row = index - nbr_lo.
+                               nbr_hi <= nbr_lo means "all" */
+    int32_t dense_cin;      /* 0 = no fused Dense */
+    int32_t accumulate;     /* out += result instead of out = result */
+} dmcf_conv_desc;
+
+int dmcf_cconv_forward(const dmcf_conv_desc* desc, const float* filters,
+                       const float* out_positions, int64_t n_out,
+                       const float* inp_positions, const float* inp_features, int64_t inp_stride, int64_t n_inp,
+                       const float* inp_importance,
+                       const int32_t* neighbors_index, const int64_t* neighbors_row_splits,
+                       const float* neighbors_importance,
+                       const float* bias, const float* dense_inp, int64_t dense_stride,
+                       const float* residual, int64_t residual_stride,
+                       float* out, int64_t out_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * per-particle Dense:  out[n,:] = (relu_input ? max(x,0) : x) @ W[cin,cout] + b   (Keras layout)
+ * ------------------------------------------------------------------------------------------------- */
+int dmcf_dense_forward(const float* x, int64_t n, int32_t cin, int64_t x_stride, const float* w, const float* b,
+                       int32_t cout, int32_t relu_input, float* out, int64_t out_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * elementwise step pieces (models/pbf_model.py:234-250, 466-487)
+ *   integrate: vel2 = vel + dt*acc (acc == NULL -> gravity vector), pos2 = pos + dt*vel2
+ *   correct:   pos' = pos2 + out_scale * net[:, map(c)];  vel' = (pos' - pos)/dt     net has net_c in {1,2,3}
+ *              channels (1 -> repeated, 2 -> [a,b,a], models/pbf_model.py:466-469)
+ * ------------------------------------------------------------------------------------------------- */
+int dmcf_integrate(const float* pos, const float* vel, const float* acc, const float* gravity_host3, float dt,
+                   int64_t n, float* pos2, float* vel2, void* stream);
+int dmcf_correct(const float* pos, const float* pos2, const float* net, int64_t net_stride, int32_t net_c,
+                 const float* out_scale_host3, float dt, int64_t n, float* pos_new, float* vel_new, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMCF_B200_H */

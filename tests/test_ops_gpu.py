@@ -1,0 +1,274 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the O64 oracle on identical seeded inputs.
+
+Bars: neighbour rows bit-exact after a per-row sort (indices AND squared distances);
+features within 2e-5*max|ref| + 1e-6 of the float64 oracle.
+"""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import o64
+
+pytestmark = pytest.mark.gpu
+
+RTOL_MAX, ATOL = 2e-5, 1e-6
+
+
+def feat_close(got, ref, scale=1.0):
+    ref = np.asarray(ref, np.float64)
+    got = np.asarray(got, np.float64)
+    tol = scale * (RTOL_MAX * max(np.abs(ref).max(initial=0.0), 1e-30) + ATOL)
+    err = np.abs(got - ref).max(initial=0.0)
+    assert err <= tol, f"max err {err:.3e} > tol {tol:.3e} (max|ref| {np.abs(ref).max(initial=0.0):.3e})"
+
+
+def sorted_rows(index, splits, dist=None):
+    index = np.asarray(index)
+    splits = np.asarray(splits)
+    rows = np.repeat(np.arange(len(splits) - 1), np.diff(splits))
+    order = np.lexsort((index, rows))
+    return index[order], (None if dist is None else np.asarray(dist)[order])
+
+
+def clouds():
+    rng = np.random.default_rng(7)
+    lattice = np.stack(np.meshgrid(*[np.arange(12) * 0.05] * 3, indexing="ij"), -1).reshape(-1, 3)
+    yield "uniform3d", rng.random((4000, 3)).astype(np.float32), 0.1
+    yield "jitter_lattice", (lattice + rng.uniform(-0.01, 0.01, lattice.shape)).astype(np.float32), 0.1
+    yield "exact_lattice_ties", lattice.astype(np.float32), 0.1  # neighbours at exactly 2 spacings (float ties)
+    p2 = rng.random((3000, 3)).astype(np.float32); p2[:, 2] = 0
+    yield "planar2d", p2, 0.04
+    p1 = np.zeros((500, 3), np.float32); p1[:, 1] = np.sort(rng.random(500)) * 2
+    yield "column1d", p1, 0.02
+    dup = rng.random((300, 3)).astype(np.float32)
+    yield "duplicates", np.concatenate([dup, dup[:100]]), 0.15
+    yield "single", np.array([[0.3, 0.2, 0.1]], np.float32), 0.5
+    far = rng.random((1000, 3)).astype(np.float32) * np.array([100, 1, 1], np.float32) + 1000.0
+    yield "large_coords", far.astype(np.float32), 0.3
+
+
+@pytest.mark.parametrize("name,pts,radius", list(clouds()), ids=[c[0] for c in clouds()])
+@pytest.mark.parametrize("ignore", [False, True])
+def test_fixed_radius_search_bit_exact(cuda, name, pts, radius, ignore):
+    from dmcf_b200 import ops
+    t = torch.from_numpy(pts).to(cuda)
+    res = ops.fixed_radius_search(t, t, radius, ignore_query_point=ignore, return_distances=True)
+    ri, rs, rd = o64.fixed_radius_search(pts, pts, radius, ignore_query_point=ignore)
+    gi, gs, gd = res.neighbors_index.cpu().numpy(), res.neighbors_row_splits.cpu().numpy(), res.neighbors_distance.cpu().numpy()
+    assert gi.dtype == np.int32 and gs.dtype == np.int64 and gd.dtype == np.float32
+    assert np.array_equal(gs, rs)
+    a_i, a_d = sorted_rows(gi, gs, gd)
+    b_i, b_d = sorted_rows(ri, rs, rd)
+    assert np.array_equal(a_i, b_i)
+    assert np.array_equal(a_d, b_d)  # squared distances bit-exact
+
+
+def test_fixed_radius_search_distinct_sets_and_empty(cuda):
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(3)
+    pts = rng.random((2500, 3)).astype(np.float32)
+    qs = (rng.random((700, 3)) * 1.4 - 0.2).astype(np.float32)  # some queries outside the cell grid
+    res = ops.fixed_radius_search(torch.from_numpy(pts).to(cuda), torch.from_numpy(qs).to(cuda), 0.08)
+    ri, rs, rd = o64.fixed_radius_search(pts, qs, 0.08)
+    assert np.array_equal(res.neighbors_row_splits.cpu().numpy(), rs)
+    a_i, a_d = sorted_rows(res.neighbors_index.cpu().numpy(), rs, res.neighbors_distance.cpu().numpy())
+    b_i, b_d = sorted_rows(ri, rs, rd)
+    assert np.array_equal(a_i, b_i) and np.array_equal(a_d, b_d)
+    # empty point set / empty query set
+    e = torch.zeros((0, 3), device=cuda)
+    r0 = ops.fixed_radius_search(e, torch.from_numpy(qs).to(cuda), 0.1)
+    assert r0.neighbors_index.numel() == 0 and int(r0.neighbors_row_splits.abs().sum()) == 0
+    r1 = ops.fixed_radius_search(torch.from_numpy(pts).to(cuda), e, 0.1)
+    assert r1.neighbors_row_splits.shape[0] == 1 and r1.neighbors_index.numel() == 0
+    # deterministic row order: two builds give identical arrays
+    t = torch.from_numpy(pts).to(cuda)
+    x = ops.fixed_radius_search(t, t, 0.1)
+    y = ops.fixed_radius_search(t, t, 0.1)
+    assert torch.equal(x.neighbors_index, y.neighbors_index)
+
+
+def test_neighbor_counts_is_reduce_subarrays_sum(cuda):
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(5)
+    pts = rng.random((3000, 3)).astype(np.float32)
+    t = torch.from_numpy(pts).to(cuda)
+    counts, _ = ops.neighbor_counts(t, t, 0.09)
+    _, rs, _ = o64.fixed_radius_search(pts, pts, 0.09)
+    assert np.array_equal(counts.cpu().numpy(), np.diff(rs).astype(np.int32))
+
+
+def test_exclusive_scan_large(cuda):
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 5, 2048, 2049, 100_000, 3_000_001):
+        a = rng.integers(0, 2000, n).astype(np.int32)
+        out = ops.exclusive_scan(torch.from_numpy(a).to(cuda), torch.int64).cpu().numpy()
+        ref = np.concatenate([[0], np.cumsum(a.astype(np.int64))])
+        assert np.array_equal(out, ref), n
+
+
+CONV_CASES = [
+    # name, kernel_size, cin, cout, mapping, interp, align, normalize, window, ignore_q
+    ("wide444", (4, 4, 4), 32, 32, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False),
+    ("inp444", (4, 4, 4), 4, 8, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False),
+    ("c24", (4, 4, 4), 24, 32, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False),
+    ("k188", (1, 8, 8), 7, 8, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False),
+    ("k181", (1, 8, 1), 8, 16, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", True),
+    ("radial_norm", (3, 3, 3), 5, 6, "ball_to_cube_radial", "linear", True, True, None, False),
+    ("radial_norm_win", (3, 3, 3), 5, 6, "ball_to_cube_radial", "linear", True, True, "cubic", False),
+    ("identity_noalign", (4, 3, 2), 3, 2, "identity", "linear", False, False, "linear", False),
+    ("border", (3, 3, 3), 4, 4, "ball_to_cube_radial", "linear_border", False, False, "peak", True),
+    ("nearest", (3, 3, 3), 4, 4, "ball_to_cube_volume_preserving", "nearest_neighbor", True, False, None, False),
+    ("cout64", (4, 4, 4), 16, 64, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", True),
+    ("cin96", (4, 4, 4), 96, 64, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", True),
+    ("cout3", (6, 6, 6), 32, 3, "ball_to_cube_volume_preserving", "linear", True, False, "peak", True),
+    ("sampling111", (1, 1, 1), 3, 3, "ball_to_cube_radial", "linear", True, True, "poly6", False),
+    ("cubic_grad", (2, 2, 2), 2, 1, "ball_to_cube_radial", "linear", True, False, "cubic_grad", False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("fused_window", [False, True])
+def test_continuous_conv_matches_oracle(cuda, case, fused_window):
+    from dmcf_b200 import ops
+    name, ks, cin, cout, mapping, interp, align, normalize, window, ignore_q = case
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    n_in, n_out = 900, 700
+    pts = rng.random((n_in, 3)).astype(np.float32)
+    if ks[0] == 1:
+        pts[:, 2] = 0
+    if ks[2] == 1:
+        pts[:, 0] = 0
+    outp = pts[:n_out].copy()
+    outp[n_out // 2:] += rng.normal(0, 0.01, (n_out - n_out // 2, 3)).astype(np.float32) * (pts[:1] * 0 + (np.array(ks[::-1]) > 1))
+    outp = outp.astype(np.float32)
+    feats = rng.standard_normal((n_in, cin)).astype(np.float32)
+    filt = rng.uniform(-0.5, 0.5, ks + (cin, cout)).astype(np.float32)
+    extent = np.float32(0.25)
+    radius = np.float32(0.5) * extent
+    idx, splits, d2 = o64.fixed_radius_search(pts, outp, radius, ignore_query_point=ignore_q)
+    imp = None
+    if window is not None:
+        imp = o64.window(window, d2.astype(np.float64) / (np.float64(radius) ** 2))
+    ref = o64.continuous_conv(filt, outp, extent, (0, 0, 0), pts, feats, None, idx, imp, splits, align_corners=align,
+                              coordinate_mapping=mapping, normalize=normalize, interpolation=interp)
+    dev = cuda
+    t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    kw = dict(align_corners=align, coordinate_mapping=mapping, normalize=normalize, interpolation=interp)
+    if fused_window or window is None:
+        got = ops.continuous_conv(t(filt), t(outp), float(extent), None, t(pts), t(feats), None, t(idx), None, t(splits),
+                                  window=window, **kw)
+    else:
+        got = ops.continuous_conv(t(filt), t(outp), float(extent), None, t(pts), t(feats), None, t(idx),
+                                  t(imp.astype(np.float32)), t(splits), **kw)
+    scale = 4.0 if cin * np.prod(ks) > 4096 else 1.0  # very long float32 dot products (cin96: K = 6144)
+    feat_close(got.cpu().numpy(), ref, scale)
+
+
+def test_continuous_conv_fused_extras(cuda):
+    """relu on the input, feature scale, neighbour sub-range, skip-self on a self-containing CSR, fused Dense,
+    bias, residual, accumulate, strided in/out rows."""
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(11)
+    n, cin, cout, ks = 800, 24, 32, (4, 4, 4)
+    pts = rng.random((n, 3)).astype(np.float32)
+    feats_wide = rng.standard_normal((n, cin + 5)).astype(np.float32)
+    feats = feats_wide[:, 2:2 + cin]
+    filt = rng.uniform(-0.3, 0.3, ks + (cin, cout)).astype(np.float32)
+    dk = rng.uniform(-0.3, 0.3, (cin, cout)).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    resid = rng.standard_normal((n, cout)).astype(np.float32)
+    extent = np.float32(0.3)
+    radius = np.float32(0.5) * extent
+    idx, splits, d2 = o64.fixed_radius_search(pts, pts, radius, ignore_query_point=False)  # contains self
+    lo, hi = 100, 650
+    # reference: relu, scale, ignore self, only neighbours in [lo,hi)
+    keep = (idx >= lo) & (idx < hi) & ~np.all(pts[idx] == np.repeat(pts, np.diff(splits), axis=0), axis=1)
+    rows = np.repeat(np.arange(n), np.diff(splits))[keep]
+    k_idx = idx[keep]
+    k_splits = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int64)
+    imp = o64.window("poly6", d2[keep].astype(np.float64) / np.float64(radius) ** 2)
+    g = np.maximum(feats, 0) * 0.5
+    ref = o64.continuous_conv(filt, pts, extent, (0, 0, 0), pts, g, None, k_idx, imp, k_splits, align_corners=True,
+                              coordinate_mapping="ball_to_cube_volume_preserving", normalize=False, interpolation="linear")
+    ref = ref + np.maximum(feats, 0).astype(np.float64) @ dk + bias + resid
+    prev = rng.standard_normal((n, cout)).astype(np.float32)
+    ref_acc = ref + prev
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    fw = t(feats_wide)
+    w_ext = torch.cat([t(filt).reshape(-1, cout), t(dk)], dim=0)
+    out_wide = torch.zeros((n, cout + 7), device=cuda)
+    out_view = out_wide[:, 3:3 + cout]
+    out_view.copy_(t(prev))
+    # neighbour sub-range: features/positions of the sub-range are passed as their own arrays (row = index - lo)
+    ops.continuous_conv(w_ext, t(pts), float(extent), None, t(pts[lo:hi]), fw[lo:hi, 2:2 + cin], None, t(idx), None, t(splits),
+                        align_corners=True, coordinate_mapping="ball_to_cube_volume_preserving", normalize=False,
+                        interpolation="linear", window="poly6", relu_input=True, feat_scale=0.5, skip_self=True,
+                        nbr_range=(lo, hi), bias=t(bias), dense_inp=fw[:, 2:2 + cin], dense_cin=cin, residual=t(resid),
+                        out=out_view, accumulate=True, kernel_size=ks)
+    feat_close(out_view.cpu().numpy(), ref_acc)
+    assert float(out_wide[:, :3].abs().sum()) == 0 and float(out_wide[:, 3 + cout:].abs().sum()) == 0
+
+
+def test_ascc_fused_matches_reference_form_and_conserves(cuda):
+    """Antisymmetric layer: fused (f_j + f_i) kernel vs the reference's two-pass form (utils/convolutions.py:433-458)
+    and momentum conservation sum_i out_i = 0."""
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(13)
+    n, cin, cout = 1500, 32, 3
+    pts = rng.random((n, 3)).astype(np.float32) * 0.6
+    feats = rng.standard_normal((n, cin)).astype(np.float32)
+    half = rng.uniform(-0.5, 0.5, (6, 3, 6, cin, cout)).astype(np.float32)
+    extent = np.float32(0.2)
+    ref = o64.cconv_layer(np.maximum(feats, 0), pts, pts, extent, half, None, align_corners=True,
+                          coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear", normalize=False,
+                          ignore_query_points=True, window_name="peak", symmetric=True, sym_axis=1)
+    full = o64.symmetric_kernel(half, 1).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    nns = ops.fixed_radius_search(t(pts), t(pts), float(np.float32(0.5) * extent), ignore_query_point=True)
+    got = ops.continuous_conv(t(full), t(pts), float(extent), None, t(pts), t(feats), None, nns.neighbors_index, None,
+                              nns.neighbors_row_splits, align_corners=True,
+                              coordinate_mapping="ball_to_cube_volume_preserving", normalize=False, interpolation="linear",
+                              window="peak", relu_input=True, ascc=True).cpu().numpy().astype(np.float64)
+    feat_close(got, ref)
+    total = np.abs(got).sum(axis=0)
+    assert np.all(np.abs(got.sum(axis=0)) <= 1e-5 * total + 1e-5), (got.sum(axis=0), total)
+
+
+def test_dense_and_elementwise(cuda):
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(17)
+    for n, cin, cout in [(1000, 7, 8), (513, 32, 32), (77, 96, 64), (1, 4, 8), (0, 4, 8)]:
+        x = rng.standard_normal((n, cin)).astype(np.float32)
+        w = rng.standard_normal((cin, cout)).astype(np.float32)
+        b = rng.standard_normal(cout).astype(np.float32)
+        t = lambda a: torch.from_numpy(a).to(cuda)
+        got = ops.dense(t(x), t(w), t(b), relu_input=True).cpu().numpy()
+        feat_close(got, o64.dense(np.maximum(x, 0), w, b))
+    n = 1234
+    pos = rng.random((n, 3)).astype(np.float32); vel = rng.standard_normal((n, 3)).astype(np.float32)
+    acc = rng.standard_normal((n, 3)).astype(np.float32)
+    dt = np.float32(0.02)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    p2, v2 = ops.integrate(t(pos), t(vel), t(acc), (0, -9.81, 0), float(dt))
+    v_ref = vel + dt * acc
+    p_ref = pos + dt * v_ref
+    assert np.allclose(v2.cpu().numpy(), v_ref, rtol=1e-6, atol=1e-7) and np.allclose(p2.cpu().numpy(), p_ref, rtol=1e-6, atol=1e-7)
+    p2g, v2g = ops.integrate(t(pos), t(vel), None, (0, -9.81, 0), float(dt))
+    assert np.allclose(v2g.cpu().numpy(), vel + dt * np.array([0, -9.81, 0], np.float32), rtol=1e-6, atol=1e-7)
+    for c in (1, 2, 3):
+        net = rng.standard_normal((n + 50, c)).astype(np.float32)
+        pn, vn = ops.correct(t(pos), p2, t(net), (0.5, 0.25, 0.125), float(dt))
+        e = np.repeat(net, 3, axis=1) if c == 1 else (np.concatenate([net, net[:, :1]], 1) if c == 2 else net)
+        pr = p2.cpu().numpy() + np.array([0.5, 0.25, 0.125], np.float32) * e[:n]
+        assert np.allclose(pn.cpu().numpy(), pr, rtol=1e-6, atol=1e-7)
+        assert np.allclose(vn.cpu().numpy(), (pr - pos) / dt, rtol=1e-5, atol=1e-5)
+
+
+def test_no_cpu_fallback(cuda):
+    from dmcf_b200 import ops
+    from dmcf_b200._lib import DmcfError
+    with pytest.raises(DmcfError):
+        ops.fixed_radius_search(torch.zeros((4, 3)), torch.zeros((4, 3)), 0.1)
