@@ -49,6 +49,10 @@ SIGNATURES = {
                                    c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "dmcf_dense_forward": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "dmcf_integrate": (c_i32, [c_vp, c_vp, c_vp, C.POINTER(c_f32), c_f32, c_i64, c_vp, c_vp, c_vp]),
+    "dmcf_grid_pos_mark": (c_i32, [c_vp, c_i64, C.POINTER(c_f32), C.POINTER(c_f32), c_f32, C.POINTER(c_i32),
+                                   C.POINTER(c_i32), c_vp, c_vp]),
+    "dmcf_grid_pos_emit": (c_i32, [c_vp, c_vp, C.POINTER(c_f32), C.POINTER(c_f32), C.POINTER(c_i32), C.POINTER(c_i32),
+                                   c_vp, c_vp]),
     "dmcf_correct": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_i64, c_vp, c_vp, c_vp]),
 }
 

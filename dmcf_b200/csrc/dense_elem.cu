@@ -40,9 +40,10 @@ __global__ void __launch_bounds__(256) k_integrate(const float* __restrict__ pos
     if (i >= n3) return;
     const int c = (int)(i % 3);
     const float a = acc ? acc[i] : (c == 0 ? gx : (c == 1 ? gy : gz));
-    const float v2 = vel[i] + dt * a;  // models/pbf_model.py:237-238
+    // separately rounded multiply / add like the reference's elementwise TF ops (no FMA contraction)
+    const float v2 = __fadd_rn(vel[i], __fmul_rn(dt, a));  // models/pbf_model.py:237-238
     vel2[i] = v2;
-    pos2[i] = pos[i] + dt * v2;  // :239
+    pos2[i] = __fadd_rn(pos[i], __fmul_rn(dt, v2));  // :239
 }
 
 __global__ void __launch_bounds__(256) k_correct(const float* __restrict__ pos, const float* __restrict__ pos2,
@@ -56,9 +57,9 @@ __global__ void __launch_bounds__(256) k_correct(const float* __restrict__ pos, 
     // channel expansion of models/pbf_model.py:466-469: 1 -> repeat, 2 -> [a, b, a]
     const int src = (net_c == 1) ? 0 : ((net_c == 2 && c == 2) ? 0 : c);
     const float s = c == 0 ? sx : (c == 1 ? sy : sz);
-    const float pn = pos2[i] + s * net[r * net_stride + src];  // :474, :248
+    const float pn = __fadd_rn(pos2[i], __fmul_rn(s, net[r * net_stride + src]));  // :474, :248
     pos_new[i] = pn;
-    vel_new[i] = (pn - pos[i]) / dt;  // :249
+    vel_new[i] = __fdiv_rn(__fsub_rn(pn, pos[i]), dt);  // :249
 }
 
 }  // namespace dmcf

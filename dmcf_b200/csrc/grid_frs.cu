@@ -285,6 +285,76 @@ __global__ void __launch_bounds__(256) k_frs(GridView g, const float* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// grid_pos (utils/tools/losses.py:136-181)
+// ---------------------------------------------------------------------------------------------------------
+struct LatticeParams {
+    float vx, vy, vz;     // voxel pitch
+    float cx, cy, cz;     // centre (0 when not centralised)
+    float hx, hy, hz;     // hysteresis per axis (0 on inactive axes)
+    int ax, ay, az;       // axis active (voxel >= 1e-5)
+    int lox, loy, loz, dx, dy, dz;
+    int centralize;
+};
+
+__device__ __forceinline__ int lattice_coord(float p, float c, float v, float h) {
+    // floor(pos / max(v,1e-5) -/+ hyst) in float32, each operation rounded (utils/tools/losses.py:142-150)
+    const float vm = fmaxf(v, 1e-5f);
+    return (int)floorf(__fadd_rn(__fdiv_rn(__fsub_rn(p, c), vm), h));
+}
+
+__global__ void __launch_bounds__(256) k_grid_pos_mark(const float* __restrict__ pos, int64_t n, LatticeParams L,
+                                                         int32_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        const float s = sgn ? 1.0f : -1.0f;
+        const int bx = lattice_coord(px, L.cx, L.vx, s * L.hx) - L.lox;
+        const int by = lattice_coord(py, L.cy, L.vy, s * L.hy) - L.loy;
+        const int bz = lattice_coord(pz, L.cz, L.vz, s * L.hz) - L.loz;
+        for (int oz = 0; oz <= L.az; ++oz)
+            for (int oy = 0; oy <= L.ay; ++oy)
+                for (int ox = 0; ox <= L.ax; ++ox) {
+                    const int x = bx + ox, y = by + oy, z = bz + oz;
+                    if (x >= 0 && x < L.dx && y >= 0 && y < L.dy && z >= 0 && z < L.dz)
+                        flags[((int64_t)z * L.dy + y) * L.dx + x] = 1;
+                }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_grid_pos_emit(const int32_t* __restrict__ flags, const int32_t* __restrict__ offsets,
+                                                         int64_t n_cells, LatticeParams L, float* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells || !flags[c]) return;
+    const int x = (int)(c % L.dx) + L.lox;
+    const int y = (int)((c / L.dx) % L.dy) + L.loy;
+    const int z = (int)(c / ((int64_t)L.dx * L.dy)) + L.loz;
+    const int64_t o = offsets[c];
+    // gpos * voxel + (center | voxel/2), multiply and add rounded separately (:176-179)
+    const float ax = L.centralize ? L.cx : L.vx / 2.0f;
+    const float ay = L.centralize ? L.cy : L.vy / 2.0f;
+    const float az = L.centralize ? L.cz : L.vz / 2.0f;
+    out[3 * o] = __fadd_rn(__fmul_rn((float)x, L.vx), ax);
+    out[3 * o + 1] = __fadd_rn(__fmul_rn((float)y, L.vy), ay);
+    out[3 * o + 2] = __fadd_rn(__fmul_rn((float)z, L.vz), az);
+}
+
+static int make_lattice(const float* v, const float* c, float hyst, const int32_t* lo, const int32_t* dims, LatticeParams* L) {
+    DMCF_REQUIRE(v && lo && dims, "grid_pos: NULL parameter");
+    DMCF_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "grid_pos: dims must be positive");
+    DMCF_REQUIRE((int64_t)dims[0] * dims[1] * dims[2] < ((int64_t)1 << 31), "grid_pos: lattice too large");
+    L->vx = v[0]; L->vy = v[1]; L->vz = v[2];
+    L->centralize = c != nullptr;
+    L->cx = c ? c[0] : 0.f; L->cy = c ? c[1] : 0.f; L->cz = c ? c[2] : 0.f;
+    L->ax = v[0] >= 1e-5f; L->ay = v[1] >= 1e-5f; L->az = v[2] >= 1e-5f;
+    L->hx = L->ax ? hyst : 0.f; L->hy = L->ay ? hyst : 0.f; L->hz = L->az ? hyst : 0.f;
+    L->lox = lo[0]; L->loy = lo[1]; L->loz = lo[2];
+    L->dx = dims[0]; L->dy = dims[1]; L->dz = dims[2];
+    return DMCF_OK;
+}
+
 static int make_view(const dmcf_grid* grid, GridView* v) {
     DMCF_REQUIRE(grid != nullptr, "grid is NULL");
     DMCF_REQUIRE(grid->dims[0] > 0 && grid->dims[1] > 0 && grid->dims[2] > 0, "grid dims must be positive");
@@ -399,5 +469,29 @@ extern "C" int dmcf_frs_fill(const dmcf_grid* grid, const float* queries, int64_
                                                                            ignore_query_point, row_splits, capacity, nullptr,
                                                                            neighbors_index, neighbors_distance, overflow_flag);
     DMCF_LAUNCH_CHECK("k_frs<fill>");
+    return DMCF_OK;
+}
+
+extern "C" int dmcf_grid_pos_mark(const float* pos, int64_t n, const float* voxel, const float* center, float hyst,
+                                  const int32_t* lo, const int32_t* dims, int32_t* flags, void* stream) {
+    LatticeParams L;
+    int rc = make_lattice(voxel, center, hyst, lo, dims, &L);
+    if (rc) return rc;
+    DMCF_REQUIRE(n >= 0 && flags && (n == 0 || pos), "grid_pos_mark: NULL buffer");
+    if (n == 0) return DMCF_OK;
+    k_grid_pos_mark<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, n, L, flags);
+    DMCF_LAUNCH_CHECK("k_grid_pos_mark");
+    return DMCF_OK;
+}
+
+extern "C" int dmcf_grid_pos_emit(const int32_t* flags, const int32_t* offsets, const float* voxel, const float* center,
+                                  const int32_t* lo, const int32_t* dims, float* out, void* stream) {
+    LatticeParams L;
+    int rc = make_lattice(voxel, center, 0.f, lo, dims, &L);
+    if (rc) return rc;
+    DMCF_REQUIRE(flags && offsets && out, "grid_pos_emit: NULL buffer");
+    const int64_t n_cells = (int64_t)L.dx * L.dy * L.dz;
+    k_grid_pos_emit<<<(unsigned)ceil_div(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(flags, offsets, n_cells, L, out);
+    DMCF_LAUNCH_CHECK("k_grid_pos_emit");
     return DMCF_OK;
 }

@@ -1,0 +1,99 @@
+"""Host-side mirror of the hot-path pieces of the reference's ``utils/tools/losses.py``:
+``get_window_func`` (:8-44), ``grid_pos`` (:136-181), ``get_dilated_pos`` (:249-284), ``compute_density`` (:287-308).
+Training losses / EMD / chamfer of that file are out of scope."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+_TYPES = ("poly6", "cubic", "linear", "peak", "cubic_grad")
+
+
+class WindowFunction:
+    """Callable radial window on q = d^2/r^2 (torch tensors).  Carries ``typ``/``fac`` so ContinuousConv can
+    evaluate it inside the CUDA kernel instead of materialising a per-pair importance array."""
+
+    def __init__(self, typ, fac=1.0):
+        if typ not in _TYPES:
+            raise NotImplementedError(typ)
+        self.typ = typ
+        self.fac = float(fac)
+
+    def __call__(self, q):
+        fac, typ = self.fac, self.typ
+        if typ == "poly6":
+            return fac * torch.clamp((1 - q) ** 3, 0, 1)
+        qs = torch.sqrt(q)
+        if typ == "cubic":
+            return fac * 4 / 3 * torch.where(q <= 1, torch.where(qs <= 0.5, 6 * (qs ** 3 - q) + 1, 2 * (1 - qs) ** 3),
+                                             torch.zeros_like(qs))
+        if typ == "linear":
+            return fac * (1 - qs)
+        if typ == "peak":
+            return fac * (1 - 2 * qs + q)
+        return fac * 4 / 3 * torch.where(q <= 1, torch.where(qs <= 0.5, 18 * q - 12 * qs, -6 * (1 - qs) ** 2),
+                                         torch.zeros_like(qs))
+
+
+def get_window_func(typ, fac=1.0, **kwargs):
+    """utils/tools/losses.py:8-44: returns None for ``typ is None``."""
+    if typ is None:
+        return None
+    return WindowFunction(typ, fac)
+
+
+def point_mean(pos):
+    """Mean position used by ``centralize`` (utils/tools/losses.py:137-139).  Accumulated in float64 and rounded
+    once so that every implementation in this repo (CUDA, oracles, slab ranks) gets bit-identical lattices."""
+    return pos.to(torch.float64).mean(dim=0).to(torch.float32)
+
+
+def grid_pos(pos, voxel_size, centralize=False, pad=0, hyst=0.1, center=None):
+    """Lattice points (cell pitch ``voxel_size``) touched by any particle, utils/tools/losses.py:136-181.
+    Output order is ascending linear voxel id (the reference's first-occurrence order is an internal detail,
+    SURVEY A.6)."""
+    if pad != 0:
+        raise NotImplementedError("sample_pad != 0 is not used by any shipped config")
+    v = [float(x) for x in torch.as_tensor(voxel_size, dtype=torch.float32).reshape(3).tolist()]
+    if centralize and center is None:
+        center = point_mean(pos)
+    return ops.grid_pos(pos, v, center if centralize else None, float(hyst))
+
+
+def get_dilated_pos(pos, strides, voxel_size=None, centralize=False, pad=0, hyst=0.1):
+    """utils/tools/losses.py:249-284 (voxel mode).  Returns (positions per scale, counts per scale, idx) like the
+    reference; ``idx`` is unused in voxel mode."""
+    dilated, pcnt, idx = [], [], []
+    center = None
+    for stride in strides:
+        if stride == 1:
+            dilated.append(pos)
+            pcnt.append(pos.shape[0])
+            idx.append(None)
+        else:
+            if voxel_size is None:
+                raise NotImplementedError("farthest-point sub-sampling (voxel_size: null) is out of scope (SURVEY 8f)")
+            if centralize and center is None:
+                center = point_mean(pos)
+            vs = torch.as_tensor(voxel_size, dtype=torch.float32).reshape(3) * float(stride)
+            dilated.append(grid_pos(pos, vs, centralize, pad, hyst, center))
+            pcnt.append(dilated[-1].shape[0])
+    return dilated, pcnt, idx
+
+
+def compute_density(out_pos, in_pos=None, radius=0.005, win=None):
+    """utils/tools/losses.py:287-308: sum over neighbours of win(d^2/r^2)."""
+    if in_pos is None:
+        in_pos = out_pos
+    if win is None:
+        win = lambda x: x  # noqa: E731  (the reference warns and uses the identity)
+    nns = ops.fixed_radius_search(in_pos, out_pos, radius, return_distances=True)
+    r = torch.tensor(float(radius), dtype=torch.float32, device=out_pos.device)
+    w = win(nns.neighbors_distance / (r * r))
+    csum = torch.zeros(w.shape[0] + 1, dtype=torch.float64, device=out_pos.device)
+    csum[1:] = torch.cumsum(w.to(torch.float64), 0)
+    rs = nns.neighbors_row_splits
+    return (csum[rs[1:]] - csum[rs[:-1]]).to(torch.float32)

@@ -1,0 +1,742 @@
+"""PBFNet / HRNet / SymNet / CConv with the reference's constructor kwargs and dataflow
+(models/base_model.py, models/pbf_model.py, models/hrnet.py, models/sym_net.py, models/cconv.py), on torch CUDA
+tensors and the sm_100a kernels.  Inference only.
+
+Two execution modes produce the same numbers (tests assert it):
+  * ``fused=False``: every layer is called on its own exactly like the reference does (one neighbour search per
+    conv, separate Dense / relu / add): the readable statement of the dataflow;
+  * ``fused=True`` (default): what the rollout runs.  Per step: particles are put in cell order for locality, one
+    neighbour list per distinct (input set, output set, radius) is built and shared by every conv that needs it,
+    relu / window / Dense / bias / residual / add-merge / the antisymmetric centre term ride inside the conv kernel,
+    and the two input convs + two input Dense layers collapse into one conv over zero-padded features.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .convolutions import ContinuousConv, PointSampling, _init
+from .losses import get_dilated_pos, get_window_func
+
+__all__ = ["BaseModel", "PBFNet", "HRNet", "SymNet", "CConv", "Dense", "align_vector"]
+
+
+class Dense(torch.nn.Module):
+    """tf.keras.layers.Dense(units, activation=None): x @ kernel[Cin,Cout] + bias, built lazily."""
+
+    def __init__(self, units, name=None, activation=None):
+        super().__init__()
+        assert activation is None
+        self.units = int(units)
+        self.layer_name = name
+        self.kernel = None
+        self.bias = None
+
+    def build(self, in_channels, device, generator=None):
+        self.kernel = torch.nn.Parameter(_init("glorot_uniform", (int(in_channels), self.units), device,
+                                               generator=generator), requires_grad=False)
+        self.bias = torch.nn.Parameter(torch.zeros(self.units, device=device), requires_grad=False)
+
+    def forward(self, x, relu_input=False):
+        if self.kernel is None:
+            self.build(x.shape[-1], x.device)
+        return ops.dense(x, self.kernel, self.bias, relu_input=relu_input)
+
+
+def align_vector(v0, v1):
+    """Rotation taking v0 onto v1 (models/pbf_model.py:12-28); 3x3 float32 tensor on v1's device."""
+    v0n = v0 / (torch.linalg.norm(v0) + 1e-9)
+    v1n = v1 / (torch.linalg.norm(v1) + 1e-9)
+    v = torch.linalg.cross(v0n, v1n)
+    c = torch.dot(v0n, v1n)
+    s = torch.linalg.norm(v)
+    eye = torch.eye(3, device=v1.device, dtype=v1.dtype)
+    if float(s) < 1e-6:
+        return eye * (-1.0 if float(c) < 0 else 1.0)
+    z = torch.zeros((), device=v1.device, dtype=v1.dtype)
+    vx = torch.stack([torch.stack([z, -v[2], v[1]]), torch.stack([v[2], z, -v[0]]), torch.stack([-v[1], v[0], z])])
+    return eye + vx + (vx @ vx) / (1 + c)
+
+
+class BaseModel(torch.nn.Module):
+    """models/base_model.py:10-29: call = transform -> preprocess -> forward -> postprocess -> inv_transform."""
+
+    def __init__(self, name, **kwargs):
+        super().__init__()
+        self.model_name = name
+        self.cfg = dict(kwargs)
+
+    @property
+    def name(self):
+        return self.model_name
+
+    def __call__(self, data, training=False, **kwargs):
+        return self.call(data, training=training, **kwargs)
+
+    def call(self, data, training=False, **kwargs):
+        d = self.transform(data, training=training, **kwargs)
+        x = self.preprocess(d, training=training, **kwargs)
+        x = self.forward(x, d, training=training, **kwargs)
+        x = self.postprocess(x, d, training=training, **kwargs)
+        x = self.inv_transform(x, data, training=training, **kwargs)
+        return x
+
+
+class _StepCache:
+    """Per-step neighbour lists shared between convs (the reference rebuilds one per conv call)."""
+
+    def __init__(self):
+        self.cells = {}
+        self.nns = {}
+
+    def search(self, key, inp_pos, out_pos, radius):
+        k = (key, float(radius))
+        if k not in self.nns:
+            ck = (key[0], float(radius))
+            if ck not in self.cells:
+                self.cells[ck] = ops.CellList(inp_pos, float(radius))
+            self.nns[k] = ops.fixed_radius_search(inp_pos, out_pos, radius, ignore_query_point=False,
+                                                  return_distances=False, cell_list=self.cells[ck])
+        return self.nns[k]
+
+
+class PBFNet(BaseModel):
+    """models/pbf_model.py:31-489."""
+
+    def __init__(self, name="PBFNet", kernel_size=[4, 4, 4], channels=16, strides=[1], particle_radii=[0.05],
+                 coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear", window=None,
+                 window_dens=None, ignore_query_points=False, grav=-9.81, transformation={}, loss=None, timestep=0.01,
+                 dens_radius=None, circular=False, dens_feats=False, pres_feats=False, equivar=False, use_vel=True,
+                 use_acc=True, use_feats=False, use_box_feats=True, use_pre_adv=False, use_bnds=True, dens_norm=False,
+                 rest_dens=3.5, stiffness=20.0, voxel_size=None, centralize=False, out_scale=[0.01, 0.01, 0.01],
+                 sample_pad=0, sample_hyst=0.1, part_scale=1.0, fused=True, **kwargs):
+        super().__init__(name=name, **kwargs)
+        for flag, val in (("dens_feats", dens_feats), ("pres_feats", pres_feats), ("equivar", equivar),
+                          ("use_pre_adv", use_pre_adv), ("dens_norm", dens_norm), ("use_feats", use_feats)):
+            if val:
+                raise NotImplementedError(f"{flag}=True is disabled in every shipped config and not implemented "
+                                          "(SURVEY 8 a16)")
+        self.kernel_size = list(kernel_size)
+        self.channel = channels
+        self.strides = list(strides)
+        self.particle_radii = [float(r) for r in particle_radii]
+        self.coordinate_mapping = coordinate_mapping
+        self.interpolation = interpolation
+        self.window = window
+        self.window_dens = window_dens
+        self.ignore_query_points = ignore_query_points
+        self.voxel_size = None if voxel_size is None else [float(v) for v in voxel_size]
+        self.centralize = centralize
+        self.circular = circular
+        self.transformation = dict(transformation or {})
+        self.sample_pad = sample_pad
+        self.sample_hyst = sample_hyst
+        self.out_scale = [float(v) for v in out_scale]
+        self.use_vel, self.use_acc, self.use_box_feats, self.use_bnds = use_vel, use_acc, use_box_feats, use_bnds
+        self.timestep = float(timestep)
+        self.grav = float(grav)
+        self.part_scale = float(part_scale)
+        self.rest_dens, self.stiffness = rest_dens, stiffness
+        self.dens_radius = dens_radius if dens_radius is not None else particle_radii
+        self.fused = fused
+        self.num_fluid_neighbors = None
+        self._all_convs = []
+        self._box_cache = None
+        self._wcache = {}
+        self.fluid_convs = self.get_cconv(name="fluid_obs", filters=channels, window_func=self.window, circular=circular)
+        self.fluid_dense = Dense(channels, name="fluid_dense")
+        self.obs_convs = self.get_cconv(name="obs_conv", filters=channels, window_func=self.window, circular=circular)
+        self.obs_dense = Dense(channels, name="obs_dense")
+        self.setup()
+        self._convs_ml = torch.nn.ModuleList([c for _, c in self._all_convs])
+
+    def setup(self):
+        return
+
+    # -- layer factory: models/pbf_model.py:197-224 --------------------------------------------------------
+    def get_cconv(self, name, kernel_size=None, activation=None, ignore_query_points=None, window_func=None,
+                  normalize=False, **kwargs):
+        if kernel_size is None:
+            kernel_size = self.kernel_size
+        if ignore_query_points is None:
+            ignore_query_points = self.ignore_query_points
+        conv = ContinuousConv(name=name, kernel_size=kernel_size, activation=activation, align_corners=True,
+                              interpolation=self.interpolation, coordinate_mapping=self.coordinate_mapping,
+                              normalize=normalize, window_function=get_window_func(window_func),
+                              radius_search_ignore_query_points=ignore_query_points, use_dense_layer_for_center=False,
+                              **kwargs)
+        self._all_convs.append((name, conv))
+        return conv
+
+    # -- physics: models/pbf_model.py:234-250 -----------------------------------------------------------------
+    def integrate_pos_vel(self, pos1, vel1, acc1=None):
+        return ops.integrate(pos1, vel1, acc1, (0.0, self.grav, 0.0), self.timestep)
+
+    def compute_new_pos_vel(self, pos1, vel1, pos2, vel2, pos_correction):
+        pos = pos2 + pos_correction
+        return pos, (pos - pos1) / self.timestep
+
+    # -- transform / inv_transform: models/pbf_model.py:252-301 -----------------------------------------------
+    def transform(self, data, training=False, **kwargs):
+        pos, vel, acc, feats, box, bfeats = data
+        dev = pos.device
+        tr = self.transformation
+        if "translate" in tr:
+            t = torch.tensor(tr["translate"], dtype=torch.float32, device=dev)
+            pos, box = pos + t, box + t
+        if "scale" in tr:
+            s = torch.tensor(tr["scale"], dtype=torch.float32, device=dev)
+            pos, box, vel = pos * s, box * s, vel * s
+            if acc is not None:
+                acc = acc * s
+        if "grav_eqvar" in tr:
+            g = torch.tensor(tr["grav_eqvar"], dtype=torch.float32, device=dev)
+            self.R = align_vector(g, acc[0])
+            pos, vel, acc, box, bfeats = pos @ self.R, vel @ self.R, acc @ self.R, box @ self.R, bfeats @ self.R
+        return [pos, vel, acc, feats, box, bfeats]
+
+    def inv_transform(self, prev, data, training=False, **kwargs):
+        pos, vel = prev
+        dev = pos.device
+        tr = self.transformation
+        if "grav_eqvar" in tr:
+            Rt = self.R.t()
+            pos, vel = pos @ Rt, vel @ Rt
+        if "scale" in tr:
+            s = torch.clamp(torch.tensor(tr["scale"], dtype=torch.float32, device=dev), min=1e-5)
+            pos, vel = pos / s, vel / s
+        if "translate" in tr:
+            pos = pos - torch.tensor(tr["translate"], dtype=torch.float32, device=dev)
+        return pos, vel
+
+    # -- full step ------------------------------------------------------------------------------------------
+    def call(self, data, training=False, **kwargs):
+        if training:
+            raise NotImplementedError("training is out of scope (SURVEY 8f rank 1)")
+        data = list(data)
+        if len(data) != 6:
+            raise ValueError("data must be [pos, vel, acc, feats, box, box_normals]")
+        perm = None
+        if self.fused and data[0].shape[0] > 0:
+            # cell order for locality; undone on the outputs.  Not part of the reference semantics.
+            cl = ops.CellList(data[0], self.particle_radii[0])
+            perm = cl.sorted_index[: data[0].shape[0]].long()
+            data[0], data[1] = data[0][perm], data[1][perm]
+            if data[2] is not None:
+                data[2] = data[2][perm]
+            data[4], data[5] = self._sorted_box(data[4], data[5])
+        pos, vel = super().call(data, training=training, **kwargs)
+        if perm is not None:
+            pos_o, vel_o = torch.empty_like(pos), torch.empty_like(vel)
+            pos_o[perm], vel_o[perm] = pos, vel
+            pos, vel = pos_o, vel_o
+        return pos, vel
+
+    def _sorted_box(self, box, bfeats):
+        """The boundary is static over a rollout: put it in cell order once and reuse."""
+        key = (box.data_ptr(), bfeats.data_ptr(), box.shape[0], box._version, bfeats._version)
+        if self._box_cache is None or self._box_cache[0] != key:
+            if box.shape[0] > 0:
+                perm = ops.CellList(box, self.particle_radii[0]).sorted_index[: box.shape[0]].long()
+                self._box_cache = (key, box[perm].contiguous(), bfeats[perm].contiguous(), box, bfeats)
+            else:
+                self._box_cache = (key, box, bfeats, box, bfeats)
+        return self._box_cache[1], self._box_cache[2]
+
+    # -- preprocess: models/pbf_model.py:303-438 ----------------------------------------------------------------
+    def preprocess(self, data, training=False, **kwargs):
+        _pos, _vel, acc, feats, box, bfeats = data
+        pos, vel = self.integrate_pos_vel(_pos, _vel, acc)
+        filter_extent = [np.float32(r) * np.float32(2) for r in self.particle_radii]
+        e_last = float(filter_extent[-1])
+        if pos.shape[0] > 0:
+            lo, hi = pos.amin(dim=0) - e_last, pos.amax(dim=0) + e_last
+            fltr = ((box >= lo) & (box <= hi)).all(dim=1)
+            box, bfeats = box[fltr], bfeats[fltr]
+        n_f, n_b = pos.shape[0], box.shape[0]
+        fluid_feats = [torch.ones_like(pos[:, :1])]
+        if self.use_vel:
+            fluid_feats.append(vel)
+        if self.use_acc:
+            if acc is None:
+                raise ValueError("use_acc=True needs the per-particle acceleration (data[2])")
+            fluid_feats.append(acc)
+        box_feats = [torch.ones_like(box[:, :1])]
+        if self.use_box_feats:
+            box_feats.append(bfeats)
+        fluid_feats = torch.cat(fluid_feats, dim=-1)
+        box_feats = torch.cat(box_feats, dim=-1)
+        all_pos = torch.cat([pos, box], dim=0)
+        self.all_pos = all_pos
+        self.inp_feats, self.inp_bfeats = fluid_feats, box_feats
+        self._n_fluid = n_f
+        self._step = _StepCache()
+        ext0 = float(filter_extent[0])
+        ch = self.channel
+        if not self.fused:
+            ans_conv = self.fluid_convs(fluid_feats * self.part_scale, pos, all_pos, ext0, None)  # :378
+            ans_dense = self.fluid_dense(fluid_feats)
+            ans_obs = self.obs_convs(box_feats * self.part_scale, box, all_pos, ext0, None)  # :382
+            ans_dense_obs = self.obs_dense(box_feats)
+            feats_out = torch.cat([ans_conv, ans_obs, torch.cat([ans_dense, ans_dense_obs], dim=0)], dim=-1)  # :411
+        else:
+            cf, cb = fluid_feats.shape[1], box_feats.shape[1]
+            self._ensure_built_inputs(cf, cb, pos.device)
+            x = torch.zeros((n_f + n_b, cf + cb), dtype=torch.float32, device=pos.device)
+            x[:n_f, :cf] = fluid_feats
+            x[n_f:, cf:] = box_feats
+            w, b = self._input_weights(cf, cb)
+            nns = self._step.search((0, 0), all_pos, all_pos, 0.5 * ext0)
+            win = self.fluid_convs.window_function
+            feats_out = ops.continuous_conv(
+                w, all_pos, ext0, None, all_pos, x, None, nns.neighbors_index, None, nns.neighbors_row_splits,
+                align_corners=True, coordinate_mapping=self.coordinate_mapping, normalize=False,
+                interpolation=self.interpolation, window=win.typ if win else None, window_fac=win.fac if win else 1.0,
+                feat_scale=self.part_scale, skip_self=self.ignore_query_points, bias=b, dense_inp=x,
+                dense_cin=cf + cb, kernel_size=self.kernel_size)
+        src = all_pos if self.use_bnds else pos
+        dilated_pos, _, idx = get_dilated_pos(src, self.strides, voxel_size=self.voxel_size,
+                                              centralize=self.centralize, pad=self.sample_pad, hyst=self.sample_hyst)
+        self.dilated_pos = dilated_pos
+        return [dilated_pos, feats_out, idx, None]
+
+    def _ensure_built_inputs(self, cf, cb, device):
+        if self.fluid_convs.kernel is None:
+            self.fluid_convs.build(cf, device)
+        if self.obs_convs.kernel is None:
+            self.obs_convs.build(cb, device)
+        if self.fluid_dense.kernel is None:
+            self.fluid_dense.build(cf, device)
+        if self.obs_dense.kernel is None:
+            self.obs_dense.build(cb, device)
+
+    def _input_weights(self, cf, cb):
+        """One filter for [fluid conv | obstacle conv | fluid/obstacle Dense] over zero-padded [fluid|box] features.
+        Dense biases ride on the constant-one feature channels (0 and cf)."""
+        layers = (self.fluid_convs.kernel, self.obs_convs.kernel, self.fluid_dense.kernel, self.obs_dense.kernel,
+                  self.fluid_convs.bias, self.obs_convs.bias, self.fluid_dense.bias, self.obs_dense.bias)
+        key = tuple((t.data_ptr(), t._version) for t in layers)
+        hit = self._wcache.get("input")
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        ch = self.channel
+        kf, ko = self.fluid_convs.effective_kernel(), self.obs_convs.effective_kernel()
+        cells = kf.shape[0] * kf.shape[1] * kf.shape[2]
+        dev = kf.device
+        w = torch.zeros((cells, cf + cb, 3 * ch), device=dev)
+        w[:, :cf, :ch] = kf.reshape(cells, cf, ch)
+        w[:, cf:, ch:2 * ch] = ko.reshape(cells, cb, ch)
+        wd = torch.zeros((cf + cb, 3 * ch), device=dev)
+        wd[:cf, 2 * ch:] = self.fluid_dense.kernel
+        wd[cf:, 2 * ch:] = self.obs_dense.kernel
+        wd[0, 2 * ch:] += self.fluid_dense.bias
+        wd[cf, 2 * ch:] += self.obs_dense.bias
+        b = torch.zeros(3 * ch, device=dev)
+        b[:ch] = self.fluid_convs.bias
+        b[ch:2 * ch] = self.obs_convs.bias
+        w_ext = torch.cat([w.reshape(-1, 3 * ch), wd], dim=0).contiguous()
+        self._wcache["input"] = (key, w_ext, b)
+        return w_ext, b
+
+    def _block_weights(self, conv, dense):
+        """Flattened conv filter with the Dense kernel appended, and the summed bias."""
+        ts = [conv.kernel] + ([conv.bias] if conv.bias is not None else []) + ([dense.kernel, dense.bias] if dense else [])
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        ck = (id(conv), id(dense))
+        hit = self._wcache.get(ck)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        k = conv.effective_kernel()
+        w = k.reshape(-1, k.shape[-1])
+        b = conv.bias
+        if dense is not None:
+            w = torch.cat([w, dense.kernel], dim=0)
+            b = dense.bias if b is None else b + dense.bias
+        w = w.contiguous()
+        self._wcache[ck] = (key, w, b)
+        return w, b
+
+    def conv_block(self, conv, dense, x, inp_pos, out_pos, extent, key, *, relu=True, scale=1.0, same_set=False,
+                   residual=None, out=None, accumulate=False, ascc=False):
+        """relu -> conv (+ Dense on the same relu'd features) (+ residual), the unit models/hrnet.py:81-99 and
+        models/cconv.py:60-67 repeat; fused into one kernel launch."""
+        if conv.kernel is None:
+            conv.build(x.shape[1], x.device)
+        if dense is not None and dense.kernel is None:
+            dense.build(x.shape[1], x.device)
+        w, b = self._block_weights(conv, dense)
+        nns = self._step.search(key, inp_pos, out_pos, 0.5 * float(extent))
+        win = conv.window_function
+        return ops.continuous_conv(
+            w, out_pos, float(extent), None, inp_pos, x, None, nns.neighbors_index, None, nns.neighbors_row_splits,
+            align_corners=True, coordinate_mapping=self.coordinate_mapping, normalize=False,
+            interpolation=self.interpolation, window=win.typ if win else None, window_fac=win.fac if win else 1.0,
+            relu_input=relu, feat_scale=scale, ascc=ascc,
+            skip_self=bool(conv.radius_search_ignore_query_points and same_set), bias=b,
+            dense_inp=x if dense is not None else None, dense_cin=x.shape[1] if dense is not None else 0,
+            residual=residual, out=out, accumulate=accumulate, kernel_size=conv.kernel_size)
+
+    # -- postprocess: models/pbf_model.py:440-489 -----------------------------------------------------------------
+    def postprocess(self, prev, data, training=False, **kwargs):
+        pos, vel, acc = data[:3]
+        pcnt = pos.shape[0]
+        out = prev
+        self.net_out = out
+        pos2, vel2 = self.integrate_pos_vel(pos, vel, acc)
+        scale = self.out_scale
+        pos_new, vel_new = ops.correct(pos, pos2, out, scale, self.timestep)
+        return [pos_new, vel_new]
+
+    @property
+    def pos_correction(self):
+        out = self.net_out
+        if out.shape[-1] == 1:
+            out = out.repeat(1, 3)
+        elif out.shape[-1] == 2:
+            out = torch.cat([out, out[:, :1]], dim=-1)
+        return torch.tensor(self.out_scale, device=out.device) * out[: self._n_fluid]
+
+    def fluid_neighbor_counts(self):
+        """num_fluid_neighbors of models/pbf_model.py:450-453 (training-loss input), computed on demand."""
+        n_f = self._n_fluid
+        counts, _ = ops.neighbor_counts(self.all_pos[:n_f], self.all_pos, self.particle_radii[0],
+                                        ignore_query_point=self.ignore_query_points)
+        return counts[:n_f].to(torch.float32)
+
+    # -- weights --------------------------------------------------------------------------------------------
+    def named_layers(self):
+        """{checkpoint-style name: layer}."""
+        out = {"fluid_convs": self.fluid_convs, "obs_convs": self.obs_convs, "fluid_dense": self.fluid_dense,
+               "obs_dense": self.obs_dense}
+        for n, (_, conv) in enumerate(self._all_convs):
+            if n >= 2:
+                out["_all_convs/%d" % n] = conv
+        return out
+
+    def load_weights(self, weights, device="cuda"):
+        """Assigns ``{name/kernel|bias: array}`` (see ``dmcf_b200.checkpoint.model_weights``); names follow the TF
+        object graph of the shipped checkpoints, '/1' of '_all_convs/<n>/1' being optional."""
+        weights = {k.replace("/1/", "/") if k.startswith("_all_convs/") else k: v for k, v in weights.items()}
+        missing = []
+        for name, layer in self.named_layers().items():
+            aliases = [name] + list(getattr(layer, "_aliases", []))
+            found = next((a for a in aliases if a + "/kernel" in weights), None)
+            if found is None:
+                missing.append(name)
+                continue
+            k = torch.as_tensor(np.asarray(weights[found + "/kernel"]), dtype=torch.float32).to(device)
+            layer.kernel = torch.nn.Parameter(k.contiguous(), requires_grad=False)
+            has_bias = found + "/bias" in weights
+            if isinstance(layer, ContinuousConv):
+                layer.in_channels = k.shape[-2]
+                if tuple(k.shape) != tuple(layer.kernel_shape(k.shape[-2])):
+                    raise ValueError(f"{name}: checkpoint kernel {tuple(k.shape)} does not match the layer "
+                                     f"{layer.kernel_shape(k.shape[-2])}")
+                layer._eff_cache = None
+                if layer.use_bias != has_bias:
+                    raise ValueError(f"{name}: bias presence differs between checkpoint and layer")
+            if has_bias:
+                layer.bias = torch.nn.Parameter(
+                    torch.as_tensor(np.asarray(weights[found + "/bias"]), dtype=torch.float32).to(device),
+                    requires_grad=False)
+        self._wcache = {}
+        return missing
+
+    def init_weights(self, seed=0, device="cuda", scale=None):
+        """Random weights of the architecture's shapes (no checkpoint): Keras defaults, or uniform(-scale, scale)."""
+        gen = torch.Generator().manual_seed(seed)
+        for name, layer, cin in self.layer_shapes():
+            if isinstance(layer, ContinuousConv):
+                layer.build(cin, device, generator=gen)
+                if scale is not None:
+                    layer.kernel.data = ((torch.rand(layer.kernel.shape, generator=gen) * 2 - 1) * scale).to(device)
+                if layer.bias is not None and scale is not None:
+                    layer.bias.data = ((torch.rand(layer.bias.shape, generator=gen) * 2 - 1) * scale).to(device)
+            else:
+                layer.build(cin, device, generator=gen)
+                if scale is not None:
+                    layer.bias.data = ((torch.rand(layer.bias.shape, generator=gen) * 2 - 1) * scale).to(device)
+        self._wcache = {}
+
+    def input_channels(self):
+        cf = 1 + (3 if self.use_vel else 0) + (3 if self.use_acc else 0)
+        cb = 1 + (3 if self.use_box_feats else 0)
+        return cf, cb
+
+    def layer_shapes(self):
+        """[(name, layer, in_channels)] for every layer that gets weights (what lazy building would produce)."""
+        cf, cb = self.input_channels()
+        return [("fluid_convs", self.fluid_convs, cf), ("obs_convs", self.obs_convs, cb),
+                ("fluid_dense", self.fluid_dense, cf), ("obs_dense", self.obs_dense, cb)]
+
+    def state_arrays(self):
+        """{name/kernel|bias: ndarray} of every built layer (the oracle consumes this)."""
+        out = {}
+        for name, layer in self.named_layers().items():
+            if layer.kernel is not None:
+                out[name + "/kernel"] = layer.kernel.detach().cpu().numpy()
+                if layer.bias is not None:
+                    out[name + "/bias"] = layer.bias.detach().cpu().numpy()
+        return out
+
+
+class HRNet(PBFNet):
+    """models/hrnet.py:12-133 (multi-scale conv stack)."""
+
+    def __init__(self, name="HRNet", layer_channels=[[16], [32], [32], [3]], window=None, window_dens=None,
+                 circular=False, add_merge=False, out_activation=None, **kwargs):
+        self.layer_channels = layer_channels
+        self.add_merge = add_merge
+        if out_activation == "tanh":
+            self.out_activation = torch.tanh
+        elif out_activation is None:
+            self.out_activation = None
+        else:
+            raise NotImplementedError()
+        torch.nn.Module.__init__(self)
+        super().__init__(name=name, channels=layer_channels[0][0][0], window=window, window_dens=window_dens,
+                         circular=circular, **kwargs)
+
+    def setup(self):  # models/hrnet.py:39-67
+        self.convs, self.denses = [], []
+        lc = self.layer_channels
+        for i in range(1, len(lc)):
+            self.denses.append([])
+            self.convs.append([])
+            for j in range(len(lc[i])):
+                self.convs[-1].append([])
+                self.denses[-1].append([])
+                for k in range(len(lc[i][j])):
+                    ch = lc[i][j][k]
+                    self.convs[-1][-1].append([])
+                    self.denses[-1][-1].append([])
+                    for l in range(len(lc[i - 1]) if k == 0 else 1):
+                        conv = self.get_cconv(name="conv{0}{1}{2}_{3}".format(i, j, k, l), filters=ch,
+                                              window_func=self.window,
+                                              ignore_query_points=self.ignore_query_points and (j == l or k > 0),
+                                              circular=self.circular)
+                        conv._aliases = ["convs/%d/%d/%d/%d" % (i - 1, j, k, l)]
+                        self.convs[-1][-1][-1].append(conv)
+                        self.denses[-1][-1][-1].append(Dense(ch, name="dense{0}{1}{2}_{3}".format(i, j, k, l)))
+        self._dense_ml = torch.nn.ModuleList([d for a in self.denses for b in a for c in b for d in c])
+
+    def named_layers(self):
+        out = super().named_layers()
+        for i, a in enumerate(self.denses):
+            for j, b in enumerate(a):
+                for k, c in enumerate(b):
+                    for l, d in enumerate(c):
+                        if self._dense_used(i, j, k, l):
+                            out["denses/%d/%d/%d/%d" % (i, j, k, l)] = d
+        return out
+
+    def _dense_used(self, i, j, k, l):
+        return k > 0 or j == l  # voxel mode: only the diagonal Dense layers ever run (models/hrnet.py:94-99)
+
+    def _scale_channels(self):
+        """Channel count of ans_convs[layer][scale] for every layer (index 0 = the preprocess output)."""
+        lc = self.layer_channels
+        chans = [[3 * self.channel]]
+        for i in range(1, len(lc)):
+            cur = []
+            for j in range(len(lc[i])):
+                c = lc[i][j][0] if self.add_merge else lc[i][j][0] * len(lc[i - 1])
+                if len(lc[i][j]) > 1:
+                    c = lc[i][j][-1]
+                cur.append(c)
+            chans.append(cur)
+        return chans
+
+    def layer_shapes(self):
+        out = super().layer_shapes()
+        lc = self.layer_channels
+        chans = self._scale_channels()
+        for i in range(1, len(lc)):
+            for j in range(len(lc[i])):
+                for k in range(len(lc[i][j])):
+                    for l in range(len(lc[i - 1]) if k == 0 else 1):
+                        if k == 0:
+                            cin = chans[i - 1][l]
+                        elif k == 1:
+                            cin = lc[i][j][0] if self.add_merge else lc[i][j][0] * len(lc[i - 1])
+                        else:
+                            cin = lc[i][j][k - 1]
+                        out.append(("conv", self.convs[i - 1][j][k][l], cin))
+                        if self._dense_used(i - 1, j, k, l):
+                            out.append(("dense", self.denses[i - 1][j][k][l], cin))
+        return out
+
+    def forward(self, prev, data, training=False, **kwargs):  # models/hrnet.py:69-133
+        pos, feats, idx, dens = prev
+        if not self.use_bnds:
+            feats = feats[: pos[0].shape[0]]
+        filter_extent = [float(np.float32(r) * np.float32(2)) for r in self.particle_radii]
+        ans_convs = [[feats]]
+        for layer in range(len(self.convs)):
+            ans = []
+            for scale in range(len(self.convs[layer])):
+                importance = self.part_scale if scale == 0 else 1.0
+                n_inp = len(ans_convs[-1])
+                ext = filter_extent[scale]
+                if self.fused:
+                    cw = self.convs[layer][scale][0][0].filters
+                    buf = torch.empty((pos[scale].shape[0], cw if self.add_merge else cw * n_inp),
+                                      dtype=torch.float32, device=feats.device)
+                    for inp_scale in range(n_inp):
+                        x = ans_convs[-1][inp_scale]
+                        ext = filter_extent[max(inp_scale, scale)]
+                        same = scale == inp_scale
+                        res = ans_convs[-1][scale] if same and cw == ans_convs[-1][scale].shape[-1] else None
+                        o = buf if self.add_merge else buf[:, inp_scale * cw:(inp_scale + 1) * cw]
+                        self.conv_block(self.convs[layer][scale][0][inp_scale],
+                                        self.denses[layer][scale][0][inp_scale] if same else None, x, pos[inp_scale],
+                                        pos[scale], ext, (inp_scale, scale), relu=True, scale=importance,
+                                        same_set=same, residual=res, out=o,
+                                        accumulate=self.add_merge and inp_scale > 0)
+                    ans.append(buf)
+                else:
+                    inp = []
+                    for inp_scale in range(n_inp):
+                        f = torch.relu(ans_convs[-1][inp_scale])
+                        ext = filter_extent[max(inp_scale, scale)]
+                        a = self.convs[layer][scale][0][inp_scale](f * importance, pos[inp_scale], pos[scale], ext, None)
+                        if scale == inp_scale:
+                            a = a + self.denses[layer][scale][0][inp_scale](f)
+                            if a.shape[-1] == ans_convs[-1][scale].shape[-1]:
+                                a = a + ans_convs[-1][scale]
+                        inp.append(a)
+                    if self.add_merge:
+                        s = inp[0]
+                        for a in inp[1:]:
+                            s = s + a
+                        ans.append(s)
+                    else:
+                        ans.append(torch.cat(inp, dim=-1))
+                for i in range(1, len(self.convs[layer][scale])):  # extra k>0 convs on the same scale (:120-129)
+                    x = ans[-1]
+                    res = None
+                    if len(ans_convs[-1]) > scale and self.convs[layer][scale][i][0].filters == ans_convs[-1][scale].shape[-1]:
+                        res = ans_convs[-1][scale]
+                    if self.fused:
+                        ans[-1] = self.conv_block(self.convs[layer][scale][i][0], self.denses[layer][scale][i][0], x,
+                                                  pos[scale], pos[scale], ext, (scale, scale), relu=False,
+                                                  scale=importance, same_set=True, residual=res)
+                    else:
+                        a = self.convs[layer][scale][i][0](x * importance, pos[scale], pos[scale], ext, None)
+                        a = a + self.denses[layer][scale][i][0](x)
+                        ans[-1] = a + res if res is not None else a
+            ans_convs.append(ans)
+        out = ans_convs[-1][0]
+        return self.out_activation(out) if self.out_activation is not None else out
+
+
+class SymNet(HRNet):
+    """models/sym_net.py:12-69: HRNet followed by antisymmetric (momentum conserving) ContinuousConv layer(s)."""
+
+    def __init__(self, name="SymNet", layer_channels=[[[16]], [[32]], [[32]], [[3]]], sym_kernel_size=[6, 6, 6],
+                 sym_axis=2, window_sym=None, out_activation=None, **kwargs):
+        self.sym_kernel_size = list(sym_kernel_size)
+        self.sym_axis = sym_axis
+        self.window_sym = window_sym
+        self.sym_channels = layer_channels[-1][-1]
+        if out_activation == "tanh":
+            self.act = torch.tanh
+        elif out_activation is None:
+            self.act = None
+        else:
+            raise NotImplementedError()
+        super().__init__(name=name, layer_channels=layer_channels[:-1], out_activation=None, **kwargs)
+
+    def setup(self):  # models/sym_net.py:39-53
+        super().setup()
+        self.sym_convs = []
+        for i, ch in enumerate(self.sym_channels):
+            conv = self.get_cconv(name="sym_conv{0}".format(i), filters=ch, use_bias=False, symmetric=True,
+                                  kernel_size=self.sym_kernel_size, ignore_query_points=True,
+                                  window_func=self.window_sym, sym_axis=self.sym_axis, circular=self.circular)
+            conv._aliases = ["sym_convs/%d" % i]
+            self.sym_convs.append(conv)
+
+    def layer_shapes(self):
+        out = super().layer_shapes()
+        cin = self._scale_channels()[-1][0]
+        for conv in self.sym_convs:
+            out.append(("sym", conv, cin))
+            cin = conv.filters
+        return out
+
+    def forward(self, prev, data, training=False, **kwargs):  # models/sym_net.py:55-69
+        pos, feats, idx, dens = prev
+        ans = super().forward(prev, data, training, **kwargs)
+        if not self.use_bnds:
+            ans = torch.cat([ans, feats[pos[0].shape[0]:]], dim=0)
+        ext = float(np.float32(self.particle_radii[0]) * np.float32(2))
+        for conv in self.sym_convs:
+            if self.fused:
+                ans = self.conv_block(conv, None, ans, self.all_pos, self.all_pos, ext, (0, 0) if self.use_bnds else ("all", "all"),
+                                      relu=True, scale=self.part_scale, same_set=True, ascc=True)
+            else:
+                ans = conv(torch.relu(ans) * self.part_scale, self.all_pos, self.all_pos, ext, None)
+        return self.act(ans) if self.act is not None else ans
+
+
+class CConv(PBFNet):
+    """models/cconv.py:12-69 (single-scale baseline of Ummenhofer et al.)."""
+
+    def __init__(self, name="CConv", layer_channels=[32, 64, 64, 3], window=None, out_activation=None, **kwargs):
+        self.layer_channels = layer_channels
+        if out_activation == "tanh":
+            self.out_activation = torch.tanh
+        elif out_activation is None:
+            self.out_activation = None
+        else:
+            raise NotImplementedError()
+        torch.nn.Module.__init__(self)
+        super().__init__(name=name, channels=layer_channels[0], window=window, **kwargs)
+
+    def setup(self):  # models/cconv.py:33-48
+        self.convs, self.denses = [], []
+        for i in range(1, len(self.layer_channels)):
+            ch = self.layer_channels[i]
+            conv = self.get_cconv(name="conv{0}".format(i), filters=ch, window_func=self.window,
+                                  ignore_query_points=self.ignore_query_points, circular=self.circular)
+            conv._aliases = ["convs/%d" % (i - 1)]
+            self.convs.append(conv)
+            self.denses.append(Dense(ch, name="dense{0}".format(i)))
+        self._dense_ml = torch.nn.ModuleList(self.denses)
+
+    def named_layers(self):
+        out = super().named_layers()
+        for i, d in enumerate(self.denses):
+            out["denses/%d" % i] = d
+        return out
+
+    def layer_shapes(self):
+        out = super().layer_shapes()
+        cin = 3 * self.channel
+        for conv, dense in zip(self.convs, self.denses):
+            out.append(("conv", conv, cin))
+            out.append(("dense", dense, cin))
+            cin = conv.filters
+        return out
+
+    def forward(self, prev, data, training=False, **kwargs):  # models/cconv.py:50-69
+        pos, feats = prev[:2]
+        pos = pos[0]
+        feats = feats[: pos.shape[0]]
+        ext = float(np.float32(self.particle_radii[0]) * np.float32(2))
+        ans = feats
+        key = (0, 0) if self.use_bnds else ("fluid", "fluid")
+        for conv, dense in zip(self.convs, self.denses):
+            if self.fused:
+                res = ans if conv.filters == ans.shape[-1] else None
+                ans = self.conv_block(conv, dense, ans, pos, pos, ext, key, relu=True, scale=1.0, same_set=True,
+                                      residual=res)
+            else:
+                f = torch.relu(ans)
+                a = conv(f, pos, pos, ext, None) + dense(f)
+                ans = a + ans if a.shape[-1] == ans.shape[-1] else a
+        return self.out_activation(ans) if self.out_activation is not None else ans

@@ -307,5 +307,44 @@ def correct(pos, pos2, net, out_scale, dt):
     return pos_new, vel_new
 
 
+def grid_pos(pos, voxel, center=None, hyst=0.1):
+    """Lattice sampling of utils/tools/losses.py:136-181 (``center`` is None when not centralised)."""
+    import numpy as np
+    lib = _lib.load()
+    pos = _pos(pos, "pos")
+    n = pos.shape[0]
+    if n == 0:
+        return torch.empty((0, 3), dtype=torch.float32, device=pos.device)
+    f32 = np.float32
+    v = np.asarray(voxel, f32).reshape(3)
+    stats = [pos.amin(dim=0), pos.amax(dim=0)]
+    if center is not None:
+        stats.append(_req(center, "center", dim=1))
+    stats = torch.stack(stats).cpu().numpy().astype(f32)  # one host sync (output size is data dependent anyway)
+    c = stats[2] if center is not None else np.zeros(3, f32)
+    vm = np.maximum(v, f32(1e-5))
+    h = np.where(v >= f32(1e-5), f32(hyst), f32(0)).astype(f32)
+    active = (v >= f32(1e-5)).astype(np.int64)
+    with np.errstate(over="ignore"):
+        lo = np.floor(((stats[0] - c).astype(f32) / vm).astype(f32) - h).astype(np.int64)
+        hi = np.floor(((stats[1] - c).astype(f32) / vm).astype(f32) + h).astype(np.int64) + active
+    dims = hi - lo + 1
+    n_cells = int(dims[0]) * int(dims[1]) * int(dims[2])
+    if n_cells >= 2 ** 31 or np.any(np.abs(lo) >= 2 ** 30):
+        raise DmcfError(f"grid_pos lattice of {dims.tolist()} voxels is too large")
+    cv = (C.c_float * 3)(*[float(x) for x in v])
+    cc = (C.c_float * 3)(*[float(x) for x in c]) if center is not None else None
+    clo = (C.c_int32 * 3)(*[int(x) for x in lo])
+    cd = (C.c_int32 * 3)(*[int(x) for x in dims])
+    flags = torch.zeros(n_cells, dtype=torch.int32, device=pos.device)
+    check(lib.dmcf_grid_pos_mark(_p(pos), n, cv, cc, float(hyst), clo, cd, _p(flags), _stream()))
+    offsets = exclusive_scan(flags, torch.int32)
+    count = int(offsets[-1].item())
+    out = torch.empty((count, 3), dtype=torch.float32, device=pos.device)
+    if count:
+        check(lib.dmcf_grid_pos_emit(_p(flags), _p(offsets), cv, cc, clo, cd, _p(out), _stream()))
+    return out
+
+
 def launch_count():
     return int(_lib.load().dmcf_launch_count())

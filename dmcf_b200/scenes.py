@@ -1,0 +1,53 @@
+"""Seeded synthetic scenes: the workloads bench.py times and the parity tests check.  NumPy only."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _walls(lo, hi, dx, dims, open_top=False):
+    """One layer of wall particles (pitch dx) half a pitch outside the axis-aligned block [lo,hi], inward normals.
+    Only the axes listed in ``dims`` get walls (2-D scenes live in the xy-plane, 1-D ones on y)."""
+    pts, nrm = [], []
+    axes = list(dims)
+    rng_ax = {a: np.arange(lo[a] - dx / 2, hi[a] + dx, dx) for a in axes}
+    for a in axes:
+        for side, coord in ((+1, lo[a] - dx / 2), (-1, hi[a] + dx / 2)):
+            if open_top and a == 1 and side == -1:
+                continue
+            others = [b for b in axes if b != a]
+            grids = np.meshgrid(*[rng_ax[b] for b in others], indexing="ij") if others else []
+            n = grids[0].size if others else 1
+            p = np.zeros((n, 3))
+            p[:, a] = coord
+            for b, g in zip(others, grids):
+                p[:, b] = g.reshape(-1)
+            q = np.zeros((n, 3))
+            q[:, a] = side
+            pts.append(p)
+            nrm.append(q)
+    return np.concatenate(pts).astype(np.float32), np.concatenate(nrm).astype(np.float32)
+
+
+def lattice_scene(shape, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0, origin=(0.0, 0.0, 0.0), open_top=False):
+    """Jittered fluid lattice of ``shape`` = (nx, ny, nz) particles (entries of 1 collapse that axis) inside a box of
+    wall particles.  Returns dict(pos, vel, box, box_normals) float32."""
+    rng = np.random.default_rng(seed)
+    dims = [a for a in range(3) if shape[a] > 1]
+    axes = [(np.arange(shape[a]) + 0.5) * dx if a in dims else np.zeros(1) for a in range(3)]
+    g = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3)
+    mask = np.array([1.0 if a in dims else 0.0 for a in range(3)])
+    pos = g + rng.uniform(-jitter * dx, jitter * dx, g.shape) * mask + np.asarray(origin)
+    vel = rng.normal(0.0, vel_sigma, g.shape) * mask
+    lo = np.asarray(origin, dtype=np.float64)
+    hi = lo + np.array([shape[a] * dx if a in dims else 0.0 for a in range(3)])
+    box, normals = _walls(lo, hi, dx, dims, open_top)
+    return dict(pos=pos.astype(np.float32), vel=vel.astype(np.float32), box=box, box_normals=normals)
+
+
+def c4_model_cfg():
+    """BASELINE.json config 4: single-scale ASCC+CConv stack (SymNet with strides [1]) on a 3-D box, Liquid3d physics."""
+    return dict(name="SymNet", layer_channels=[[[8]], [[32]], [[32]], [[32]], [[3]]], kernel_size=[4, 4, 4],
+                sym_kernel_size=[6, 6, 6], coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear",
+                window="poly6", window_sym="peak", strides=[1], particle_radii=[0.1], timestep=0.02, grav=-9.81,
+                out_scale=[0.0078125] * 3, centralize=True, voxel_size=[0.025] * 3, sym_axis=1, add_merge=True,
+                use_acc=False)

@@ -151,6 +151,21 @@ int dmcf_integrate(const float* pos, const float* vel, const float* acc, const f
 int dmcf_correct(const float* pos, const float* pos2, const float* net, int64_t net_stride, int32_t net_c,
                  const float* out_scale_host3, float dt, int64_t n, float* pos_new, float* vel_new, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * grid_pos (utils/tools/losses.py:136-181): lattice points of pitch `voxel` touched by any particle, with the
+ * +-hyst hysteresis and the {0,1} corner offsets on active axes (voxel >= 1e-5).  Float32 arithmetic in the
+ * reference's operation order.  The caller supplies the integer lattice bounds lo/dims (computable from the
+ * position min/max because every step is monotone) and a zeroed flags[dims0*dims1*dims2] array (x fastest):
+ *   dmcf_grid_pos_mark -> flags;  dmcf_exclusive_scan_i32_i32(flags) -> offsets (offsets[n_cells] = count);
+ *   dmcf_grid_pos_emit -> out[count,3] in ascending linear voxel id (the reference's tf.unique order is
+ *   first-occurrence; consumers are order independent).
+ * `center_host3` NULL = not centralised (points sit at voxel centres g*v + v/2, else g*v + center).
+ * ------------------------------------------------------------------------------------------------- */
+int dmcf_grid_pos_mark(const float* pos, int64_t n, const float* voxel_host3, const float* center_host3, float hyst,
+                       const int32_t* lo_host3, const int32_t* dims_host3, int32_t* flags, void* stream);
+int dmcf_grid_pos_emit(const int32_t* flags, const int32_t* offsets, const float* voxel_host3, const float* center_host3,
+                       const int32_t* lo_host3, const int32_t* dims_host3, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

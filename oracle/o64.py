@@ -124,12 +124,10 @@ def _sphere_to_cylinder(x, y, z):
         s_side = n / np.sqrt(xy2)
     zero = sq < 1e-12
     cap = (~zero) & (1.25 * z * z > xy2)
-    side = (~zero) & (~cap)
-    ox = np.where(zero, 0.0, np.where(cap, x * s_cap, x * s_side))
-    oy = np.where(zero, 0.0, np.where(cap, y * s_cap, y * s_side))
+    s = np.where(cap, np.nan_to_num(s_cap), np.nan_to_num(s_side, posinf=0.0))
+    ox = np.where(zero, 0.0, x * s)
+    oy = np.where(zero, 0.0, y * s)
     oz = np.where(zero, 0.0, np.where(cap, np.copysign(n, z), z * 1.5))
-    ox[~np.isfinite(ox)] = 0.0
-    oy[~np.isfinite(oy)] = 0.0
     return ox, oy, oz
 
 
@@ -334,7 +332,7 @@ def grid_pos(pos, voxel_size, centralize=False, pad=0, hyst=0.1):
     v = np.asarray(voxel_size, F32).reshape(3)
     center = None
     if centralize:  # :137-139
-        center = pos.mean(axis=0, dtype=F32).astype(F32)
+        center = pos.astype(np.float64).mean(axis=0).astype(F32)  # float64 accumulate, rounded once (repo convention)
         pos = (pos - center).astype(F32)
     vm = np.maximum(v, F32(1e-5))
     h = np.where(v >= 1e-5, F32(hyst), F32(0.0)).astype(F32)
@@ -445,8 +443,10 @@ class ModelO64:
         # preprocess: models/pbf_model.py:303-438
         dt = c["timestep"]
         a_int = acc if acc is not None else np.array([0.0, c["grav"], 0.0])
-        vel2 = vel + dt * a_int
-        pos2 = pos + dt * vel2  # :234-240
+        # the integration itself runs in float32 with separately rounded ops, like the reference's TF ops (:234-240)
+        vel2 = (vel.astype(F32) + (F32(dt) * np.asarray(a_int, F32)).astype(F32)).astype(F32)
+        pos2 = (pos.astype(F32) + (F32(dt) * vel2).astype(F32)).astype(F32)
+        vel2, pos2 = vel2.astype(np.float64), pos2.astype(np.float64)
         ext = np.asarray(c["particle_radii"], F32) * F32(2)
         lo = pos2.min(axis=0) - float(ext[-1]); hi = pos2.max(axis=0) + float(ext[-1])
         f = np.all((box >= lo) & (box <= hi), axis=1)  # :330-334
