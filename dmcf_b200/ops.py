@@ -27,6 +27,9 @@ NeighborSearchResult = namedtuple("NeighborSearchResult",
 
 MAX_CELLS = 1 << 24
 
+# bench.py sets this to a list to get one {start,end CUDA events + shape metadata} record per conv launch
+PROFILE = None
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -251,11 +254,21 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     out_stride = out.stride(0) if n_out > 1 else max(cout, out.stride(0))
     neighbors_index = neighbors_index.contiguous()
     neighbors_row_splits = neighbors_row_splits.contiguous()
+    rec = None
+    if PROFILE is not None:
+        rec = dict(kernel_size=(kz, ky, kx), cin=cin, cout=cout, ascc=bool(ascc), n_inp=n_inp, n_out=n_out,
+                   rows=kz * ky * kx * cin + int(dense_cin), pairs=int(neighbors_index.shape[0]),
+                   residual=residual is not None, start=torch.cuda.Event(enable_timing=True),
+                   end=torch.cuda.Event(enable_timing=True))
+        rec["start"].record()
     check(lib.dmcf_cconv_forward(C.byref(d), _p(filters), _p(out_positions), n_out, _p(inp_positions),
                                  _p(inp_features), inp_stride, n_inp, _p(inp_importance),
                                  _p(neighbors_index), _p(neighbors_row_splits),
                                  _p(neighbors_importance), _p(bias), _p(dense_inp) if dense_cin else None,
                                  dense_stride, _p(residual), res_stride, _p(out), out_stride, _stream()))
+    if rec is not None:
+        rec["end"].record()
+        PROFILE.append(rec)
     return out
 
 

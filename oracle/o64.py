@@ -279,38 +279,52 @@ def symmetric_kernel(kernel, sym_axis):
 def cconv_layer(inp_features, inp_positions, out_positions, extents, kernel, bias=None, *,
                 align_corners=True, coordinate_mapping="ball_to_cube_radial", interpolation="linear",
                 normalize=True, ignore_query_points=False, window_name=None, window_fac=1.0,
-                symmetric=False, sym_axis=2, return_nns=False):
+                symmetric=False, sym_axis=2, return_nns=False, backend=None):
     """ContinuousConv.call (utils/convolutions.py:277-470) for scalar extents, no dense-for-center,
     non-circular kernels, linear activation."""
+    B = backend if backend is not None else _Backend64
+    dt = B.dtype
     radius = F32(0.5) * F32(extents)  # :353
-    idx, splits, d2 = fixed_radius_search(inp_positions, out_positions, radius,
-                                          ignore_query_point=ignore_query_points,
-                                          return_distances=window_name is not None)
+    idx, splits, d2 = B.fixed_radius_search(inp_positions, out_positions, radius,
+                                            ignore_query_point=ignore_query_points,
+                                            return_distances=window_name is not None)
     if window_name is not None:
-        q = d2.astype(np.float64) / (np.float64(radius) * np.float64(radius))  # :361-362
-        imp = window(window_name, q, window_fac)  # :378-379
+        q = d2.astype(dt) / (dt(radius) * dt(radius))  # :361-362
+        imp = B.window(window_name, q, window_fac)  # :378-379
     else:
         imp = None
-    k = np.asarray(kernel, np.float64)
+    k = np.asarray(kernel, dt)
     if symmetric:
         k = symmetric_kernel(k, sym_axis)
     kw = dict(out_positions=out_positions, extents=extents, offset=(0, 0, 0), inp_positions=inp_positions,
               inp_importance=None, neighbors_index=idx, neighbors_importance=imp,
               neighbors_row_splits=splits, align_corners=align_corners,
               coordinate_mapping=coordinate_mapping, normalize=normalize, interpolation=interpolation)
-    feats = np.asarray(inp_features, np.float64)
-    out = continuous_conv(filters=k, inp_features=feats, **kw)  # :431
+    feats = np.asarray(inp_features, dt)
+    out = B.continuous_conv(filters=k, inp_features=feats, **kw)  # :431
     if symmetric:  # :433-458
         assert inp_positions.shape == out_positions.shape
         wk = k.reshape(k.shape[0], k.shape[1], k.shape[2], 1, -1)
-        w_values = continuous_conv(filters=wk, inp_features=np.ones((feats.shape[0], 1)), **kw)
+        w_values = B.continuous_conv(filters=wk, inp_features=np.ones((feats.shape[0], 1), dt), **kw)
         res = w_values.reshape(-1, k.shape[-2], k.shape[-1])
         out = out + np.einsum("nc,nco->no", feats, res)
     if bias is not None:
-        out = out + np.asarray(bias, np.float64)
+        out = out + np.asarray(bias, dt)
     if return_nns:
         return out, (idx, splits, d2)
     return out
+
+
+class _Backend64:
+    """float64 NumPy ops (the default backend); oracle/o32.py provides the float32 C one."""
+    dtype = np.float64
+    fixed_radius_search = staticmethod(fixed_radius_search)
+    continuous_conv = staticmethod(continuous_conv)
+    window = staticmethod(window)
+
+    @staticmethod
+    def dense(x, kernel, bias):
+        return dense(x, kernel, bias)
 
 
 def point_sampling(inp_features, inp_positions, out_positions, extents, window_name=None, normalize=True):
@@ -393,7 +407,8 @@ class ModelO64:
     """Reference dataflow of PBFNet/HRNet/SymNet/CConv on a ``weights`` dict keyed by checkpoint-style names
     (SURVEY Appendix B).  ``cfg`` is the ``model:`` section of a reference YAML."""
 
-    def __init__(self, cfg, weights):
+    def __init__(self, cfg, weights, backend=None):
+        self.B = backend if backend is not None else _Backend64
         d = dict(kernel_size=[4, 4, 4], strides=[1], particle_radii=[0.05],
                  coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear", window=None,
                  ignore_query_points=False, grav=-9.81, transformation={}, timestep=0.01, use_vel=True,
@@ -414,10 +429,10 @@ class ModelO64:
                            coordinate_mapping=c["coordinate_mapping"], interpolation=c["interpolation"],
                            normalize=False,
                            ignore_query_points=c["ignore_query_points"] if ignore_q is None else ignore_q,
-                           window_name=c["window"] if window is None else window, **kw)
+                           window_name=c["window"] if window is None else window, backend=self.B, **kw)
 
     def _dense(self, key, x):
-        return dense(x, self.w[key + "/kernel"], self.w[key + "/bias"])
+        return self.B.dense(x, self.w[key + "/kernel"], self.w[key + "/bias"])
 
     # -- BaseModel.call: models/base_model.py:23-29 -----------------------------------------------------------
     def __call__(self, pos, vel, acc, box, bfeats):
@@ -545,7 +560,7 @@ class ModelO64:
             ans = cconv_layer(ans * c["part_scale"], all_pos, all_pos, ext[0], self.w["sym_convs/%d/kernel" % i],
                               None, align_corners=True, coordinate_mapping=c["coordinate_mapping"],
                               interpolation=c["interpolation"], normalize=False, ignore_query_points=True,
-                              window_name=c["window_sym"], symmetric=True, sym_axis=c["sym_axis"])
+                              window_name=c["window_sym"], symmetric=True, sym_axis=c["sym_axis"], backend=self.B)
         return ans
 
     # -- models/cconv.py:50-69 -------------------------------------------------------------------------------

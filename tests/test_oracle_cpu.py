@@ -1,0 +1,297 @@
+"""CPU suite (-m "not gpu"): pins the oracles against every known answer the reference offers for this path
+(the generator's brute-force neighbour counter, analytic identities, structural invariants), checks O32
+against O64, and checks that the C-ABI library loads and exports every symbol include/dmcf_b200.h declares."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import o32, o64
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def sorted_rows(index, splits, dist):
+    rows = np.repeat(np.arange(len(splits) - 1), np.diff(splits))
+    o = np.lexsort((index, rows))
+    return index[o], dist[o]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fixed radius search
+# ---------------------------------------------------------------------------------------------------------
+def test_search_matches_reference_generator_neighbor_counter():
+    """Known answer from the reference's own code: SPH1D.cnt_nn (datasets/column_gen.py:36-43) counts |dx|/h <= 1."""
+    z = np.load(os.path.join(GOLDEN, "column_seed44.npz"))
+    x = z["solver_x"].astype(np.float64)
+    h = float(z["solver_h"])
+    pts = np.zeros((len(x), 3), np.float32)
+    pts[:, 1] = x
+    for impl in (o64, o32):
+        _, splits, _ = impl.fixed_radius_search(pts, pts, h)
+        assert np.array_equal(np.diff(splits), z["solver_cnt_nn"]), impl.__name__
+
+
+@pytest.mark.parametrize("ignore", [False, True])
+def test_search_equals_bruteforce_definition(ignore):
+    rng = np.random.default_rng(0)
+    lattice = np.stack(np.meshgrid(*[np.arange(7) * 0.05] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    for pts, r in [(rng.random((600, 3)).astype(np.float32), 0.13), (lattice, 0.1),
+                   (np.concatenate([lattice, lattice[:20]]), 0.05), (rng.random((1, 3)).astype(np.float32), 0.3)]:
+        ref = o64.fixed_radius_search_bruteforce(pts, pts, r, ignore)
+        for impl in (o64, o32):
+            got = impl.fixed_radius_search(pts, pts, r, ignore)
+            assert np.array_equal(got[1], ref[1])
+            a, b = sorted_rows(*got), sorted_rows(*ref)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_search_empty_and_disjoint():
+    e = np.zeros((0, 3), np.float32)
+    q = np.random.default_rng(1).random((5, 3)).astype(np.float32)
+    for impl in (o64, o32):
+        i, s, d = impl.fixed_radius_search(e, q, 0.1)
+        assert len(i) == 0 and np.array_equal(s, np.zeros(6, np.int64))
+        i, s, d = impl.fixed_radius_search(q, e, 0.1)
+        assert len(i) == 0 and len(s) == 1
+        i, s, d = impl.fixed_radius_search(q + 100, q, 0.1)
+        assert len(i) == 0 and s[-1] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# windows, mapping, interpolation, conv
+# ---------------------------------------------------------------------------------------------------------
+def test_window_known_values():
+    q = np.array([0.0, 0.25, 1.0])
+    assert np.allclose(o64.window("poly6", q), [1.0, 0.421875, 0.0])
+    assert np.allclose(o64.window("peak", q), [1.0, 0.25, 0.0])
+    assert np.allclose(o64.window("linear", q), [1.0, 0.5, 0.0])
+    assert np.allclose(o64.window("cubic", q, fac=3 / 4), [1.0, 6 * (0.125 - 0.25) + 1, 0.0])
+    assert np.allclose(o64.window("cubic_grad", q, fac=3 / 4), [0.0, 18 * 0.25 - 6, 0.0])
+    assert np.allclose(o64.window("poly6", np.array([2.0])), [0.0])  # clipped
+    assert o64.window(None, q) is None
+
+
+def test_mapping_is_odd_and_maps_ball_into_cube():
+    rng = np.random.default_rng(2)
+    v = rng.standard_normal((5000, 3))
+    v = v / np.linalg.norm(v, axis=1, keepdims=True) * rng.random((5000, 1)) ** (1 / 3) * 0.5  # in the ball of diameter 1
+    for m in ("ball_to_cube_radial", "ball_to_cube_volume_preserving", "identity"):
+        c = o64.map_coordinates(v, 1.0, m)
+        assert np.all(np.abs(c) <= 0.5 + 1e-9), m
+        assert np.allclose(o64.map_coordinates(-v, 1.0, m), -c, atol=1e-15), m
+    # volume preserving: uniform points in the ball become uniform in the cube -> mean |c| per axis = 0.25
+    c = o64.map_coordinates(v, 1.0, "ball_to_cube_volume_preserving")
+    assert np.allclose(np.abs(c).mean(0), 0.25, atol=0.01)
+    surf = v / np.linalg.norm(v, axis=1, keepdims=True) * 0.5
+    assert np.allclose(np.abs(o64.map_coordinates(surf, 1.0, "ball_to_cube_radial")).max(1), 0.5)
+
+
+def test_interpolation_partition_of_unity_and_clamping():
+    rng = np.random.default_rng(3)
+    g = rng.uniform(-1.5, 5.5, (2000, 3))
+    cell, w = o64.interpolation_weights(g, (4, 4, 4), "linear")
+    assert np.allclose(w.sum(1), 1.0) and cell.min() >= 0 and cell.max() < 64
+    cell, w = o64.interpolation_weights(g, (4, 4, 4), "linear_border")
+    assert np.all(w.sum(1) <= 1.0 + 1e-12)
+    cell, w = o64.interpolation_weights(np.array([[1.0, 2.0, 3.0]]), (4, 4, 4), "linear")
+    assert cell[0, 0] == (3 * 4 + 2) * 4 + 1 and w[0, 0] == 1.0
+
+
+def _cloud(n=400, seed=4):
+    rng = np.random.default_rng(seed)
+    return rng, (rng.random((n, 3)) * 0.5).astype(np.float32)
+
+
+def test_constant_filter_reduces_to_weighted_feature_sum():
+    rng, pts = _cloud()
+    f = rng.standard_normal((len(pts), 3)).astype(np.float32)
+    w0 = rng.standard_normal((3, 2))
+    filt = np.broadcast_to(w0, (4, 4, 4, 3, 2)).copy()
+    idx, splits, d2 = o64.fixed_radius_search(pts, pts, 0.1)
+    a = o64.window("poly6", d2 / np.float64(np.float32(0.1)) ** 2)
+    rows = np.repeat(np.arange(len(pts)), np.diff(splits))
+    expect = np.zeros((len(pts), 2))
+    np.add.at(expect, rows, (a[:, None] * f[idx]) @ w0)
+    for impl, tol in ((o64, 1e-12), (o32, 1e-5)):
+        got = impl.cconv_layer(f, pts, pts, 0.2, filt, None, coordinate_mapping="ball_to_cube_volume_preserving",
+                               normalize=False, window_name="poly6")
+        assert np.abs(got - expect).max() <= tol * max(1.0, np.abs(expect).max())
+
+
+def test_point_sampling_is_window_weighted_mean():
+    rng, pts = _cloud()
+    f = rng.standard_normal((len(pts), 4)).astype(np.float32)
+    out = o64.point_sampling(f, pts, pts[:50], 0.2, window_name="poly6", normalize=True)
+    idx, splits, d2 = o64.fixed_radius_search(pts, pts[:50], 0.1)
+    a = o64.window("poly6", d2 / np.float64(np.float32(0.1)) ** 2)
+    for o in range(50):
+        s = slice(splits[o], splits[o + 1])
+        assert np.allclose(out[o], (a[s, None] * f[idx[s]]).sum(0) / a[s].sum())
+
+
+def test_ascc_conserves_momentum_and_kernel_is_antisymmetric():
+    rng, pts = _cloud(600, 5)
+    f = rng.standard_normal((len(pts), 8)).astype(np.float32)
+    half = rng.uniform(-0.5, 0.5, (6, 3, 6, 8, 3))
+    full = o64.symmetric_kernel(half, 1)
+    assert full.shape == (6, 6, 6, 8, 3) and np.array_equal(full[::-1, ::-1, ::-1], -full)
+    kw = dict(coordinate_mapping="ball_to_cube_volume_preserving", normalize=False, window_name="peak", symmetric=True,
+              sym_axis=1, ignore_query_points=True)
+    out = o64.cconv_layer(f, pts, pts, 0.2, half, None, **kw)
+    assert np.all(np.abs(out.sum(0)) <= 1e-12 * np.abs(out).sum(0))
+    out32 = o32.cconv_layer(f, pts, pts, 0.2, half.astype(np.float32), None, **kw)
+    assert np.abs(out32 - out).max() <= 2e-5 * np.abs(out).max() + 1e-6
+    assert np.all(np.abs(out32.astype(np.float64).sum(0)) <= 1e-4 * np.abs(out32).sum(0))
+    plain = o64.cconv_layer(f, pts, pts, 0.2, full, None, **dict(kw, symmetric=False))
+    assert np.abs(plain.sum(0)).max() > 1e-3  # the plain conv does NOT conserve
+
+
+CASES = [((4, 4, 4), 16, 8, "ball_to_cube_volume_preserving", "linear", True, False, "poly6"),
+         ((1, 8, 8), 7, 8, "ball_to_cube_volume_preserving", "linear", True, False, "poly6"),
+         ((3, 3, 3), 5, 6, "ball_to_cube_radial", "linear", True, True, "cubic"),
+         ((3, 3, 3), 5, 6, "ball_to_cube_radial", "linear", True, True, None),
+         ((4, 3, 2), 3, 2, "identity", "linear", False, False, "linear"),
+         ((3, 3, 3), 4, 4, "ball_to_cube_radial", "linear_border", False, False, "peak"),
+         ((3, 3, 3), 4, 4, "ball_to_cube_volume_preserving", "nearest_neighbor", True, False, None)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_o32_conv_matches_o64(case):
+    ks, cin, cout, mapping, interp, align, normalize, win = case
+    rng, pts = _cloud(500, 6)
+    if ks[0] == 1:
+        pts[:, 2] = 0
+    f = rng.standard_normal((len(pts), cin)).astype(np.float32)
+    filt = rng.uniform(-0.5, 0.5, ks + (cin, cout)).astype(np.float32)
+    kw = dict(align_corners=align, coordinate_mapping=mapping, interpolation=interp, normalize=normalize, window_name=win)
+    a = o64.cconv_layer(f, pts, pts[:300], 0.25, filt, None, **kw)
+    b = o32.cconv_layer(f, pts, pts[:300], 0.25, filt, None, **kw)
+    assert np.abs(a - b).max() <= 2e-5 * np.abs(a).max() + 1e-6
+
+
+def test_translation_invariance():
+    rng, pts = _cloud(300, 7)
+    f = rng.standard_normal((len(pts), 4)).astype(np.float32)
+    filt = rng.uniform(-0.5, 0.5, (4, 4, 4, 4, 4))
+    kw = dict(coordinate_mapping="ball_to_cube_volume_preserving", normalize=False, window_name="poly6")
+    a = o64.cconv_layer(f, pts, pts, 0.2, filt, None, **kw)
+    shift = np.array([0.25, -0.5, 0.125], np.float32)  # exactly representable shifts keep the float32 positions exact
+    b = o64.cconv_layer(f, pts + shift, pts + shift, 0.2, filt, None, **kw)
+    assert np.abs(a - b).max() <= 1e-4 * np.abs(a).max()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-scale sampling
+# ---------------------------------------------------------------------------------------------------------
+def test_grid_pos_properties():
+    rng = np.random.default_rng(8)
+    pts = (rng.random((2000, 3)) * 0.6).astype(np.float32)
+    v = np.array([0.05, 0.05, 0.05], np.float32)
+    g = o64.grid_pos(pts, v, centralize=False)
+    assert len(np.unique(np.round(g / v * 2).astype(np.int64), axis=0)) == len(g)  # no duplicates
+    # every particle has its 8 surrounding lattice points present
+    lat = set(map(tuple, np.round(g / v - 0.5).astype(np.int64)))
+    base = np.floor(pts / v - np.float32(0.1)).astype(np.int64)
+    for b in base[:200]:
+        for o in np.ndindex(2, 2, 2):
+            assert tuple(b + np.array(o)) in lat
+    # 2-D: inactive axis collapses
+    p2 = pts.copy(); p2[:, 2] = 0
+    g2 = o64.grid_pos(p2, np.array([0.05, 0.05, 0.0], np.float32), centralize=True)
+    assert np.allclose(g2[:, 2], p2[:, 2].mean())
+    dil = o64.get_dilated_pos(pts, [1, 2, 4], voxel_size=[0.025] * 3, centralize=True)
+    assert dil[0] is not None and len(dil[1]) > len(dil[2]) > 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# whole step: O32 == O64, checkpoint fixtures load, physical sanity with the trained weights
+# ---------------------------------------------------------------------------------------------------------
+def _weights(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    w = {k.replace("|", "/"): z[k] for k in z.files}
+    return {(k.replace("/1/", "/") if k.startswith("_all_convs/") else k): v for k, v in w.items()}
+
+
+def test_liquid3d_step_o32_matches_o64_and_is_sane():
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_models_gpu import liquid3d_cfg
+    from dmcf_b200 import scenes
+    scene = scenes.lattice_scene((8, 8, 7), dx=0.05, seed=9, open_top=True)
+    w = _weights("ckpt_Liquid3d.npz")
+    assert sum(v.size for v in w.values()) == 275084
+    m64, m32 = o64.ModelO64(liquid3d_cfg(), w), o32.ModelO32(liquid3d_cfg(), w)
+    p64, v64 = m64(scene["pos"], scene["vel"], None, scene["box"], scene["box_normals"])
+    p32, v32 = m32(scene["pos"], scene["vel"], None, scene["box"], scene["box_normals"])
+    scale = np.abs(m64.net_out).max()
+    assert np.abs(m32.net_out - m64.net_out).max() <= 8 * (2e-5 * scale + 1e-6)
+    assert np.abs(p32 - p64).max() <= 1e-6
+    # trained weights on a resting block: corrections are a fraction of the particle spacing, momentum is conserved
+    assert np.abs(m64.pos_correction).max() < 0.025
+    net = m64.net_out
+    assert np.all(np.abs(net.sum(0)) <= 1e-9 * np.abs(net).sum(0) + 1e-12)
+
+
+def test_checkpoint_reader_against_reference_files():
+    ref = "/root/reference/checkpoints"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present (GPU box)")
+    from dmcf_b200.checkpoint import load_checkpoint, model_weights
+    for name, n_tensors, n_params in (("Liquid3d", 49, 275084), ("WBC-SPH", 109, 537376)):
+        w = model_weights(load_checkpoint(os.path.join(ref, name, "ckpt")))
+        assert len(w) == n_tensors and sum(v.size for v in w.values()) == n_params
+        fix = np.load(os.path.join(GOLDEN, f"ckpt_{name}.npz"))
+        for k in fix.files:
+            assert np.array_equal(fix[k], w[k.replace("|", "/")])
+        assert all(np.isfinite(v).all() for v in w.values())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# C ABI: the library loads and exports every declared symbol (no compute without a GPU)
+# ---------------------------------------------------------------------------------------------------------
+def test_c_abi_exports_every_declared_symbol():
+    from dmcf_b200 import _lib, build
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "dmcf_b200.h")).read()
+    declared = set(re.findall(r"\b(dmcf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dmcf_version() == 100
+    # error path without a GPU: invalid arguments are rejected before any CUDA call
+    import ctypes as C
+    rc = lib.dmcf_cconv_forward(None, None, None, 0, None, None, 0, 0, None, None, None, None, None, None, 0, None, 0, None, 0, None)
+    assert rc == 1 and b"desc" in lib.dmcf_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dmcf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("oracle pins", "").replace("The oracle", "") or \
+                    not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_config_contract_builds_every_shipped_hot_path_model():
+    ref = "/root/reference/configs"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present (GPU box)")
+    from dmcf_b200 import config
+    expect = {"Liquid3d.yml": 18, "WBC-SPH.yml": 43, "WaterRamps.yml": None, "column/hrnet.yml": 27, "column/symnet.yml": None,
+              "other/cconv3d.yml": 5, "other/cconv.yml": None}
+    for rel, n_convs in expect.items():
+        cfg = config.load_config(os.path.join(ref, rel), overrides={"model.timestep": "0.01"})
+        assert cfg["model"]["timestep"] == 0.01
+        m = config.build_model(cfg["model"])
+        if n_convs is not None:
+            assert len(m._all_convs) == n_convs, rel
+    with pytest.raises(NotImplementedError):
+        config.build_model(config.load_config(os.path.join(ref, "other/pointnet.yml"))["model"])
