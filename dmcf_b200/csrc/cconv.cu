@@ -45,14 +45,12 @@ struct ConvParams {
     int64_t out_stride;
 };
 
-static constexpr int kConvWarps = 8;
-
-template <int MT>
-__global__ void __launch_bounds__(kConvWarps * 32, 1) k_cconv_tile(const ConvParams p) {
+template <int MT, int NW, int CIP>
+__global__ void __launch_bounds__(NW * 32, 1) k_cconv_tile(const ConvParams p) {
     extern __shared__ __align__(16) float smem[];
-    float* patch = smem;                                    // [MT][kc_pad]
-    float* red = patch + (size_t)MT * p.kc_pad;             // [kConvWarps][MT][cp]
-    float* norm = red + (size_t)kConvWarps * MT * p.cp;     // [MT]
+    float* patch = smem;                            // [MT][kc_pad]
+    float* red = patch + (size_t)MT * p.kc_pad;     // [NW][MT][cp]
+    float* norm = red + (size_t)NW * MT * p.cp;     // [MT]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile_base = (int64_t)blockIdx.x * MT;
@@ -61,19 +59,23 @@ __global__ void __launch_bounds__(kConvWarps * 32, 1) k_cconv_tile(const ConvPar
     {
         float4* p4 = reinterpret_cast<float4*>(patch);
         const int n4 = MT * p.kc_pad / 4;
-        for (int i = tid; i < n4; i += kConvWarps * 32) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < n4; i += NW * 32) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
 
     // ---- phase 1: patch build, one warp per out point -----------------------------------------------------
-    const int cip = p.cip, cg = lane / cip, ci0 = lane % cip, n_cg = 32 / cip;
+    // lanes = (corner group, input channel): CIP = pow2 >= min(cin,32) channels, CG = 32/CIP corners in parallel
+    constexpr int cip = CIP, n_cg = (32 / CIP > 8) ? 8 : 32 / CIP;  // at most the 8 corners; extra lanes idle
+    const int cg = lane / CIP, ci0 = lane % CIP;
+    const bool lane_ok = cg < n_cg;
     const bool filter_nbr = p.nbr_hi > p.nbr_lo;
-    for (int m = warp; m < MT; m += kConvWarps) {
+    for (int m = warp; m < MT; m += NW) {
         const int64_t o = tile_base + m;
         if (o >= p.n_out) break;
         float* prow = patch + (size_t)m * p.kc_pad;
         const float ox = __ldg(p.out_pos + 3 * o), oy = __ldg(p.out_pos + 3 * o + 1), oz = __ldg(p.out_pos + 3 * o + 2);
         const int64_t rs = p.row_splits[o], re = p.row_splits[o + 1];
+        const float* crow = p.inp_feat + o * p.inp_stride;  // centre row (ascc: out set == inp set)
         float norm_acc = 0.0f;
         for (int64_t c0 = rs; c0 < re; c0 += 32) {
             // lane-parallel geometry for up to 32 neighbours
@@ -108,42 +110,68 @@ __global__ void __launch_bounds__(kConvWarps * 32, 1) k_cconv_tile(const ConvPar
                     }
                 }
             }
-            const unsigned active = __ballot_sync(0xffffffffu, row >= 0);
-            // broadcast every kept pair; lanes own (corner group, input channel)
-            unsigned todo = active;
+            // broadcast the kept pairs four at a time (four independent feature gathers in flight per lane);
+            // lanes own (corner group, input channel)
+            unsigned todo = __ballot_sync(0xffffffffu, row >= 0);
             while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int r_row = __shfl_sync(0xffffffffu, row, src);
-                const int r_i0 = __shfl_sync(0xffffffffu, g.i0, src);
-                const int r_i1 = __shfl_sync(0xffffffffu, g.i1, src);
-                const float wx0 = __shfl_sync(0xffffffffu, g.wx0, src), wx1 = __shfl_sync(0xffffffffu, g.wx1, src);
-                const float wy0 = __shfl_sync(0xffffffffu, g.wy0, src), wy1 = __shfl_sync(0xffffffffu, g.wy1, src);
-                const float wz0 = __shfl_sync(0xffffffffu, g.wz0, src), wz1 = __shfl_sync(0xffffffffu, g.wz1, src);
-                const float* frow = p.inp_feat + (int64_t)r_row * p.inp_stride;
-                const float* crow = p.inp_feat + o * p.inp_stride;  // centre row (ascc: out set == inp set)
-                for (int ci = ci0; ci < p.cin; ci += cip) {
-                    float f = __ldg(frow + ci);
-                    if (p.relu_input) f = fmaxf(f, 0.0f);
-                    f *= p.feat_scale;
-                    if (p.ascc) {
-                        float fc = __ldg(crow + ci);
+                constexpr int U = 4;
+                int r_row[U], r_i0[U], r_i1[U];
+                float wx0[U], wx1[U], wy0[U], wy1[U], wz0[U], wz1[U];
+                int first = __ffs(todo) - 1;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool valid = todo != 0;
+                    const int src = valid ? __ffs(todo) - 1 : first;
+                    if (valid) todo &= todo - 1;
+                    r_row[u] = __shfl_sync(0xffffffffu, row, src);
+                    r_i0[u] = __shfl_sync(0xffffffffu, g.i0, src);
+                    r_i1[u] = __shfl_sync(0xffffffffu, g.i1, src);
+                    wx0[u] = __shfl_sync(0xffffffffu, g.wx0, src);
+                    wx1[u] = __shfl_sync(0xffffffffu, g.wx1, src);
+                    wy0[u] = __shfl_sync(0xffffffffu, g.wy0, src);
+                    wy1[u] = __shfl_sync(0xffffffffu, g.wy1, src);
+                    const float z0 = __shfl_sync(0xffffffffu, g.wz0, src), z1 = __shfl_sync(0xffffffffu, g.wz1, src);
+                    wz0[u] = valid ? z0 : 0.0f;
+                    wz1[u] = valid ? z1 : 0.0f;
+                }
+                for (int cb0 = 0; cb0 < p.cin; cb0 += cip) {  // warp-uniform trip count (__syncwarp inside)
+                    const int ci = cb0 + ci0;
+                    const bool ci_ok = lane_ok && ci < p.cin;
+                    float f[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) f[u] = ci_ok ? __ldg(p.inp_feat + (int64_t)r_row[u] * p.inp_stride + ci) : 0.0f;
+                    float fc = 0.0f;
+                    if (p.ascc && ci_ok) {
+                        fc = __ldg(crow + ci);
                         if (p.relu_input) fc = fmaxf(fc, 0.0f);
-                        f += fc * p.feat_scale;
+                        fc *= p.feat_scale;
                     }
-                    for (int c = cg; c < 8; c += n_cg) {
-                        const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
-                        const float w = (bx ? wx1 : wx0) * (by ? wy1 : wy0) * (bz ? wz1 : wz0);
-                        if (w != 0.0f) {
-                            const int sel = (bx ? r_i1 : r_i0) & 0xff;
-                            const int sely = ((by ? r_i1 : r_i0) >> 8) & 0xff;
-                            const int selz = ((bz ? r_i1 : r_i0) >> 16) & 0xff;
-                            const int cell = (selz * p.gp.ky + sely) * p.gp.kx + sel;
-                            prow[cell * p.cin + ci] += w * f;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        float fv = f[u];
+                        if (p.relu_input) fv = fmaxf(fv, 0.0f);
+                        fv = fv * p.feat_scale + fc;
+                        const int x0 = r_i0[u] & 0xff, x1 = r_i1[u] & 0xff;
+                        const int zy00 = (((r_i0[u] >> 16) & 0xff) * p.gp.ky + ((r_i0[u] >> 8) & 0xff)) * p.gp.kx;
+                        const int zy01 = (((r_i0[u] >> 16) & 0xff) * p.gp.ky + ((r_i1[u] >> 8) & 0xff)) * p.gp.kx;
+                        const int zy10 = (((r_i1[u] >> 16) & 0xff) * p.gp.ky + ((r_i0[u] >> 8) & 0xff)) * p.gp.kx;
+                        const int zy11 = (((r_i1[u] >> 16) & 0xff) * p.gp.ky + ((r_i1[u] >> 8) & 0xff)) * p.gp.kx;
+                        float* pc = prow + ci;
+#pragma unroll
+                        for (int j = 0; j < 8 / n_cg; ++j) {
+                            const int c = j * n_cg + cg;  // compile-time when CIP == 32
+                            const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;
+                            const float w = (bx ? wx1[u] : wx0[u]) * (by ? wy1[u] : wy0[u]) * (bz ? wz1[u] : wz0[u]);
+                            if (ci_ok && w != 0.0f) {
+                                const int zy = bz ? (by ? zy11 : zy10) : (by ? zy01 : zy00);
+                                const int cell = zy + (bx ? x1 : x0);
+                                pc[cell * p.cin] += w * fv;
+                            }
                         }
+                        // with several corner groups per channel two pairs may hit one address from different lanes
+                        if (n_cg > 1) __syncwarp();
                     }
                 }
-                __syncwarp();
             }
         }
         // fused Dense input: relu'd (unscaled) centre features appended as an extra "cell"
@@ -166,27 +194,40 @@ __global__ void __launch_bounds__(kConvWarps * 32, 1) k_cconv_tile(const ConvPar
     // ---- phase 2: [MT x kc] x [kc x cout], split-K over warps, lane = (k sub-slice, output channel) -------------
     const int cp = p.cp, ks = lane / cp, cl = lane % cp, n_ks = 32 / cp;
     const int kq_total = p.kc_pad / 4;
+    const int kq_stride = NW * n_ks;
     for (int cb = 0; cb < p.cout; cb += 32) {
         const int co = cb + cl;
         const bool co_ok = co < p.cout;
         float acc[MT];
 #pragma unroll
         for (int m = 0; m < MT; ++m) acc[m] = 0.0f;
-        for (int kq = warp * n_ks + ks; kq < kq_total; kq += kConvWarps * n_ks) {
+        auto load_w = [&](int kq, float& w0, float& w1, float& w2, float& w3) {
             const int k = kq * 4;
             const float* wrow = p.filters + (int64_t)k * p.cout + co;
-            const float w0 = (co_ok && k + 0 < p.kc) ? __ldg(wrow) : 0.0f;
-            const float w1 = (co_ok && k + 1 < p.kc) ? __ldg(wrow + p.cout) : 0.0f;
-            const float w2 = (co_ok && k + 2 < p.kc) ? __ldg(wrow + 2 * p.cout) : 0.0f;
-            const float w3 = (co_ok && k + 3 < p.kc) ? __ldg(wrow + 3 * p.cout) : 0.0f;
+            w0 = (co_ok && k + 0 < p.kc) ? __ldg(wrow) : 0.0f;
+            w1 = (co_ok && k + 1 < p.kc) ? __ldg(wrow + p.cout) : 0.0f;
+            w2 = (co_ok && k + 2 < p.kc) ? __ldg(wrow + 2 * p.cout) : 0.0f;
+            w3 = (co_ok && k + 3 < p.kc) ? __ldg(wrow + 3 * p.cout) : 0.0f;
+        };
+        int kq = warp * n_ks + ks;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+        if (kq < kq_total) load_w(kq, w0, w1, w2, w3);
+        while (kq < kq_total) {
+            // register double buffer: the next filter rows travel from L2 while this quad is consumed
+            const int kn = kq + kq_stride;
+            float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+            if (kn < kq_total) load_w(kn, n0, n1, n2, n3);
+            const float* prow = patch + kq * 4;
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-                const float4 pv = *reinterpret_cast<const float4*>(patch + (size_t)m * p.kc_pad + k);
+                const float4 pv = *reinterpret_cast<const float4*>(prow + (size_t)m * p.kc_pad);
                 acc[m] = fmaf(pv.x, w0, acc[m]);
                 acc[m] = fmaf(pv.y, w1, acc[m]);
                 acc[m] = fmaf(pv.z, w2, acc[m]);
                 acc[m] = fmaf(pv.w, w3, acc[m]);
             }
+            w0 = n0; w1 = n1; w2 = n2; w3 = n3;
+            kq = kn;
         }
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
@@ -195,14 +236,14 @@ __global__ void __launch_bounds__(kConvWarps * 32, 1) k_cconv_tile(const ConvPar
             if (ks == 0) red[((size_t)warp * MT + m) * cp + cl] = v;
         }
         __syncthreads();
-        for (int t = tid; t < MT * cp; t += kConvWarps * 32) {
+        for (int t = tid; t < MT * cp; t += NW * 32) {
             const int m = t / cp, c = t % cp;
             const int64_t o = tile_base + m;
             const int oc = cb + c;
             if (o < p.n_out && oc < p.cout) {
                 float v = 0.0f;
 #pragma unroll
-                for (int w = 0; w < kConvWarps; ++w) v += red[((size_t)w * MT + m) * cp + c];
+                for (int w = 0; w < NW; ++w) v += red[((size_t)w * MT + m) * cp + c];
                 if (p.normalize) {
                     const float nv = norm[m];
                     if (nv != 0.0f) v /= nv;
@@ -224,22 +265,34 @@ static int next_pow2(int v) {
     return r;
 }
 
-static size_t conv_smem_bytes(int mt, int kc_pad, int cp) {
-    return ((size_t)mt * kc_pad + (size_t)kConvWarps * mt * cp + mt) * sizeof(float);
+static size_t conv_smem_bytes(int mt, int nw, int kc_pad, int cp) {
+    return ((size_t)mt * kc_pad + (size_t)nw * mt * cp + mt) * sizeof(float);
 }
 
-template <int MT>
-static int launch_cconv(const ConvParams& p, size_t smem, cudaStream_t st) {
+template <int MT, int NW, int CIP>
+static int launch_cconv_cip(const ConvParams& p, cudaStream_t st) {
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_cconv_tile<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_cconv_tile<MT, NW, CIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_tile)");
         attr_set = true;
     }
     const int64_t tiles = ceil_div(p.n_out, MT);
-    k_cconv_tile<MT><<<(unsigned)tiles, kConvWarps * 32, smem, st>>>(p);
+    k_cconv_tile<MT, NW, CIP><<<(unsigned)tiles, NW * 32, conv_smem_bytes(MT, NW, p.kc_pad, p.cp), st>>>(p);
     DMCF_LAUNCH_CHECK("k_cconv_tile");
     return DMCF_OK;
+}
+
+template <int MT, int NW>
+static int launch_cconv(const ConvParams& p, cudaStream_t st) {
+    switch (p.cip) {
+        case 1: return launch_cconv_cip<MT, NW, 1>(p, st);
+        case 2: return launch_cconv_cip<MT, NW, 2>(p, st);
+        case 4: return launch_cconv_cip<MT, NW, 4>(p, st);
+        case 8: return launch_cconv_cip<MT, NW, 8>(p, st);
+        case 16: return launch_cconv_cip<MT, NW, 16>(p, st);
+        default: return launch_cconv_cip<MT, NW, 32>(p, st);
+    }
 }
 
 }  // namespace dmcf
@@ -301,12 +354,13 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
 
     const size_t limit = 227 * 1024;
     cudaStream_t st = (cudaStream_t)stream;
-    // largest tile that fits (bigger tile = fewer passes over the filter); small patches prefer several CTAs per SM
-    if (conv_smem_bytes(32, p.kc_pad, p.cp) <= limit / 2) return launch_cconv<32>(p, conv_smem_bytes(32, p.kc_pad, p.cp), st);
-    if (conv_smem_bytes(32, p.kc_pad, p.cp) <= limit) return launch_cconv<32>(p, conv_smem_bytes(32, p.kc_pad, p.cp), st);
-    if (conv_smem_bytes(24, p.kc_pad, p.cp) <= limit) return launch_cconv<24>(p, conv_smem_bytes(24, p.kc_pad, p.cp), st);
-    if (conv_smem_bytes(16, p.kc_pad, p.cp) <= limit) return launch_cconv<16>(p, conv_smem_bytes(16, p.kc_pad, p.cp), st);
-    if (conv_smem_bytes(8, p.kc_pad, p.cp) <= limit) return launch_cconv<8>(p, conv_smem_bytes(8, p.kc_pad, p.cp), st);
+    // Largest tile that fits (bigger tile = fewer passes over the filter).  Small patches leave room for several
+    // 8-warp CTAs per SM; a patch tile that owns the SM runs 16 warps to hide the gather / filter latency.
+    if (conv_smem_bytes(32, 8, p.kc_pad, p.cp) <= limit / 2) return launch_cconv<32, 8>(p, st);
+    if (conv_smem_bytes(32, 16, p.kc_pad, p.cp) <= limit) return launch_cconv<32, 16>(p, st);
+    if (conv_smem_bytes(24, 16, p.kc_pad, p.cp) <= limit) return launch_cconv<24, 16>(p, st);
+    if (conv_smem_bytes(16, 16, p.kc_pad, p.cp) <= limit) return launch_cconv<16, 16>(p, st);
+    if (conv_smem_bytes(8, 16, p.kc_pad, p.cp) <= limit) return launch_cconv<8, 16>(p, st);
     return set_error(DMCF_ERR_UNSUPPORTED, "cconv: filter %dx%dx%dx%d needs %zu B of shared memory per 8 points (> %zu)",
-                     p.gp.kz, p.gp.ky, p.gp.kx, d->cin, conv_smem_bytes(8, p.kc_pad, p.cp), limit);
+                     p.gp.kz, p.gp.ky, p.gp.kx, d->cin, conv_smem_bytes(8, 16, p.kc_pad, p.cp), limit);
 }
