@@ -1,0 +1,253 @@
+// continuous_conv forward, register-patch variant for filters with a compile-time grid (4x4x4, 1x8x8, 1x8x1),
+// linear interpolation and 17..32 input channels -- the wide layers that dominate a DMCF step.
+//
+// Same tiling as k_cconv_tile (cconv.cu) but phase 1 keeps the whole trilinear patch of a point in REGISTERS:
+// one warp per out point, lane = input channel, acc[cell] for every filter cell.  The pair geometry is evaluated
+// lane-parallel for 32 neighbours and parked as compact records {row, base cell, 8 corner weights} in a per-warp
+// shared-memory scratch; the warp then walks the records (broadcast LDS.128), gathers the neighbour's feature row
+// (coalesced, four rows in flight) and a warp-uniform switch on the base cell turns the 8 corner updates into FFMAs
+// on statically indexed registers: no shared-memory read-modify-write and ~3x fewer instructions per pair than the
+// generic kernel.  The finished patch row is written once to shared memory for the shared phase 2 (patch x filter).
+#include "cconv_common.cuh"
+
+namespace dmcf {
+
+template <int KZ, int KY, int KX>
+struct FilterGrid {
+    static constexpr int K = KZ * KY * KX;
+    static constexpr int NBX = KX > 1 ? KX - 1 : 1, NBY = KY > 1 ? KY - 1 : 1, NBZ = KZ > 1 ? KZ - 1 : 1;
+    static constexpr int NB = NBX * NBY * NBZ;  // distinct "base" cells of the 2x2x2 corner block
+};
+
+// corner weights w[c], c = bx + 2*by + 4*bz, packed as wa = (w0..w3), wb = (w4..w7)
+template <int KZ, int KY, int KX, int B>
+__device__ __forceinline__ void scatter_case(float (&acc)[KZ * KY * KX], const float4& wa, const float4& wb, float f) {
+    using G = FilterGrid<KZ, KY, KX>;
+    if constexpr (B < G::NB) {
+        constexpr int x0 = B % G::NBX, y0 = (B / G::NBX) % G::NBY, z0 = B / (G::NBX * G::NBY);
+        constexpr int c000 = (z0 * KY + y0) * KX + x0;
+        constexpr int sx = 1, sy = KX, sz = KY * KX;
+        acc[c000] = fmaf(wa.x, f, acc[c000]);
+        if constexpr (KX > 1) acc[c000 + sx] = fmaf(wa.y, f, acc[c000 + sx]);
+        if constexpr (KY > 1) acc[c000 + sy] = fmaf(wa.z, f, acc[c000 + sy]);
+        if constexpr (KX > 1 && KY > 1) acc[c000 + sx + sy] = fmaf(wa.w, f, acc[c000 + sx + sy]);
+        if constexpr (KZ > 1) {
+            acc[c000 + sz] = fmaf(wb.x, f, acc[c000 + sz]);
+            if constexpr (KX > 1) acc[c000 + sz + sx] = fmaf(wb.y, f, acc[c000 + sz + sx]);
+            if constexpr (KY > 1) acc[c000 + sz + sy] = fmaf(wb.z, f, acc[c000 + sz + sy]);
+            if constexpr (KX > 1 && KY > 1) acc[c000 + sz + sx + sy] = fmaf(wb.w, f, acc[c000 + sz + sx + sy]);
+        }
+    }
+}
+
+#define DMCF_SC(i) \
+    case i:        \
+        scatter_case<KZ, KY, KX, i>(acc, wa, wb, f); \
+        break;
+#define DMCF_SC8(i) DMCF_SC(i) DMCF_SC(i + 1) DMCF_SC(i + 2) DMCF_SC(i + 3) DMCF_SC(i + 4) DMCF_SC(i + 5) DMCF_SC(i + 6) DMCF_SC(i + 7)
+
+template <int KZ, int KY, int KX>
+__device__ __forceinline__ void scatter_switch(int b, float (&acc)[KZ * KY * KX], const float4& wa, const float4& wb, float f) {
+    static_assert(FilterGrid<KZ, KY, KX>::NB <= 64, "too many base cells");
+    switch (b) {  // warp-uniform: every lane works on the same pair
+        DMCF_SC8(0) DMCF_SC8(8) DMCF_SC8(16) DMCF_SC8(24) DMCF_SC8(32) DMCF_SC8(40) DMCF_SC8(48) DMCF_SC8(56)
+        default: break;
+    }
+}
+
+// one axis of the base form: the corner block always starts at base <= fs-2; a pair clamped onto the last cell
+// (i0 == fs-1, folded weights) puts its whole weight on the upper corner.
+__device__ __forceinline__ void base_axis(int fs, int i0, float w0, float w1, int& base, float& lo, float& hi) {
+    if (fs == 1) {
+        base = 0; lo = w0 + w1; hi = 0.0f;
+    } else if (i0 > fs - 2) {
+        base = fs - 2; lo = 0.0f; hi = w0 + w1;
+    } else {
+        base = i0; lo = w0; hi = w1;
+    }
+}
+
+static constexpr int kRecWords = 12;  // {row, base, pad, pad, w0..w3, w4..w7}: 48 B, 16 B aligned, conflict-free STS.128
+
+template <int KZ, int KY, int KX, int MT, int NW, bool RED_ALIAS>
+__global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
+    using G = FilterGrid<KZ, KY, KX>;
+    extern __shared__ __align__(16) float smem[];
+    float* patch = smem;                                       // [MT][kc_pad] (also [NW][MT][cp] partial sums if RED_ALIAS)
+    const size_t patch_words = (RED_ALIAS && (size_t)NW * MT * p.cp > (size_t)MT * p.kc_pad) ? (size_t)NW * MT * p.cp
+                                                                                              : (size_t)MT * p.kc_pad;
+    float* scratch = patch + patch_words;                      // [NW][32][kRecWords]
+    float* norm = scratch + (size_t)NW * 32 * kRecWords;       // [MT]
+    float* red = RED_ALIAS ? patch : norm + MT;                // [NW][MT][cp]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile_base = (int64_t)blockIdx.x * MT;
+    float* rec = scratch + (size_t)warp * 32 * kRecWords;
+    const bool filter_nbr = p.nbr_hi > p.nbr_lo;
+    const bool lane_ci = lane < p.cin;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    for (int m = warp; m < MT; m += NW) {
+        const int64_t o = tile_base + m;
+        float* prow = patch + (size_t)m * p.kc_pad;
+        if (o >= p.n_out) {  // keep unused rows finite (they are multiplied, never stored)
+            for (int k = lane; k < p.kc_pad; k += 32) prow[k] = 0.0f;
+            continue;
+        }
+        float acc[G::K];
+#pragma unroll
+        for (int c = 0; c < G::K; ++c) acc[c] = 0.0f;
+        const float ox = __ldg(p.out_pos + 3 * o), oy = __ldg(p.out_pos + 3 * o + 1), oz = __ldg(p.out_pos + 3 * o + 2);
+        const int64_t rs = p.row_splits[o], re = p.row_splits[o + 1];
+        float fc = 0.0f;  // centre feature of the antisymmetric layer (out set == inp set)
+        if (p.ascc && lane_ci) {
+            fc = __ldg(p.inp_feat + o * p.inp_stride + lane);
+            if (p.relu_input) fc = fmaxf(fc, 0.0f);
+            fc *= p.feat_scale;
+        }
+        float norm_acc = 0.0f;
+        for (int64_t c0 = rs; c0 < re; c0 += 32) {
+            // ---- lane-parallel geometry of up to 32 neighbours -> compact records in the warp's scratch ----
+            const int64_t n = c0 + lane;
+            int row = -1, b = 0;
+            float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+            if (n < re) {
+                const int idx = __ldg(p.nbr_index + n);
+                bool keep = !filter_nbr || (idx >= p.nbr_lo && idx < p.nbr_hi);
+                const int prow_idx = filter_nbr ? idx - p.nbr_lo : idx;
+                if (keep) {
+                    const float dx = __ldg(p.inp_pos + 3 * (int64_t)prow_idx) - ox;
+                    const float dy = __ldg(p.inp_pos + 3 * (int64_t)prow_idx + 1) - oy;
+                    const float dz = __ldg(p.inp_pos + 3 * (int64_t)prow_idx + 2) - oz;
+                    if (p.skip_self && dx == 0.0f && dy == 0.0f && dz == 0.0f) keep = false;
+                    if (keep) {
+                        float a = 1.0f;
+                        if (p.nbr_importance) {
+                            a = __ldg(p.nbr_importance + n);
+                        } else if (p.window != DMCF_WIN_NONE) {
+                            const float q = __fdiv_rn(dist2_exact(dx, dy, dz), p.r2);
+                            a = window_value(p.window, p.window_fac, q);
+                        }
+                        norm_acc += (p.nbr_importance || p.window != DMCF_WIN_NONE) ? a : 1.0f;
+                        if (p.inp_importance) a *= __ldg(p.inp_importance + prow_idx);
+                        const PairGeom g = pair_geometry(p.gp, dx, dy, dz);
+                        int bx, by, bz;
+                        float xl, xh, yl, yh, zl, zh;
+                        base_axis(KX, g.i0 & 0xff, g.wx0, g.wx1, bx, xl, xh);
+                        base_axis(KY, (g.i0 >> 8) & 0xff, g.wy0, g.wy1, by, yl, yh);
+                        base_axis(KZ, (g.i0 >> 16) & 0xff, g.wz0, g.wz1, bz, zl, zh);
+                        zl *= a;
+                        zh *= a;
+                        b = (bz * G::NBY + by) * G::NBX + bx;
+                        wa = make_float4(xl * yl * zl, xh * yl * zl, xl * yh * zl, xh * yh * zl);
+                        wb = make_float4(xl * yl * zh, xh * yl * zh, xl * yh * zh, xh * yh * zh);
+                        row = prow_idx;
+                    }
+                }
+            }
+            const unsigned active = __ballot_sync(0xffffffffu, row >= 0);
+            const int cnt = __popc(active);
+            __syncwarp();  // previous chunk's records fully consumed
+            if (row >= 0) {
+                float* r = rec + __popc(active & lt_mask) * kRecWords;
+                *reinterpret_cast<int4*>(r) = make_int4(row, b, 0, 0);
+                *reinterpret_cast<float4*>(r + 4) = wa;
+                *reinterpret_cast<float4*>(r + 8) = wb;
+            }
+            __syncwarp();
+            // ---- walk the records: gather the feature row (4 in flight), scatter into the register patch ----
+            for (int j = 0; j < cnt; j += 4) {
+                int2 rb[4];
+                float fv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (j + u < cnt) {
+                        rb[u] = *reinterpret_cast<const int2*>(rec + (j + u) * kRecWords);
+                        fv[u] = lane_ci ? __ldg(p.inp_feat + (int64_t)rb[u].x * p.inp_stride + lane) : 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (j + u < cnt) {
+                        const float4 wa2 = *reinterpret_cast<const float4*>(rec + (j + u) * kRecWords + 4);
+                        const float4 wb2 = *reinterpret_cast<const float4*>(rec + (j + u) * kRecWords + 8);
+                        float f = fv[u];
+                        if (p.relu_input) f = fmaxf(f, 0.0f);
+                        f = fmaf(f, p.feat_scale, fc);
+                        scatter_switch<KZ, KY, KX>(rb[u].y, acc, wa2, wb2, f);
+                    }
+                }
+            }
+        }
+        // ---- patch row -> shared memory (lane = channel: conflict-free), Dense columns, padding ----
+        if (lane_ci) {
+#pragma unroll
+            for (int c = 0; c < G::K; ++c) prow[c * p.cin + lane] = acc[c];
+        }
+        if (p.dense_cin > 0) {
+            const float* drow = p.dense_inp + o * p.dense_stride;
+            for (int ci = lane; ci < p.dense_cin; ci += 32) {
+                float f = __ldg(drow + ci);
+                if (p.relu_input) f = fmaxf(f, 0.0f);
+                prow[p.kc_conv + ci] = f;
+            }
+        }
+        for (int k = p.kc + lane; k < p.kc_pad; k += 32) prow[k] = 0.0f;
+        if (p.normalize) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) norm_acc += __shfl_xor_sync(0xffffffffu, norm_acc, off);
+            if (lane == 0) norm[m] = norm_acc;
+        }
+    }
+    __syncthreads();
+    cconv_phase2<MT, NW, RED_ALIAS>(p, patch, red, norm, tile_base);
+}
+
+static size_t wide_smem_bytes(int mt, int nw, int kc_pad, int cp, bool alias) {
+    size_t patch = (size_t)mt * kc_pad, red = (size_t)nw * mt * cp;
+    size_t words = (size_t)nw * 32 * kRecWords + mt + (alias ? (patch > red ? patch : red) : patch + red);
+    return words * sizeof(float);
+}
+
+template <int KZ, int KY, int KX, int MT, int NW, bool ALIAS>
+static int launch_wide(const ConvParams& p, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_cconv_wide<KZ, KY, KX, MT, NW, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_wide)");
+        attr_set = true;
+    }
+    const int64_t tiles = ceil_div(p.n_out, MT);
+    k_cconv_wide<KZ, KY, KX, MT, NW, ALIAS><<<(unsigned)tiles, NW * 32, wide_smem_bytes(MT, NW, p.kc_pad, p.cp, ALIAS), st>>>(p);
+    DMCF_LAUNCH_CHECK("k_cconv_wide");
+    return DMCF_OK;
+}
+
+template <int KZ, int KY, int KX>
+static int launch_wide_grid(const ConvParams& p, cudaStream_t st, bool* handled) {
+    const size_t limit = 227 * 1024;
+    *handled = true;
+    if (p.cout <= 32) {  // partial sums may reuse the patch tile
+        if (wide_smem_bytes(32, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 32, 16, true>(p, st);
+        if (wide_smem_bytes(24, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 24, 16, true>(p, st);
+        if (wide_smem_bytes(16, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 16, 16, true>(p, st);
+    } else {
+        if (wide_smem_bytes(24, 16, p.kc_pad, p.cp, false) <= limit) return launch_wide<KZ, KY, KX, 24, 16, false>(p, st);
+        if (wide_smem_bytes(16, 16, p.kc_pad, p.cp, false) <= limit) return launch_wide<KZ, KY, KX, 16, 16, false>(p, st);
+    }
+    *handled = false;
+    return DMCF_OK;
+}
+
+// Tries the register-patch kernel; *handled = false means "not eligible, use the generic kernel".
+int launch_cconv_wide(const ConvParams& p, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (p.gp.interp != DMCF_INTERP_LINEAR || p.cin <= 16 || p.cin > 32) return DMCF_OK;
+    if (p.gp.kz == 4 && p.gp.ky == 4 && p.gp.kx == 4) return launch_wide_grid<4, 4, 4>(p, st, handled);
+    if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 8) return launch_wide_grid<1, 8, 8>(p, st, handled);
+    if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 1) return launch_wide_grid<1, 8, 1>(p, st, handled);
+    return DMCF_OK;
+}
+
+}  // namespace dmcf

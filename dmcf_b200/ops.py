@@ -359,5 +359,10 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
     return out
 
 
+def set_kernel_options(options):
+    """bit 0: register-patch kernel for wide layers (default on).  Returns the previous mask."""
+    return int(_lib.load().dmcf_set_kernel_options(int(options)))
+
+
 def launch_count():
     return int(_lib.load().dmcf_launch_count())

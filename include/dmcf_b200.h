@@ -134,6 +134,10 @@ int dmcf_cconv_forward(const dmcf_conv_desc* desc, const float* filters,
                        const float* residual, int64_t residual_stride,
                        float* out, int64_t out_stride, void* stream);
 
+/* Kernel selection bit mask (default 1): bit 0 = use the register-patch kernel for eligible wide layers; 0 forces the
+ * generic kernel everywhere.  Returns the previous mask.  Results agree to float32 rounding. */
+int dmcf_set_kernel_options(int options);
+
 /* ---------------------------------------------------------------------------------------------------
  * per-particle Dense:  out[n,:] = (relu_input ? max(x,0) : x) @ W[cin,cout] + b   (Keras layout)
  * ------------------------------------------------------------------------------------------------- */

@@ -126,12 +126,23 @@ CONV_CASES = [
     ("cout3", (6, 6, 6), 32, 3, "ball_to_cube_volume_preserving", "linear", True, False, "peak", True),
     ("sampling111", (1, 1, 1), 3, 3, "ball_to_cube_radial", "linear", True, True, "poly6", False),
     ("cubic_grad", (2, 2, 2), 2, 1, "ball_to_cube_radial", "linear", True, False, "cubic_grad", False),
+    ("wide188", (1, 8, 8), 32, 32, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False),
+    ("wide181", (1, 8, 1), 24, 16, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", True),
+    ("wide444_norm_radial", (4, 4, 4), 20, 40, "ball_to_cube_radial", "linear", False, True, "cubic", False),
 ]
+
+
+@pytest.fixture(params=[1, 0], ids=["wide-kernels", "generic-kernel"])
+def kernel_options(request):
+    from dmcf_b200 import ops
+    prev = ops.set_kernel_options(request.param)
+    yield request.param
+    ops.set_kernel_options(prev)
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 @pytest.mark.parametrize("fused_window", [False, True])
-def test_continuous_conv_matches_oracle(cuda, case, fused_window):
+def test_continuous_conv_matches_oracle(cuda, case, fused_window, kernel_options):
     from dmcf_b200 import ops
     name, ks, cin, cout, mapping, interp, align, normalize, window, ignore_q = case
     rng = np.random.default_rng(zlib.crc32(name.encode()))
@@ -167,7 +178,7 @@ def test_continuous_conv_matches_oracle(cuda, case, fused_window):
     feat_close(got.cpu().numpy(), ref, scale)
 
 
-def test_continuous_conv_fused_extras(cuda):
+def test_continuous_conv_fused_extras(cuda, kernel_options):
     """relu on the input, feature scale, neighbour sub-range, skip-self on a self-containing CSR, fused Dense,
     bias, residual, accumulate, strided in/out rows."""
     from dmcf_b200 import ops
@@ -212,7 +223,7 @@ def test_continuous_conv_fused_extras(cuda):
     assert float(out_wide[:, :3].abs().sum()) == 0 and float(out_wide[:, 3 + cout:].abs().sum()) == 0
 
 
-def test_ascc_fused_matches_reference_form_and_conserves(cuda):
+def test_ascc_fused_matches_reference_form_and_conserves(cuda, kernel_options):
     """Antisymmetric layer: fused (f_j + f_i) kernel vs the reference's two-pass form (utils/convolutions.py:433-458)
     and momentum conservation sum_i out_i = 0."""
     from dmcf_b200 import ops
