@@ -46,7 +46,10 @@ SIGNATURES = {
     "dmcf_exclusive_scan_i32_i64": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "dmcf_exclusive_scan_i32_i32": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "dmcf_cconv_forward": (c_i32, [C.POINTER(ConvDesc), c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp,
-                                   c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+                                   c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "dmcf_cconv_records_bytes": (c_sz, [c_i64]),
+    "dmcf_cconv_prepare": (c_i32, [C.POINTER(ConvDesc), c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
+                                   c_vp]),
     "dmcf_set_kernel_options": (c_i32, [c_i32]),
     "dmcf_dense_forward": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "dmcf_integrate": (c_i32, [c_vp, c_vp, c_vp, C.POINTER(c_f32), c_f32, c_i64, c_vp, c_vp, c_vp]),

@@ -41,7 +41,6 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_tile(const ConvParams p) {
     constexpr int cip = CIP, n_cg = (32 / CIP > 8) ? 8 : 32 / CIP;  // at most the 8 corners; extra lanes idle
     const int cg = lane / CIP, ci0 = lane % CIP;
     const bool lane_ok = cg < n_cg;
-    const bool filter_nbr = p.nbr_hi > p.nbr_lo;
     for (int m = warp; m < MT; m += NW) {
         const int64_t o = tile_base + m;
         if (o >= p.n_out) break;
@@ -53,36 +52,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_tile(const ConvParams p) {
         for (int64_t c0 = rs; c0 < re; c0 += 32) {
             // lane-parallel geometry for up to 32 neighbours
             const int64_t n = c0 + lane;
-            int row = -1;
-            PairGeom g;
-            g.i0 = g.i1 = 0;
-            g.wx0 = g.wx1 = g.wy0 = g.wy1 = g.wz0 = g.wz1 = 0.0f;
-            if (n < re) {
-                const int idx = __ldg(p.nbr_index + n);
-                bool keep = !filter_nbr || (idx >= p.nbr_lo && idx < p.nbr_hi);
-                const int prow_idx = filter_nbr ? idx - p.nbr_lo : idx;
-                if (keep) {
-                    const float dx = __ldg(p.inp_pos + 3 * (int64_t)prow_idx) - ox;
-                    const float dy = __ldg(p.inp_pos + 3 * (int64_t)prow_idx + 1) - oy;
-                    const float dz = __ldg(p.inp_pos + 3 * (int64_t)prow_idx + 2) - oz;
-                    if (p.skip_self && dx == 0.0f && dy == 0.0f && dz == 0.0f) keep = false;
-                    if (keep) {
-                        float a = 1.0f;
-                        if (p.nbr_importance) {
-                            a = __ldg(p.nbr_importance + n);
-                        } else if (p.window != DMCF_WIN_NONE) {
-                            const float q = __fdiv_rn(dist2_exact(dx, dy, dz), p.r2);
-                            a = window_value(p.window, p.window_fac, q);
-                        }
-                        norm_acc += (p.nbr_importance || p.window != DMCF_WIN_NONE) ? a : 1.0f;
-                        if (p.inp_importance) a *= __ldg(p.inp_importance + prow_idx);
-                        g = pair_geometry(p.gp, dx, dy, dz);
-                        g.wz0 *= a;
-                        g.wz1 *= a;
-                        row = prow_idx;
-                    }
-                }
-            }
+            const PairRec pr = pair_record(p, n, n < re, ox, oy, oz);
+            const int row = pr.row;
+            const PairGeom g = pr.g;
+            norm_acc += pr.norm;
             // broadcast the kept pairs four at a time (four independent feature gathers in flight per lane);
             // lanes own (corner group, input channel)
             unsigned todo = __ballot_sync(0xffffffffu, row >= 0);
@@ -203,19 +176,16 @@ static int launch_cconv(const ConvParams& p, cudaStream_t st) {
     }
 }
 
-int launch_cconv_wide(const ConvParams& p, cudaStream_t st, bool* handled);  // cconv_wide.cu
-std::atomic<int> g_kernel_options{1};
+int launch_cconv_wide(const ConvParams& p, cudaStream_t st, bool* handled);    // cconv_wide.cu
+int launch_cconv_direct(const ConvParams& p, cudaStream_t st, bool* handled);  // cconv_direct.cu
+std::atomic<int> g_kernel_options{3};
 
-}  // namespace dmcf
 
-using namespace dmcf;
 
-extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters, const float* out_positions, int64_t n_out,
-                                  const float* inp_positions, const float* inp_features, int64_t inp_stride, int64_t n_inp,
-                                  const float* inp_importance, const int32_t* neighbors_index,
-                                  const int64_t* neighbors_row_splits, const float* neighbors_importance, const float* bias,
-                                  const float* dense_inp, int64_t dense_stride, const float* residual, int64_t residual_stride,
-                                  float* out, int64_t out_stride, void* stream) {
+static int fill_params(const dmcf_conv_desc* d, const float* filters, const float* out_positions, int64_t n_out,
+                       const float* inp_positions, const float* inp_features, int64_t inp_stride, int64_t n_inp,
+                       const float* inp_importance, const int32_t* neighbors_index, const int64_t* neighbors_row_splits,
+                       const float* neighbors_importance, ConvParams* pp) {
     DMCF_REQUIRE(d != nullptr, "cconv: desc is NULL");
     DMCF_REQUIRE(d->kernel_size[0] >= 1 && d->kernel_size[1] >= 1 && d->kernel_size[2] >= 1 && d->kernel_size[0] <= 255 &&
                      d->kernel_size[1] <= 255 && d->kernel_size[2] <= 255,
@@ -229,13 +199,7 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
     DMCF_REQUIRE(!(d->normalize && d->dense_cin > 0), "cconv: normalize cannot be combined with a fused Dense");
     DMCF_REQUIRE(!(d->ascc && d->nbr_hi > d->nbr_lo), "cconv: ascc needs the full neighbour set");
     DMCF_REQUIRE(!(d->ascc && n_out != n_inp), "cconv: ascc needs out set == inp set");
-    DMCF_REQUIRE(d->dense_cin >= 0 && (d->dense_cin == 0 || dense_inp), "cconv: dense_inp is NULL");
-    if (n_out == 0) return DMCF_OK;
-    DMCF_REQUIRE(filters && out_positions && neighbors_row_splits && out, "cconv: NULL buffer");
-    DMCF_REQUIRE(n_inp == 0 || (inp_positions && inp_features && neighbors_index), "cconv: NULL input buffer");
-    DMCF_REQUIRE(inp_stride >= d->cin && out_stride >= d->cout, "cconv: row stride smaller than channel count");
-
-    ConvParams p;
+    ConvParams& p = *pp;
     memset(&p, 0, sizeof(p));
     p.gp.kz = d->kernel_size[0]; p.gp.ky = d->kernel_size[1]; p.gp.kx = d->kernel_size[2];
     p.gp.mapping = d->mapping; p.gp.interp = d->interpolation; p.gp.align_corners = d->align_corners;
@@ -260,16 +224,92 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
     p.filters = filters; p.out_pos = out_positions; p.inp_pos = inp_positions; p.inp_feat = inp_features;
     p.inp_stride = inp_stride; p.n_out = n_out; p.n_inp = n_inp; p.inp_importance = inp_importance;
     p.nbr_index = neighbors_index; p.row_splits = neighbors_row_splits; p.nbr_importance = neighbors_importance;
+    return DMCF_OK;
+}
+
+// one warp per out point, lanes over its neighbours: coalesced writes of the 9 record arrays
+__global__ void __launch_bounds__(256) k_cconv_prepare(const ConvParams p, float* __restrict__ records) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t P = p.n_pairs;
+    for (int64_t o = warp0; o < p.n_out; o += n_warps) {
+        const float ox = __ldg(p.out_pos + 3 * o), oy = __ldg(p.out_pos + 3 * o + 1), oz = __ldg(p.out_pos + 3 * o + 2);
+        const int64_t rs = p.row_splits[o], re = p.row_splits[o + 1];
+        for (int64_t n = rs + lane; n < re; n += 32) {
+            const PairRec r = eval_pair(p, n, true, ox, oy, oz);
+            float* f = records + n;
+            f[0] = __int_as_float(r.row);
+            f[P] = __int_as_float(r.g.i0);
+            f[2 * P] = __int_as_float(r.g.i1);
+            f[3 * P] = r.g.wx0; f[4 * P] = r.g.wx1;
+            f[5 * P] = r.g.wy0; f[6 * P] = r.g.wy1;
+            f[7 * P] = r.g.wz0; f[8 * P] = r.g.wz1;
+        }
+    }
+}
+
+}  // namespace dmcf
+
+using namespace dmcf;
+
+extern "C" size_t dmcf_cconv_records_bytes(int64_t n_pairs) {
+    return (size_t)(n_pairs > 0 ? n_pairs : 0) * kRecordFields * sizeof(float);
+}
+
+extern "C" int dmcf_cconv_prepare(const dmcf_conv_desc* d, const float* out_positions, int64_t n_out, const float* inp_positions,
+                                  int64_t n_inp, const float* inp_importance, const int32_t* neighbors_index,
+                                  const int64_t* neighbors_row_splits, const float* neighbors_importance, int64_t n_pairs,
+                                  float* records, void* stream) {
+    ConvParams p;
+    int rc = fill_params(d, nullptr, out_positions, n_out, inp_positions, nullptr, 0, n_inp, inp_importance, neighbors_index,
+                         neighbors_row_splits, neighbors_importance, &p);
+    if (rc) return rc;
+    DMCF_REQUIRE(!d->normalize, "cconv_prepare: records do not carry the normaliser; call cconv_forward without records");
+    DMCF_REQUIRE(n_pairs >= 0, "cconv_prepare: negative pair count");
+    if (n_out == 0 || n_pairs == 0) return DMCF_OK;
+    DMCF_REQUIRE(out_positions && inp_positions && neighbors_index && neighbors_row_splits && records, "cconv_prepare: NULL buffer");
+    p.n_pairs = n_pairs;
+    int64_t blocks = ceil_div(n_out, 8);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_cconv_prepare<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, records);
+    DMCF_LAUNCH_CHECK("k_cconv_prepare");
+    return DMCF_OK;
+}
+
+extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters, const float* out_positions, int64_t n_out,
+                                  const float* inp_positions, const float* inp_features, int64_t inp_stride, int64_t n_inp,
+                                  const float* inp_importance, const int32_t* neighbors_index,
+                                  const int64_t* neighbors_row_splits, const float* neighbors_importance, const float* bias,
+                                  const float* dense_inp, int64_t dense_stride, const float* residual, int64_t residual_stride,
+                                  float* out, int64_t out_stride, const float* pair_records, int64_t n_pairs, void* stream) {
+    ConvParams p;
+    int rc = fill_params(d, filters, out_positions, n_out, inp_positions, inp_features, inp_stride, n_inp, inp_importance,
+                         neighbors_index, neighbors_row_splits, neighbors_importance, &p);
+    if (rc) return rc;
+    DMCF_REQUIRE(d->dense_cin >= 0 && (d->dense_cin == 0 || dense_inp), "cconv: dense_inp is NULL");
+    DMCF_REQUIRE(!(pair_records && d->normalize), "cconv: pair records cannot be combined with normalize");
+    if (n_out == 0) return DMCF_OK;
+    DMCF_REQUIRE(filters && out_positions && neighbors_row_splits && out, "cconv: NULL buffer");
+    DMCF_REQUIRE(n_inp == 0 || (inp_features && (pair_records || (inp_positions && neighbors_index))), "cconv: NULL input buffer");
+    DMCF_REQUIRE(inp_stride >= d->cin && out_stride >= d->cout, "cconv: row stride smaller than channel count");
     p.bias = bias; p.dense_inp = dense_inp; p.dense_stride = dense_stride;
     p.residual = residual; p.residual_stride = residual_stride; p.out = out; p.out_stride = out_stride;
+    p.records = pair_records; p.n_pairs = n_pairs;
 
     const size_t limit = 227 * 1024;
     cudaStream_t st = (cudaStream_t)stream;
-    // register-patch kernel for the wide layers (dmcf_set_kernel_options(0) forces the generic kernel; the parity
-    // tests run both)
-    if (g_kernel_options.load(std::memory_order_relaxed) & 1) {
+    // specialised kernels (dmcf_set_kernel_options(0) forces the generic kernel; the parity tests run both)
+    const int options = g_kernel_options.load(std::memory_order_relaxed);
+    p.debug_wrap_w = (options >> 8) & 7;
+    if (options & 2) {  // resident-filter direct kernel for cout <= 4
         bool handled = false;
-        int rc = launch_cconv_wide(p, st, &handled);
+        rc = launch_cconv_direct(p, st, &handled);
+        if (rc || handled) return rc;
+    }
+    if (options & 1) {
+        bool handled = false;
+        rc = launch_cconv_wide(p, st, &handled);
         if (rc || handled) return rc;
     }
     // Largest tile that fits (bigger tile = fewer passes over the filter).  Small patches leave room for several

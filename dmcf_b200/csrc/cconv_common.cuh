@@ -13,6 +13,7 @@ struct ConvParams {
     float feat_scale;
     int ascc, skip_self, nbr_lo, nbr_hi, dense_cin, accumulate;
     int kc_conv, kc, kc_pad;  // patch columns: conv part, conv+dense, padded to 4
+    int debug_wrap_w;         // timing experiment switch (dmcf_set_kernel_options bit 8), never set in production
     int cip, cp;              // pow2 lane groupings for input / output channels
     const float* filters;
     const float* out_pos;
@@ -31,7 +32,77 @@ struct ConvParams {
     int64_t residual_stride;
     float* out;
     int64_t out_stride;
+    // optional precomputed pair records (dmcf_cconv_prepare): 9 arrays of n_pairs words
+    // {row, i0, i1, wx0, wx1, wy0, wy1, wz0*a, wz1*a}; row < 0 marks a dropped pair
+    const float* records;
+    int64_t n_pairs;
 };
+
+static constexpr int kRecordFields = 9;
+
+// One neighbour pair of an out point, ready for the scatter: feature row, corner cells and per-axis corner weights
+// with the pair's importance (window * neighbour importance * input importance) folded into the z weights.
+struct PairRec {
+    int row;      // input feature/position row, -1 = dropped (sub-range filter, skip-self, out of the list)
+    PairGeom g;
+    float norm;   // contribution to the normaliser (sum of neighbour importances / neighbour count)
+};
+
+// Evaluates pair `n` of the CSR list for the out point at (ox,oy,oz).
+__device__ __forceinline__ PairRec eval_pair(const ConvParams& p, int64_t n, bool in_range, float ox, float oy, float oz) {
+    PairRec r;
+    r.row = -1;
+    r.norm = 0.0f;
+    r.g.i0 = r.g.i1 = 0;
+    r.g.wx0 = r.g.wx1 = r.g.wy0 = r.g.wy1 = r.g.wz0 = r.g.wz1 = 0.0f;
+    if (!in_range) return r;
+    const bool filter_nbr = p.nbr_hi > p.nbr_lo;
+    const int idx = __ldg(p.nbr_index + n);
+    if (filter_nbr && (idx < p.nbr_lo || idx >= p.nbr_hi)) return r;
+    const int row = filter_nbr ? idx - p.nbr_lo : idx;
+    const float dx = __ldg(p.inp_pos + 3 * (int64_t)row) - ox;
+    const float dy = __ldg(p.inp_pos + 3 * (int64_t)row + 1) - oy;
+    const float dz = __ldg(p.inp_pos + 3 * (int64_t)row + 2) - oz;
+    if (p.skip_self && dx == 0.0f && dy == 0.0f && dz == 0.0f) return r;
+    float a = 1.0f;
+    if (p.nbr_importance) {
+        a = __ldg(p.nbr_importance + n);
+    } else if (p.window != DMCF_WIN_NONE) {
+        const float q = __fdiv_rn(dist2_exact(dx, dy, dz), p.r2);
+        a = window_value(p.window, p.window_fac, q);
+    }
+    r.norm = (p.nbr_importance || p.window != DMCF_WIN_NONE) ? a : 1.0f;
+    if (p.inp_importance) a *= __ldg(p.inp_importance + row);
+    r.g = pair_geometry(p.gp, dx, dy, dz);
+    r.g.wz0 *= a;
+    r.g.wz1 *= a;
+    r.row = row;
+    return r;
+}
+
+// Same pair from the precomputed record arrays (normaliser not stored: prepare refuses `normalize`).
+__device__ __forceinline__ PairRec load_pair(const ConvParams& p, int64_t n, bool in_range) {
+    PairRec r;
+    r.row = -1;
+    r.norm = 0.0f;
+    r.g.i0 = r.g.i1 = 0;
+    r.g.wx0 = r.g.wx1 = r.g.wy0 = r.g.wy1 = r.g.wz0 = r.g.wz1 = 0.0f;
+    if (!in_range) return r;
+    const float* f = p.records + n;
+    const int64_t P = p.n_pairs;
+    r.row = __float_as_int(__ldg(f));
+    if (r.row < 0) return r;
+    r.g.i0 = __float_as_int(__ldg(f + P));
+    r.g.i1 = __float_as_int(__ldg(f + 2 * P));
+    r.g.wx0 = __ldg(f + 3 * P); r.g.wx1 = __ldg(f + 4 * P);
+    r.g.wy0 = __ldg(f + 5 * P); r.g.wy1 = __ldg(f + 6 * P);
+    r.g.wz0 = __ldg(f + 7 * P); r.g.wz1 = __ldg(f + 8 * P);
+    return r;
+}
+
+__device__ __forceinline__ PairRec pair_record(const ConvParams& p, int64_t n, bool in_range, float ox, float oy, float oz) {
+    return p.records ? load_pair(p, n, in_range) : eval_pair(p, n, in_range, ox, oy, oz);
+}
 
 // ---- phase 2 + epilogue: [MT x kc] x [kc x cout], split-K over warps, lane = (k sub-slice, output channel) ----------
 // `red` may alias `patch` when RED_ALIASES_PATCH (only valid for cout <= 32: the patch is dead once every warp has
@@ -93,6 +164,102 @@ __device__ __forceinline__ void cconv_phase2(const ConvParams& p, const float* p
                 float v = 0.0f;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) v += red[((size_t)w * MT + m) * cp + c];
+                if (p.normalize) {
+                    const float nv = norm[m];
+                    if (nv != 0.0f) v /= nv;
+                }
+                if (p.bias) v += __ldg(p.bias + oc);
+                if (p.residual) v += __ldg(p.residual + o * p.residual_stride + oc);
+                float* dst = p.out + o * p.out_stride + oc;
+                if (p.accumulate) v += *dst;
+                *dst = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- phase 2, register-blocked variant used by k_cconv_wide ------------------------------------------------------------
+// Patch tile stored k-quad major: word((k, m)) = ((k >> 2) * (MT + 1) + m) * 4 + (k & 3)  (the +1 keeps the phase-1
+// stores conflict free), so the MT float4s of one k-quad sit at compile-time offsets: no address arithmetic in the
+// inner loop.  Lane = (point group pg = lane / 8, channel quad cq = lane % 8): each thread owns MT/4 points x 4 output
+// channels, filter rows arrive as LDG.128 (register double buffered), 16 FFMA per LDS.128.
+// Needs cout % 4 == 0 and a 16-byte aligned filter.  Split-K over warps, partial sums meet in `red` ([NW][MT][32]).
+template <int MT>
+__device__ __forceinline__ int patchq_index(int m, int k) {
+    return ((k >> 2) * (MT + 1) + m) * 4 + (k & 3);
+}
+
+template <int MT, int NW, bool RED_ALIASES_PATCH>
+__device__ __forceinline__ void cconv_phase2_v2(const ConvParams& p, const float* patchq, float* red, const float* norm,
+                                                int64_t tile_base) {
+    static_assert(MT % 4 == 0, "MT must be a multiple of 4");
+    constexpr int R = MT / 4, MTP = MT + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pg = lane >> 3, cq = lane & 7;
+    const int kq_total = p.kc_pad / 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int cb = 0; cb < p.cout; cb += 32) {
+        const int co0 = cb + cq * 4;
+        const bool co_ok = co0 < p.cout;
+        float acc[R][4];
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+        // filter rows as float4 (cout % 4 == 0, 16-byte aligned); whole k-quads below kq_full need no guards
+        const int row4 = p.cout >> 2;                      // float4s per filter row
+        const int kq_full = co_ok ? (p.kc >> 2) : 0;        // k-quads with all 4 rows present (0 disables the lane)
+        const float4* wbase = reinterpret_cast<const float4*>(p.filters) + (co0 >> 2);
+        const int dbg_mask = p.debug_wrap_w ? 7 : 0x7fffffff;  // timing experiment only: every tile re-reads 8 k-quads
+        auto load_w = [&](int kq, float4 (&w)[4]) {
+            if (kq < kq_full) {
+                const float4* wp = wbase + (size_t)(kq & dbg_mask) * 4 * row4;
+                w[0] = __ldg(wp); w[1] = __ldg(wp + row4); w[2] = __ldg(wp + 2 * row4); w[3] = __ldg(wp + 3 * row4);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    w[j] = (co_ok && kq * 4 + j < p.kc) ? __ldg(wbase + (size_t)(kq * 4 + j) * row4) : zero4;
+            }
+        };
+        int kq = warp;
+        float4 w[4] = {zero4, zero4, zero4, zero4};
+        if (kq < kq_total) load_w(kq, w);
+        while (kq < kq_total) {
+            const int kn = kq + NW;
+            float4 wn[4] = {zero4, zero4, zero4, zero4};
+            if (kn < kq_total) load_w(kn, wn);
+            const float4* pq = reinterpret_cast<const float4*>(patchq) + (size_t)kq * MTP + pg * R;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const float4 pv = pq[i];
+                acc[i][0] = fmaf(pv.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(pv.x, w[0].y, acc[i][1]);
+                acc[i][2] = fmaf(pv.x, w[0].z, acc[i][2]); acc[i][3] = fmaf(pv.x, w[0].w, acc[i][3]);
+                acc[i][0] = fmaf(pv.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(pv.y, w[1].y, acc[i][1]);
+                acc[i][2] = fmaf(pv.y, w[1].z, acc[i][2]); acc[i][3] = fmaf(pv.y, w[1].w, acc[i][3]);
+                acc[i][0] = fmaf(pv.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(pv.z, w[2].y, acc[i][1]);
+                acc[i][2] = fmaf(pv.z, w[2].z, acc[i][2]); acc[i][3] = fmaf(pv.z, w[2].w, acc[i][3]);
+                acc[i][0] = fmaf(pv.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(pv.w, w[3].y, acc[i][1]);
+                acc[i][2] = fmaf(pv.w, w[3].z, acc[i][2]); acc[i][3] = fmaf(pv.w, w[3].w, acc[i][3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = wn[j];
+            kq = kn;
+        }
+        if (RED_ALIASES_PATCH) __syncthreads();
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+            *reinterpret_cast<float4*>(red + ((size_t)warp * MT + pg * R + i) * 32 + cq * 4) =
+                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        __syncthreads();
+        for (int t = tid; t < MT * 32; t += NW * 32) {
+            const int m = t >> 5, c = t & 31;
+            const int64_t o = tile_base + m;
+            const int oc = cb + c;
+            if (o < p.n_out && oc < p.cout) {
+                float v = 0.0f;
+#pragma unroll
+                for (int w2 = 0; w2 < NW; ++w2) v += red[((size_t)w2 * MT + m) * 32 + c];
                 if (p.normalize) {
                     const float nv = norm[m];
                     if (nv != 0.0f) v /= nv;

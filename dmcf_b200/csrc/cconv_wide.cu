@@ -1,5 +1,5 @@
 // continuous_conv forward, register-patch variant for filters with a compile-time grid (4x4x4, 1x8x8, 1x8x1),
-// linear interpolation and 17..32 input channels -- the wide layers that dominate a DMCF step.
+// linear interpolation and <= 32 input channels -- the wide layers that dominate a DMCF step.
 //
 // Same tiling as k_cconv_tile (cconv.cu) but phase 1 keeps the whole trilinear patch of a point in REGISTERS:
 // one warp per out point, lane = input channel, acc[cell] for every filter cell.  The pair geometry is evaluated
@@ -73,25 +73,23 @@ template <int KZ, int KY, int KX, int MT, int NW, bool RED_ALIAS>
 __global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
     using G = FilterGrid<KZ, KY, KX>;
     extern __shared__ __align__(16) float smem[];
-    float* patch = smem;                                       // [MT][kc_pad] (also [NW][MT][cp] partial sums if RED_ALIAS)
-    const size_t patch_words = (RED_ALIAS && (size_t)NW * MT * p.cp > (size_t)MT * p.kc_pad) ? (size_t)NW * MT * p.cp
-                                                                                              : (size_t)MT * p.kc_pad;
+    float* patch = smem;  // k-quad major [kc_pad/4][MT+1][4] (also [NW][MT][32] partial sums if RED_ALIAS)
+    const size_t tile_words = (size_t)(p.kc_pad / 4) * (MT + 1) * 4, red_words = (size_t)NW * MT * 32;
+    const size_t patch_words = (RED_ALIAS && red_words > tile_words) ? red_words : tile_words;
     float* scratch = patch + patch_words;                      // [NW][32][kRecWords]
     float* norm = scratch + (size_t)NW * 32 * kRecWords;       // [MT]
-    float* red = RED_ALIAS ? patch : norm + MT;                // [NW][MT][cp]
+    float* red = RED_ALIAS ? patch : norm + MT;                // [NW][MT][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile_base = (int64_t)blockIdx.x * MT;
     float* rec = scratch + (size_t)warp * 32 * kRecWords;
-    const bool filter_nbr = p.nbr_hi > p.nbr_lo;
     const bool lane_ci = lane < p.cin;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     for (int m = warp; m < MT; m += NW) {
         const int64_t o = tile_base + m;
-        float* prow = patch + (size_t)m * p.kc_pad;
         if (o >= p.n_out) {  // keep unused rows finite (they are multiplied, never stored)
-            for (int k = lane; k < p.kc_pad; k += 32) prow[k] = 0.0f;
+            for (int k = lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
             continue;
         }
         float acc[G::K];
@@ -109,41 +107,20 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
         for (int64_t c0 = rs; c0 < re; c0 += 32) {
             // ---- lane-parallel geometry of up to 32 neighbours -> compact records in the warp's scratch ----
             const int64_t n = c0 + lane;
-            int row = -1, b = 0;
+            const PairRec pr = pair_record(p, n, n < re, ox, oy, oz);
+            const int row = pr.row;
+            norm_acc += pr.norm;
+            int b = 0;
             float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
-            if (n < re) {
-                const int idx = __ldg(p.nbr_index + n);
-                bool keep = !filter_nbr || (idx >= p.nbr_lo && idx < p.nbr_hi);
-                const int prow_idx = filter_nbr ? idx - p.nbr_lo : idx;
-                if (keep) {
-                    const float dx = __ldg(p.inp_pos + 3 * (int64_t)prow_idx) - ox;
-                    const float dy = __ldg(p.inp_pos + 3 * (int64_t)prow_idx + 1) - oy;
-                    const float dz = __ldg(p.inp_pos + 3 * (int64_t)prow_idx + 2) - oz;
-                    if (p.skip_self && dx == 0.0f && dy == 0.0f && dz == 0.0f) keep = false;
-                    if (keep) {
-                        float a = 1.0f;
-                        if (p.nbr_importance) {
-                            a = __ldg(p.nbr_importance + n);
-                        } else if (p.window != DMCF_WIN_NONE) {
-                            const float q = __fdiv_rn(dist2_exact(dx, dy, dz), p.r2);
-                            a = window_value(p.window, p.window_fac, q);
-                        }
-                        norm_acc += (p.nbr_importance || p.window != DMCF_WIN_NONE) ? a : 1.0f;
-                        if (p.inp_importance) a *= __ldg(p.inp_importance + prow_idx);
-                        const PairGeom g = pair_geometry(p.gp, dx, dy, dz);
-                        int bx, by, bz;
-                        float xl, xh, yl, yh, zl, zh;
-                        base_axis(KX, g.i0 & 0xff, g.wx0, g.wx1, bx, xl, xh);
-                        base_axis(KY, (g.i0 >> 8) & 0xff, g.wy0, g.wy1, by, yl, yh);
-                        base_axis(KZ, (g.i0 >> 16) & 0xff, g.wz0, g.wz1, bz, zl, zh);
-                        zl *= a;
-                        zh *= a;
-                        b = (bz * G::NBY + by) * G::NBX + bx;
-                        wa = make_float4(xl * yl * zl, xh * yl * zl, xl * yh * zl, xh * yh * zl);
-                        wb = make_float4(xl * yl * zh, xh * yl * zh, xl * yh * zh, xh * yh * zh);
-                        row = prow_idx;
-                    }
-                }
+            if (row >= 0) {
+                int bx, by, bz;
+                float xl, xh, yl, yh, zl, zh;
+                base_axis(KX, pr.g.i0 & 0xff, pr.g.wx0, pr.g.wx1, bx, xl, xh);
+                base_axis(KY, (pr.g.i0 >> 8) & 0xff, pr.g.wy0, pr.g.wy1, by, yl, yh);
+                base_axis(KZ, (pr.g.i0 >> 16) & 0xff, pr.g.wz0, pr.g.wz1, bz, zl, zh);
+                b = (bz * G::NBY + by) * G::NBX + bx;
+                wa = make_float4(xl * yl * zl, xh * yl * zl, xl * yh * zl, xh * yh * zl);
+                wb = make_float4(xl * yl * zh, xh * yl * zh, xl * yh * zh, xh * yh * zh);
             }
             const unsigned active = __ballot_sync(0xffffffffu, row >= 0);
             const int cnt = __popc(active);
@@ -156,6 +133,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
             }
             __syncwarp();
             // ---- walk the records: gather the feature row (4 in flight), scatter into the register patch ----
+            if (p.debug_wrap_w & 4) continue;  // timing experiment: geometry only
             for (int j = 0; j < cnt; j += 4) {
                 int2 rb[4];
                 float fv[4];
@@ -182,17 +160,17 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
         // ---- patch row -> shared memory (lane = channel: conflict-free), Dense columns, padding ----
         if (lane_ci) {
 #pragma unroll
-            for (int c = 0; c < G::K; ++c) prow[c * p.cin + lane] = acc[c];
+            for (int c = 0; c < G::K; ++c) patch[patchq_index<MT>(m, c * p.cin + lane)] = acc[c];
         }
         if (p.dense_cin > 0) {
             const float* drow = p.dense_inp + o * p.dense_stride;
             for (int ci = lane; ci < p.dense_cin; ci += 32) {
                 float f = __ldg(drow + ci);
                 if (p.relu_input) f = fmaxf(f, 0.0f);
-                prow[p.kc_conv + ci] = f;
+                patch[patchq_index<MT>(m, p.kc_conv + ci)] = f;
             }
         }
-        for (int k = p.kc + lane; k < p.kc_pad; k += 32) prow[k] = 0.0f;
+        for (int k = p.kc + lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
         if (p.normalize) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) norm_acc += __shfl_xor_sync(0xffffffffu, norm_acc, off);
@@ -200,11 +178,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
         }
     }
     __syncthreads();
-    cconv_phase2<MT, NW, RED_ALIAS>(p, patch, red, norm, tile_base);
+    if (p.debug_wrap_w & 2) return;  // timing experiment: phase 1 only
+    cconv_phase2_v2<MT, NW, RED_ALIAS>(p, patch, red, norm, tile_base);
 }
 
 static size_t wide_smem_bytes(int mt, int nw, int kc_pad, int cp, bool alias) {
-    size_t patch = (size_t)mt * kc_pad, red = (size_t)nw * mt * cp;
+    (void)cp;
+    size_t patch = (size_t)(kc_pad / 4) * (mt + 1) * 4, red = (size_t)nw * mt * 32;
     size_t words = (size_t)nw * 32 * kRecWords + mt + (alias ? (patch > red ? patch : red) : patch + red);
     return words * sizeof(float);
 }
@@ -230,10 +210,11 @@ static int launch_wide_grid(const ConvParams& p, cudaStream_t st, bool* handled)
     *handled = true;
     if (p.cout <= 32) {  // partial sums may reuse the patch tile
         if (wide_smem_bytes(32, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 32, 16, true>(p, st);
-        if (wide_smem_bytes(24, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 24, 16, true>(p, st);
+        if (wide_smem_bytes(24, 12, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 24, 12, true>(p, st);  // 2 points per warp
+        if (wide_smem_bytes(20, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 20, 16, true>(p, st);
         if (wide_smem_bytes(16, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 16, 16, true>(p, st);
     } else {
-        if (wide_smem_bytes(24, 16, p.kc_pad, p.cp, false) <= limit) return launch_wide<KZ, KY, KX, 24, 16, false>(p, st);
+        if (wide_smem_bytes(24, 12, p.kc_pad, p.cp, false) <= limit) return launch_wide<KZ, KY, KX, 24, 12, false>(p, st);
         if (wide_smem_bytes(16, 16, p.kc_pad, p.cp, false) <= limit) return launch_wide<KZ, KY, KX, 16, 16, false>(p, st);
     }
     *handled = false;
@@ -243,7 +224,8 @@ static int launch_wide_grid(const ConvParams& p, cudaStream_t st, bool* handled)
 // Tries the register-patch kernel; *handled = false means "not eligible, use the generic kernel".
 int launch_cconv_wide(const ConvParams& p, cudaStream_t st, bool* handled) {
     *handled = false;
-    if (p.gp.interp != DMCF_INTERP_LINEAR || p.cin <= 16 || p.cin > 32) return DMCF_OK;
+    if (p.gp.interp != DMCF_INTERP_LINEAR || p.cin > 32) return DMCF_OK;
+    if (p.cout % 4 != 0 || ((uintptr_t)p.filters & 15) != 0) return DMCF_OK;  // phase 2 reads filter rows as float4
     if (p.gp.kz == 4 && p.gp.ky == 4 && p.gp.kx == 4) return launch_wide_grid<4, 4, 4>(p, st, handled);
     if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 8) return launch_wide_grid<1, 8, 8>(p, st, handled);
     if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 1) return launch_wide_grid<1, 8, 1>(p, st, handled);

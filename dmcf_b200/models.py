@@ -91,6 +91,7 @@ class _StepCache:
     def __init__(self):
         self.cells = {}
         self.nns = {}
+        self.recs = {}
 
     def search(self, key, inp_pos, out_pos, radius):
         k = (key, float(radius))
@@ -101,6 +102,17 @@ class _StepCache:
             self.nns[k] = ops.fixed_radius_search(inp_pos, out_pos, radius, ignore_query_point=False,
                                                   return_distances=False, cell_list=self.cells[ck])
         return self.nns[k]
+
+    def records(self, key, nns, kernel_size, inp_pos, out_pos, extent, mapping, interpolation, window, skip_self):
+        """Pair geometry shared by every conv on the same (neighbour list, filter grid, window)."""
+        k = (key, tuple(kernel_size), float(extent), mapping, interpolation, window.typ if window else None,
+             window.fac if window else 1.0, bool(skip_self))
+        if k not in self.recs:
+            self.recs[k] = ops.prepare_pair_records(
+                kernel_size, out_pos, extent, None, inp_pos, None, nns.neighbors_index, None, nns.neighbors_row_splits,
+                align_corners=True, coordinate_mapping=mapping, interpolation=interpolation,
+                window=window.typ if window else None, window_fac=window.fac if window else 1.0, skip_self=skip_self)
+        return self.recs[k]
 
 
 class PBFNet(BaseModel):
@@ -291,12 +303,14 @@ class PBFNet(BaseModel):
             w, b = self._input_weights(cf, cb)
             nns = self._step.search((0, 0), all_pos, all_pos, 0.5 * ext0)
             win = self.fluid_convs.window_function
+            recs = self._step.records((0, 0), nns, self.kernel_size, all_pos, all_pos, ext0, self.coordinate_mapping,
+                                      self.interpolation, win, self.ignore_query_points)
             feats_out = ops.continuous_conv(
                 w, all_pos, ext0, None, all_pos, x, None, nns.neighbors_index, None, nns.neighbors_row_splits,
                 align_corners=True, coordinate_mapping=self.coordinate_mapping, normalize=False,
                 interpolation=self.interpolation, window=win.typ if win else None, window_fac=win.fac if win else 1.0,
                 feat_scale=self.part_scale, skip_self=self.ignore_query_points, bias=b, dense_inp=x,
-                dense_cin=cf + cb, kernel_size=self.kernel_size)
+                dense_cin=cf + cb, kernel_size=self.kernel_size, pair_records=recs)
         src = all_pos if self.use_bnds else pos
         dilated_pos, _, idx = get_dilated_pos(src, self.strides, voxel_size=self.voxel_size,
                                               centralize=self.centralize, pad=self.sample_pad, hyst=self.sample_hyst)
@@ -370,14 +384,17 @@ class PBFNet(BaseModel):
         w, b = self._block_weights(conv, dense)
         nns = self._step.search(key, inp_pos, out_pos, 0.5 * float(extent))
         win = conv.window_function
+        skip = bool(conv.radius_search_ignore_query_points and same_set)
+        recs = self._step.records(key, nns, conv.kernel_size, inp_pos, out_pos, float(extent), self.coordinate_mapping,
+                                  self.interpolation, win, skip)
         return ops.continuous_conv(
             w, out_pos, float(extent), None, inp_pos, x, None, nns.neighbors_index, None, nns.neighbors_row_splits,
             align_corners=True, coordinate_mapping=self.coordinate_mapping, normalize=False,
             interpolation=self.interpolation, window=win.typ if win else None, window_fac=win.fac if win else 1.0,
             relu_input=relu, feat_scale=scale, ascc=ascc,
-            skip_self=bool(conv.radius_search_ignore_query_points and same_set), bias=b,
+            skip_self=skip, bias=b,
             dense_inp=x if dense is not None else None, dense_cin=x.shape[1] if dense is not None else 0,
-            residual=residual, out=out, accumulate=accumulate, kernel_size=conv.kernel_size)
+            residual=residual, out=out, accumulate=accumulate, kernel_size=conv.kernel_size, pair_records=recs)
 
     # -- postprocess: models/pbf_model.py:440-489 -----------------------------------------------------------------
     def postprocess(self, prev, data, training=False, **kwargs):

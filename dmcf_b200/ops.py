@@ -173,7 +173,7 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
                     coordinate_mapping="ball_to_cube_radial", normalize=False, interpolation="linear",
                     max_temp_mem_MB=64, *, window=None, window_fac=1.0, relu_input=False, feat_scale=1.0,
                     ascc=False, skip_self=False, nbr_range=None, bias=None, dense_inp=None, dense_cin=0,
-                    residual=None, out=None, accumulate=False, kernel_size=None):
+                    residual=None, out=None, accumulate=False, kernel_size=None, pair_records=None):
     """``ml3d.ops.continuous_conv`` (kwargs as assembled at utils/convolutions.py:414-429) plus keyword-only fused
     extras (see include/dmcf_b200.h).  ``filters`` is [kz,ky,kx,Cin,Cout] or, with a fused Dense, the flattened
     [(kz*ky*kx*Cin + dense_cin), Cout] matrix together with ``kernel_size``."""
@@ -261,15 +261,60 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
                    residual=residual is not None, start=torch.cuda.Event(enable_timing=True),
                    end=torch.cuda.Event(enable_timing=True))
         rec["start"].record()
+    n_pairs = 0
+    if pair_records is not None:
+        _req(pair_records, "pair_records", dim=2)
+        n_pairs = int(neighbors_index.shape[0])
+        if tuple(pair_records.shape) != (9, n_pairs) or not pair_records.is_contiguous():
+            raise ValueError("pair_records must be a contiguous [9, n_pairs] tensor from prepare_pair_records")
     check(lib.dmcf_cconv_forward(C.byref(d), _p(filters), _p(out_positions), n_out, _p(inp_positions),
                                  _p(inp_features), inp_stride, n_inp, _p(inp_importance),
                                  _p(neighbors_index), _p(neighbors_row_splits),
                                  _p(neighbors_importance), _p(bias), _p(dense_inp) if dense_cin else None,
-                                 dense_stride, _p(residual), res_stride, _p(out), out_stride, _stream()))
+                                 dense_stride, _p(residual), res_stride, _p(out), out_stride, _p(pair_records), n_pairs,
+                                 _stream()))
     if rec is not None:
         rec["end"].record()
         PROFILE.append(rec)
     return out
+
+
+def prepare_pair_records(kernel_size, out_positions, extents, offset, inp_positions, inp_importance, neighbors_index,
+                         neighbors_importance, neighbors_row_splits, align_corners=True,
+                         coordinate_mapping="ball_to_cube_radial", interpolation="linear", *, window=None, window_fac=1.0,
+                         skip_self=False, nbr_range=None):
+    """Per-pair geometry of a neighbour list, evaluated once and shared by every conv with the same geometry arguments
+    (dmcf_cconv_prepare).  Returns a [9, n_pairs] float32 tensor to pass as ``pair_records`` to continuous_conv."""
+    lib = _lib.load()
+    out_positions = _pos(out_positions, "out_positions")
+    inp_positions = _pos(inp_positions, "inp_positions")
+    _req(neighbors_index, "neighbors_index", torch.int32, 1)
+    _req(neighbors_row_splits, "neighbors_row_splits", torch.int64, 1)
+    neighbors_index = neighbors_index.contiguous()
+    neighbors_row_splits = neighbors_row_splits.contiguous()
+    if inp_importance is not None and inp_importance.numel() == 0:
+        inp_importance = None
+    if neighbors_importance is not None and neighbors_importance.numel() == 0:
+        neighbors_importance = None
+    d = ConvDesc()
+    d.kernel_size[:] = [int(k) for k in kernel_size]
+    d.cin, d.cout = 1, 1
+    d.mapping = MAPPINGS[coordinate_mapping]
+    d.interpolation = INTERPOLATIONS[interpolation]
+    d.align_corners = int(bool(align_corners))
+    d.window = WINDOWS[window]
+    d.window_fac = float(window_fac)
+    d.extent = float(torch.as_tensor(extents).reshape(-1)[0])
+    d.offset[:] = [0.0, 0.0, 0.0] if offset is None else [float(v) for v in torch.as_tensor(offset).reshape(-1).tolist()]
+    d.feat_scale = 1.0
+    d.skip_self = int(bool(skip_self))
+    d.nbr_lo, d.nbr_hi = (0, 0) if nbr_range is None else (int(nbr_range[0]), int(nbr_range[1]))
+    n_pairs = int(neighbors_index.shape[0])
+    records = torch.empty((9, n_pairs), dtype=torch.float32, device=out_positions.device)
+    check(lib.dmcf_cconv_prepare(C.byref(d), _p(out_positions), out_positions.shape[0], _p(inp_positions),
+                                 inp_positions.shape[0], _p(inp_importance), _p(neighbors_index), _p(neighbors_row_splits),
+                                 _p(neighbors_importance), n_pairs, _p(records), _stream()))
+    return records
 
 
 def dense(x, kernel, bias=None, relu_input=False, out=None):

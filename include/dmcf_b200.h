@@ -132,10 +132,23 @@ int dmcf_cconv_forward(const dmcf_conv_desc* desc, const float* filters,
                        const float* neighbors_importance,
                        const float* bias, const float* dense_inp, int64_t dense_stride,
                        const float* residual, int64_t residual_stride,
-                       float* out, int64_t out_stride, void* stream);
+                       float* out, int64_t out_stride,
+                       const float* pair_records, int64_t n_pairs, void* stream);
 
-/* Kernel selection bit mask (default 1): bit 0 = use the register-patch kernel for eligible wide layers; 0 forces the
- * generic kernel everywhere.  Returns the previous mask.  Results agree to float32 rounding. */
+/* Optional: evaluate the per-pair geometry (coordinate mapping, trilinear corner cells/weights, window / importances,
+ * sub-range and skip-self filtering) ONCE for a neighbour list and reuse it for every conv that shares the list and the
+ * geometry fields of `desc` (kernel_size, mapping, interpolation, align_corners, extent, offset, window*, skip_self,
+ * nbr_lo/hi) -- e.g. the input conv and the three CConv layers of one DMCF step.  `records` holds
+ * dmcf_cconv_records_bytes(n_pairs) bytes (9 float arrays of n_pairs).  Pass it as `pair_records` to
+ * dmcf_cconv_forward; positions / neighbors_index / importances are then not read.  Not available with `normalize`. */
+size_t dmcf_cconv_records_bytes(int64_t n_pairs);
+int dmcf_cconv_prepare(const dmcf_conv_desc* desc, const float* out_positions, int64_t n_out,
+                       const float* inp_positions, int64_t n_inp, const float* inp_importance,
+                       const int32_t* neighbors_index, const int64_t* neighbors_row_splits,
+                       const float* neighbors_importance, int64_t n_pairs, float* records, void* stream);
+
+/* Kernel selection bit mask (default 3): bit 0 = register-patch kernel for compile-time filter grids (k_cconv_wide),
+ * bit 1 = resident-filter direct kernel for cout <= 4 (k_cconv_direct); 0 forces the generic kernel everywhere.  Returns the previous mask.  Results agree to float32 rounding. */
 int dmcf_set_kernel_options(int options);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -129,10 +129,13 @@ CONV_CASES = [
     ("wide188", (1, 8, 8), 32, 32, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False),
     ("wide181", (1, 8, 1), 24, 16, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", True),
     ("wide444_norm_radial", (4, 4, 4), 20, 40, "ball_to_cube_radial", "linear", False, True, "cubic", False),
+    ("direct_cout1_cin40", (3, 3, 3), 40, 1, "ball_to_cube_radial", "linear", True, True, "poly6", False),
+    ("direct_cout2_188", (1, 8, 8), 32, 2, "ball_to_cube_volume_preserving", "linear", True, False, "peak", True),
+    ("direct_cout4_border", (3, 3, 3), 6, 4, "ball_to_cube_radial", "linear_border", False, False, "peak", True),
 ]
 
 
-@pytest.fixture(params=[1, 0], ids=["wide-kernels", "generic-kernel"])
+@pytest.fixture(params=[3, 0], ids=["fast-kernels", "generic-kernel"])
 def kernel_options(request):
     from dmcf_b200 import ops
     prev = ops.set_kernel_options(request.param)
@@ -176,6 +179,13 @@ def test_continuous_conv_matches_oracle(cuda, case, fused_window, kernel_options
                                   t(imp.astype(np.float32)), t(splits), **kw)
     scale = 4.0 if cin * np.prod(ks) > 4096 else 1.0  # very long float32 dot products (cin96: K = 6144)
     feat_close(got.cpu().numpy(), ref, scale)
+    if not normalize and (fused_window or window is None):
+        # same conv through precomputed pair records (dmcf_cconv_prepare): bit-identical to the on-the-fly geometry
+        recs = ops.prepare_pair_records(ks, t(outp), float(extent), None, t(pts), None, t(idx), None, t(splits),
+                                        align_corners=align, coordinate_mapping=mapping, interpolation=interp, window=window)
+        got2 = ops.continuous_conv(t(filt), t(outp), float(extent), None, t(pts), t(feats), None, t(idx), None, t(splits),
+                                   window=window, pair_records=recs, **kw)
+        assert torch.equal(got, got2)
 
 
 def test_continuous_conv_fused_extras(cuda, kernel_options):

@@ -265,7 +265,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.dmcf_version() == 100
     # error path without a GPU: invalid arguments are rejected before any CUDA call
     import ctypes as C
-    rc = lib.dmcf_cconv_forward(None, None, None, 0, None, None, 0, 0, None, None, None, None, None, None, 0, None, 0, None, 0, None)
+    rc = lib.dmcf_cconv_forward(None, None, None, 0, None, None, 0, 0, None, None, None, None, None, None, 0, None, 0, None, 0, None, 0, None)
     assert rc == 1 and b"desc" in lib.dmcf_last_error()
 
 
