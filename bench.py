@@ -190,9 +190,17 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
 
-    scene, cfg = build_workload(args.n_side, seed=rank)
+    if world > 1:
+        from dmcf_b200 import scenes
+        from dmcf_b200.slab import SlabContext
+        scene, faces = scenes.slab_scene(args.n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0)
+        cfg = scenes.c4_model_cfg()
+    else:
+        scene, cfg = build_workload(args.n_side, seed=rank)
     model = config.build_model(cfg)
     model.init_weights(seed=0, device=dev, scale=0.1)
+    if world > 1:
+        model.set_slab(SlabContext(faces, axis=0))
     sim = Simulator(model, device=f"cuda:{local_rank}")
     n_fluid = scene["pos"].shape[0]
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
@@ -299,7 +307,9 @@ def main():
             "config": {"workload": f"C4: synthetic 3-D box, {args.n_side}^3 = {n_fluid} fluid + {scene['box'].shape[0]} wall particles per "
                                    "GPU, single-scale SymNet (input convs, 3x CConv 4x4x4 ->32 + Dense, ASCC 6x6x6 32->3), r=0.1, "
                                    "seeded random weights",
-                       "parallelism": f"slab x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"{world} spatial slabs along x of one {world}x{args.n_side} x {args.n_side} x {args.n_side} box, "
+                                       "position halo per step + feature halo per conv layer over NCCL send/recv")
+                       if world > 1 else "single GPU",
                        "l2": "per-step working set (features 136 MB/layer + 140 MB neighbour list) exceeds the 126 MB L2; "
                              "no explicit flush",
                        "state": "every step restarts from the same resident scene (fixed work per step)"},

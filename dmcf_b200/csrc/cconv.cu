@@ -198,7 +198,7 @@ static int fill_params(const dmcf_conv_desc* d, const float* filters, const floa
     DMCF_REQUIRE(n_out >= 0 && n_inp >= 0, "cconv: negative point count");
     DMCF_REQUIRE(!(d->normalize && d->dense_cin > 0), "cconv: normalize cannot be combined with a fused Dense");
     DMCF_REQUIRE(!(d->ascc && d->nbr_hi > d->nbr_lo), "cconv: ascc needs the full neighbour set");
-    DMCF_REQUIRE(!(d->ascc && n_out != n_inp), "cconv: ascc needs out set == inp set");
+    DMCF_REQUIRE(!(d->ascc && n_out > n_inp), "cconv: ascc needs out point o == input row o (out set a prefix of the inp set)");
     ConvParams& p = *pp;
     memset(&p, 0, sizeof(p));
     p.gp.kz = d->kernel_size[0]; p.gp.ky = d->kernel_size[1]; p.gp.kx = d->kernel_size[2];

@@ -154,6 +154,7 @@ class PBFNet(BaseModel):
         self.rest_dens, self.stiffness = rest_dens, stiffness
         self.dens_radius = dens_radius if dens_radius is not None else particle_radii
         self.fused = fused
+        self.slab = None  # dmcf_b200.slab.SlabContext for multi-GPU runs (set_slab)
         self.num_fluid_neighbors = None
         self._all_convs = []
         self._box_cache = None
@@ -167,6 +168,17 @@ class PBFNet(BaseModel):
 
     def setup(self):
         return
+
+    def set_slab(self, slab):
+        """Multi-GPU: this rank owns one spatial slab; convs see [owned | ghost] inputs (dmcf_b200/slab.py)."""
+        if slab is not None and slab.world > 1:
+            if len(self.strides) != 1 or self.strides[0] != 1:
+                raise NotImplementedError("slab decomposition currently covers single-scale nets (strides: [1]); "
+                                          "multi-scale lattices need per-scale ownership (SURVEY 8e)")
+            if not self.use_bnds:
+                raise NotImplementedError("slab decomposition with use_bnds=False")
+            self.fused = True
+        self.slab = slab
 
     # -- layer factory: models/pbf_model.py:197-224 --------------------------------------------------------
     def get_cconv(self, name, kernel_size=None, activation=None, ignore_query_points=None, window_func=None,
@@ -264,9 +276,16 @@ class PBFNet(BaseModel):
         pos, vel = self.integrate_pos_vel(_pos, _vel, acc)
         filter_extent = [np.float32(r) * np.float32(2) for r in self.particle_radii]
         e_last = float(filter_extent[-1])
-        if pos.shape[0] > 0:
-            lo, hi = pos.amin(dim=0) - e_last, pos.amax(dim=0) + e_last
-            fltr = ((box >= lo) & (box <= hi)).all(dim=1)
+        slab = self.slab if (self.slab is not None and self.slab.world > 1) else None
+        if pos.shape[0] > 0 or slab is not None:
+            if pos.shape[0] > 0:
+                lo, hi = pos.amin(dim=0), pos.amax(dim=0)
+            else:
+                inf = torch.full((3,), float("inf"), device=pos.device)
+                lo, hi = inf, -inf
+            if slab is not None:  # the cull uses the GLOBAL fluid bounding box (models/pbf_model.py:330-334)
+                lo, hi = slab.all_reduce_minmax(lo, hi)
+            fltr = ((box >= lo - e_last) & (box <= hi + e_last)).all(dim=1)
             box, bfeats = box[fltr], bfeats[fltr]
         n_f, n_b = pos.shape[0], box.shape[0]
         fluid_feats = [torch.ones_like(pos[:, :1])]
@@ -301,12 +320,17 @@ class PBFNet(BaseModel):
             x[:n_f, :cf] = fluid_feats
             x[n_f:, cf:] = box_feats
             w, b = self._input_weights(cf, cb)
-            nns = self._step.search((0, 0), all_pos, all_pos, 0.5 * ext0)
+            all_in = all_pos
+            if slab is not None:  # ghosts of the two neighbouring slabs: positions once per step, features per layer
+                all_in = torch.cat([all_pos, slab.position_halo(all_pos, 0.5 * ext0)], dim=0)
+                x = slab.with_ghosts(x)
+            self._all_in = all_in
+            nns = self._step.search((0, 0), all_in, all_pos, 0.5 * ext0)
             win = self.fluid_convs.window_function
-            recs = self._step.records((0, 0), nns, self.kernel_size, all_pos, all_pos, ext0, self.coordinate_mapping,
+            recs = self._step.records((0, 0), nns, self.kernel_size, all_in, all_pos, ext0, self.coordinate_mapping,
                                       self.interpolation, win, self.ignore_query_points)
             feats_out = ops.continuous_conv(
-                w, all_pos, ext0, None, all_pos, x, None, nns.neighbors_index, None, nns.neighbors_row_splits,
+                w, all_pos, ext0, None, all_in, x, None, nns.neighbors_index, None, nns.neighbors_row_splits,
                 align_corners=True, coordinate_mapping=self.coordinate_mapping, normalize=False,
                 interpolation=self.interpolation, window=win.typ if win else None, window_fac=win.fac if win else 1.0,
                 feat_scale=self.part_scale, skip_self=self.ignore_query_points, bias=b, dense_inp=x,
@@ -382,6 +406,10 @@ class PBFNet(BaseModel):
         if dense is not None and dense.kernel is None:
             dense.build(x.shape[1], x.device)
         w, b = self._block_weights(conv, dense)
+        if self.slab is not None and self.slab.world > 1:
+            # owned rows out, [owned | ghost] rows in: refresh the ghost rows of this layer's input from the neighbours
+            x = self.slab.with_ghosts(x)
+            inp_pos = self._all_in
         nns = self._step.search(key, inp_pos, out_pos, 0.5 * float(extent))
         win = conv.window_function
         skip = bool(conv.radius_search_ignore_query_points and same_set)

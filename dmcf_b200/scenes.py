@@ -51,3 +51,22 @@ def c4_model_cfg():
                 window="poly6", window_sym="peak", strides=[1], particle_radii=[0.1], timestep=0.02, grav=-9.81,
                 out_scale=[0.0078125] * 3, centralize=True, voxel_size=[0.025] * 3, sym_axis=1, add_merge=True,
                 use_acc=False)
+
+
+def slab_scene(n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0):
+    """Rank ``rank``'s share of a (world*n_side) x n_side x n_side box split into slabs along x (weak scaling: every
+    rank owns n_side^3 fluid particles).  Walls exist on the outer faces only; wall particles are owned by
+    coordinate.  Returns (scene dict, slab faces along x)."""
+    length = n_side * dx
+    sc = lattice_scene((n_side, n_side, n_side), dx=dx, jitter=jitter, vel_sigma=vel_sigma, seed=seed + rank,
+                       origin=(rank * length, 0.0, 0.0))
+    lo = np.zeros(3)
+    hi = np.array([world * length, length, length])
+    box, normals = _walls(lo, hi, dx, [0, 1, 2])
+    inf = float("inf")
+    faces = [-inf] + [k * length for k in range(1, world)] + [inf]
+    own = (box[:, 0] >= faces[rank]) & (box[:, 0] < faces[rank + 1])
+    # jitter must not push a fluid particle across a face (ownership is by coordinate)
+    sc["pos"][:, 0] = np.clip(sc["pos"][:, 0], rank * length + 1e-4, (rank + 1) * length - 1e-4)
+    sc["box"], sc["box_normals"] = box[own], normals[own]
+    return sc, faces

@@ -40,6 +40,13 @@ class Simulator:
         """One model call on one sample ``[pos, vel, acc|None, feats|None, box, box_normals]`` -> the next sample
         (the body of run_inference, pipelines/simulator.py:68-70)."""
         pos, vel = self.model(inputs, training=False)
+        slab = getattr(self.model, "slab", None)
+        if slab is not None and slab.world > 1:
+            # hand particles that crossed a slab face to the neighbouring rank (per-particle acc travels with them)
+            if inputs[2] is not None:
+                pos, vel, acc = slab.migrate(pos, vel, inputs[2])
+                return [pos, vel, acc] + list(inputs[3:])
+            pos, vel = slab.migrate(pos, vel)
         return [pos, vel] + list(inputs[2:])
 
     @torch.no_grad()

@@ -1,0 +1,149 @@
+"""Spatial slab decomposition across GPUs with one-hop halo exchange.  The reference is single device
+(run_pipeline.py:84-100); this is the multi-GPU design the north star asks for.
+
+One process per GPU.  Rank k owns the particles whose coordinate along ``axis`` lies in [faces[k], faces[k+1]).
+Per step:
+  * bbox / mean all-reduces (the boundary cull of models/pbf_model.py:330-336 and ``centralize`` need global values),
+  * one POSITION halo: every rank sends the owned points within ``radius`` of a face to the rank behind that face,
+  * one FEATURE halo per conv layer: the same rows of the layer's input features (lists fixed for the step),
+  * MIGRATION of particles that crossed a face after the position update.
+Convs then run on [owned | ghosts] inputs and owned outputs; pair terms are evaluated from bit-identical operands on
+both sides of a face, so the antisymmetric layer conserves momentum across ranks exactly as on one GPU.
+
+Everything here is plain torch + torch.distributed point-to-point (NCCL on GPUs, gloo in the CPU tests); payloads
+are a few MB per face per layer, i.e. latency bound, so they are batched into one isend/irecv group per exchange.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class SlabContext:
+    def __init__(self, faces, axis=0, group=None, rank=None, world_size=None):
+        """``faces``: world_size+1 increasing coordinates (use -inf / +inf for the outer ones)."""
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world_size is None else world_size
+        if len(faces) != self.world + 1:
+            raise ValueError("need world_size+1 slab faces")
+        self.faces = [float(f) for f in faces]
+        self.axis = axis
+        self.lo, self.hi = self.faces[self.rank], self.faces[self.rank + 1]
+        self.left = self.rank - 1 if self.rank > 0 else None
+        self.right = self.rank + 1 if self.rank < self.world - 1 else None
+        self.send_left = self.send_right = None  # halo row lists of the current step
+        self.n_from_left = self.n_from_right = 0
+        self.bytes_exchanged = 0
+
+    # -- ownership -------------------------------------------------------------------------------------------
+    @staticmethod
+    def uniform_faces(lo, hi, world):
+        inf = float("inf")
+        inner = [lo + (hi - lo) * k / world for k in range(1, world)]
+        return [-inf] + inner + [inf]
+
+    def owner_of(self, pos):
+        """Rank owning each position (bucketize on the inner faces)."""
+        inner = torch.tensor(self.faces[1:-1], dtype=pos.dtype, device=pos.device)
+        return torch.bucketize(pos[:, self.axis].contiguous(), inner, right=True)
+
+    def owned_mask(self, pos):
+        x = pos[:, self.axis]
+        return (x >= self.lo) & (x < self.hi)
+
+    # -- collectives -----------------------------------------------------------------------------------------
+    def all_reduce_minmax(self, lo, hi):
+        """Global bounding box of per-rank (lo, hi) 3-vectors."""
+        if self.world == 1:
+            return lo, hi
+        buf = torch.cat([-lo, hi]).contiguous()
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self.group)
+        return -buf[:3], buf[3:]
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def _exchange(self, to_left, to_right, n_from_left=None, n_from_right=None):
+        """Sends row blocks to the two neighbours, returns (from_left, from_right).  Row counts are exchanged first
+        unless the caller already knows them (feature halos reuse the counts of the position halo)."""
+        dev, dt = to_left.device, to_left.dtype
+        cols = to_left.shape[1:]
+        if n_from_left is None:
+            cnt_out = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=dev)
+            cnt_l = torch.zeros(1, dtype=torch.int64, device=dev)
+            cnt_r = torch.zeros(1, dtype=torch.int64, device=dev)
+            ops = []
+            if self.left is not None:
+                ops += [dist.P2POp(dist.isend, cnt_out[0:1], self.left, self.group),
+                        dist.P2POp(dist.irecv, cnt_l, self.left, self.group)]
+            if self.right is not None:
+                ops += [dist.P2POp(dist.isend, cnt_out[1:2], self.right, self.group),
+                        dist.P2POp(dist.irecv, cnt_r, self.right, self.group)]
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            n_from_left, n_from_right = int(cnt_l.item()), int(cnt_r.item())
+        from_left = torch.empty((n_from_left, *cols), dtype=dt, device=dev)
+        from_right = torch.empty((n_from_right, *cols), dtype=dt, device=dev)
+        ops = []
+        to_left, to_right = to_left.contiguous(), to_right.contiguous()
+        if self.left is not None:
+            if to_left.numel():
+                ops.append(dist.P2POp(dist.isend, to_left, self.left, self.group))
+            if from_left.numel():
+                ops.append(dist.P2POp(dist.irecv, from_left, self.left, self.group))
+        if self.right is not None:
+            if to_right.numel():
+                ops.append(dist.P2POp(dist.isend, to_right, self.right, self.group))
+            if from_right.numel():
+                ops.append(dist.P2POp(dist.irecv, from_right, self.right, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        self.bytes_exchanged += (to_left.numel() + to_right.numel()) * to_left.element_size()
+        return from_left, from_right, n_from_left, n_from_right
+
+    # -- halos -----------------------------------------------------------------------------------------------
+    def position_halo(self, pos, radius):
+        """Fixes the halo row lists for this step from the owned positions and returns the ghost positions
+        [from left ; from right].  A point within ``radius`` (padded like the search) of a face is sent."""
+        x = pos[:, self.axis]
+        pad = float(radius) * 1.0001 + 1e-6 * max(abs(self.lo) if self.lo > -1e30 else 0.0, abs(self.hi) if self.hi < 1e30 else 0.0)
+        empty = torch.zeros(0, dtype=torch.int64, device=pos.device)
+        self.send_left = torch.nonzero(x < self.lo + pad).flatten() if self.left is not None else empty
+        self.send_right = torch.nonzero(x >= self.hi - pad).flatten() if self.right is not None else empty
+        gl, gr, self.n_from_left, self.n_from_right = self._exchange(pos[self.send_left], pos[self.send_right])
+        return torch.cat([gl, gr], dim=0)
+
+    def feature_halo(self, feats):
+        """Ghost rows of ``feats`` (same order as the ghost positions of this step)."""
+        gl, gr, _, _ = self._exchange(feats[self.send_left], feats[self.send_right], self.n_from_left, self.n_from_right)
+        return torch.cat([gl, gr], dim=0)
+
+    def with_ghosts(self, feats):
+        if self.world == 1:
+            return feats
+        return torch.cat([feats, self.feature_halo(feats)], dim=0)
+
+    # -- migration -------------------------------------------------------------------------------------------
+    def migrate(self, pos, *others):
+        """Re-establishes ownership after a position update: rows that left the slab go to the neighbour (one hop per
+        step: speed*dt << slab width), arrivals are appended.  Returns the new (pos, *others)."""
+        if self.world == 1:
+            return (pos, *others)
+        x = pos[:, self.axis]
+        go_l = x < self.lo
+        go_r = x >= self.hi
+        stay = ~(go_l | go_r)
+        packed = torch.cat([pos] + [o.reshape(o.shape[0], -1) for o in others], dim=1)
+        fl, fr, _, _ = self._exchange(packed[go_l], packed[go_r])
+        new = torch.cat([packed[stay], fl, fr], dim=0)
+        outs, c = [], 0
+        for t in (pos, *others):
+            w = t.reshape(t.shape[0], -1).shape[1]
+            outs.append(new[:, c:c + w].reshape(-1, *t.shape[1:]))
+            c += w
+        return tuple(outs)

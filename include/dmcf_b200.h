@@ -115,7 +115,8 @@ typedef struct dmcf_conv_desc {
     float offset[3];        /* x,y,z */
     int32_t relu_input;
     float feat_scale;
-    int32_t ascc;           /* add the centre feature to every neighbour feature (needs out set == inp set) */
+    int32_t ascc;           /* add the centre feature to every neighbour feature: out point o must be input row o
+                               (out set == inp set, or a prefix of it when ghost rows are appended) */
     int32_t skip_self;      /* drop neighbours whose position equals the out position (lets one CSR that
                                contains self serve ignore_query_point layers) */
     int32_t nbr_lo, nbr_hi; /* keep only neighbours with nbr_lo <= index < nbr_hi; feature row = index - nbr_lo.

@@ -1,0 +1,110 @@
+"""N>1 path on CPU: world_size-2 gloo processes run the slab partition / halo / migration logic with the CPU oracle as
+the per-rank conv kernel and must reproduce the single-process oracle on the undivided scene."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KW = dict(coordinate_mapping="ball_to_cube_volume_preserving", normalize=False, align_corners=True, interpolation="linear")
+EXTENT = np.float32(0.2)
+
+
+def make_problem():
+    from dmcf_b200 import scenes
+    rng = np.random.default_rng(3)
+    sc = scenes.lattice_scene((16, 6, 6), dx=0.05, seed=11)
+    pts = np.concatenate([sc["pos"], sc["box"]]).astype(np.float32)
+    feats = rng.standard_normal((len(pts), 6)).astype(np.float32)
+    w1 = rng.uniform(-0.3, 0.3, (4, 4, 4, 6, 8)).astype(np.float32)
+    w2 = rng.uniform(-0.3, 0.3, (4, 4, 4, 8, 5)).astype(np.float32)
+    half = rng.uniform(-0.3, 0.3, (6, 3, 6, 5, 3)).astype(np.float32)
+    return pts, feats, w1, w2, half
+
+
+def stack(o64, feats, inp_pos, out_pos, w1, w2, half, ghosts):
+    """conv(poly6) -> relu -> conv(poly6) -> relu -> ASCC(peak); ``ghosts(x)`` appends the halo rows of x."""
+    radius = np.float32(0.5) * EXTENT
+    idx, splits, d2 = o64.fixed_radius_search(inp_pos, out_pos, radius)
+    imp = o64.window("poly6", d2.astype(np.float64) / np.float64(radius) ** 2)
+    a = o64.continuous_conv(w1, out_pos, EXTENT, None, inp_pos, ghosts(feats), None, idx, imp, splits, **KW)
+    b = o64.continuous_conv(w2, out_pos, EXTENT, None, inp_pos, ghosts(np.maximum(a, 0)), None, idx, imp, splits, **KW)
+    # antisymmetric layer, fused form sum_j a F(r)^T (f_j + f_i) on the self-free list
+    idx2, splits2, d22 = o64.fixed_radius_search(inp_pos, out_pos, radius, ignore_query_point=True)
+    imp2 = o64.window("peak", d22.astype(np.float64) / np.float64(radius) ** 2)
+    full = o64.symmetric_kernel(half, 1)
+    g = ghosts(np.maximum(b, 0))
+    n_out = out_pos.shape[0]
+    rows = np.repeat(np.arange(n_out), np.diff(splits2))
+    # (f_j + f_i): evaluate the conv on per-pair features through a one-hot trick: conv is linear in f, so add the
+    # centre term as a second conv with features f_i broadcast == f_i * (sum_j a F(r_ij)) (utils/convolutions.py:433-458)
+    c1 = o64.continuous_conv(full, out_pos, EXTENT, None, inp_pos, g, None, idx2, imp2, splits2, **KW)
+    wk = full.reshape(6, 6, 6, 1, -1)
+    wv = o64.continuous_conv(wk, out_pos, EXTENT, None, inp_pos, np.ones((inp_pos.shape[0], 1)), None, idx2, imp2, splits2, **KW)
+    c = c1 + np.einsum("nc,nco->no", g[:n_out], wv.reshape(n_out, full.shape[-2], full.shape[-1]))
+    return a, b, c
+
+
+def worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dmcf_b200.slab import SlabContext
+    from oracle import o64
+    pts, feats, w1, w2, half = make_problem()
+    faces = SlabContext.uniform_faces(float(pts[:, 0].min()), float(pts[:, 0].max()) + 1e-3, world)
+    slab = SlabContext(faces, axis=0)
+    own = slab.owned_mask(torch.from_numpy(pts)).numpy()
+    ids = np.nonzero(own)[0]
+    p_own, f_own = pts[own], feats[own]
+    # bbox all-reduce
+    lo, hi = slab.all_reduce_minmax(torch.from_numpy(p_own.min(0)), torch.from_numpy(p_own.max(0)))
+    assert np.allclose(lo.numpy(), pts.min(0)) and np.allclose(hi.numpy(), pts.max(0))
+    ghosts_pos = slab.position_halo(torch.from_numpy(p_own), float(np.float32(0.5) * EXTENT)).numpy()
+    p_in = np.concatenate([p_own, ghosts_pos])
+    gh = lambda x: slab.with_ghosts(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))).numpy()
+    a, b, c = stack(o64, f_own.astype(np.float64), p_in, p_own, w1, w2, half, gh)
+    # migration: shift everything by 0.3 along x, particles crossing the inner face change rank
+    moved = p_own + np.array([0.3 if rank == 0 else -0.3, 0, 0], np.float32)
+    tag = ids.astype(np.float32)[:, None]
+    mp_, mt_ = slab.migrate(torch.from_numpy(moved), torch.from_numpy(tag))
+    assert bool(slab.owned_mask(mp_).all())
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=ids, a=a, b=b, c=c, mig_ids=mt_.numpy()[:, 0], mig_pos=mp_.numpy(),
+             n_ghost=len(ghosts_pos))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_slab_matches_single_process(tmp_path):
+    from oracle import o64
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    pts, feats, w1, w2, half = make_problem()
+    a, b, c = stack(o64, feats.astype(np.float64), pts, pts, w1, w2, half, lambda x: x)
+    seen = np.zeros(len(pts), bool)
+    n_ghost = 0
+    mig = {}
+    for r in range(2):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        ids = z["ids"]
+        assert not seen[ids].any()
+        seen[ids] = True
+        n_ghost += int(z["n_ghost"])
+        for name, ref in (("a", a), ("b", b), ("c", c)):
+            err = np.abs(z[name] - ref[ids]).max()
+            assert err <= 1e-10 * max(np.abs(ref).max(), 1.0), (name, r, err)
+        for i, p in zip(z["mig_ids"].astype(int), z["mig_pos"]):
+            mig[i] = (r, p)
+    assert seen.all() and n_ghost > 0
+    # momentum conservation of the antisymmetric output across the two ranks
+    assert np.all(np.abs(c.sum(0)) <= 1e-9 * np.abs(c).sum(0))
+    # migration kept every particle exactly once and on the rank that owns its new position
+    assert len(mig) == len(pts)
