@@ -147,6 +147,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_traffic(top):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/roofline_traffic.json, written by hand from profiles/*_full.md); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    key = f"{top['kernel']}:{'x'.join(str(v) for v in top['filter'])}:{top['cin']}->{top['cout']}"
+    return json.load(open(p)).get(key)
+
+
 def conv_algorithmic_bytes(rec):
     """N_in(12+4Cin) + N_out(12+4Cout) + 4 K Cin Cout (+ residual read) (+ CSR since we consume one)."""
     b = rec["n_inp"] * (12 + 4 * rec["cin"]) + rec["n_out"] * (12 + 4 * rec["cout"]) + 4 * rec["rows"] * rec["cout"]
@@ -253,13 +263,13 @@ def main():
         for k, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
             avg_ms = g["ms"] / g["n"]
             gb = conv_algorithmic_bytes(g["rec"]) / 1e9
-            breakdown.append({"kernel": "k_cconv_tile", "filter": list(k[0]), "cin": k[1], "cout": k[2], "ascc": bool(k[3]),
+            breakdown.append({"kernel": g["rec"]["kernel"], "filter": list(k[0]), "cin": k[1], "cout": k[2], "ascc": bool(k[3]),
                               "launches": g["n"], "avg_ms": round(avg_ms, 4), "share_of_step": round(g["ms"] / ms, 4),
                               "algorithmic_GB": round(gb, 4), "GBps": round(gb / (avg_ms * 1e-3), 1),
                               "fp32_TFLOPs": round(conv_flops(g["rec"]) / (avg_ms * 1e-3) / 1e12, 2)})
         top = breakdown[0]
         roofline = {"bound": "hbm", "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": round(top["GBps"] / peak, 4),
-                    "traffic": None, "kernel": f"k_cconv_tile filter {top['filter']} {top['cin']}->{top['cout']}" + (" ascc" if top["ascc"] else ""),
+                    "traffic": ncu_traffic(top), "kernel": f"{top['kernel']} filter {top['filter']} {top['cin']}->{top['cout']}" + (" ascc" if top["ascc"] else ""),
                     "peak_source": peak_src, "avg_launch_ms": top["avg_ms"], "share_of_step": top["share_of_step"],
                     "fp32_tflops": top["fp32_TFLOPs"], "fp32_simt_peak_tflops": 74.0,
                     "note": "wide CConv layers are fp32-FLOP bound (SURVEY 8d): HBM fraction reported as BASELINE asks, "

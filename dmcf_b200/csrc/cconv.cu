@@ -236,15 +236,40 @@ __global__ void __launch_bounds__(256) k_cconv_prepare(const ConvParams p, float
     for (int64_t o = warp0; o < p.n_out; o += n_warps) {
         const float ox = __ldg(p.out_pos + 3 * o), oy = __ldg(p.out_pos + 3 * o + 1), oz = __ldg(p.out_pos + 3 * o + 2);
         const int64_t rs = p.row_splits[o], re = p.row_splits[o + 1];
-        for (int64_t n = rs + lane; n < re; n += 32) {
-            const PairRec r = eval_pair(p, n, true, ox, oy, oz);
-            float* f = records + n;
-            f[0] = __int_as_float(r.row);
-            f[P] = __int_as_float(r.g.i0);
-            f[2 * P] = __int_as_float(r.g.i1);
-            f[3 * P] = r.g.wx0; f[4 * P] = r.g.wx1;
-            f[5 * P] = r.g.wy0; f[6 * P] = r.g.wy1;
-            f[7 * P] = r.g.wz0; f[8 * P] = r.g.wz1;
+        for (int64_t c0 = rs; c0 < re; c0 += 32) {
+            const int64_t n = c0 + lane;
+            PairRec r = eval_pair(p, n, n < re, ox, oy, oz);
+            // Order the chunk by the corner block's base cell (dropped pairs last): the conv kernels walk the records
+            // in order, so consecutive pairs land in neighbouring cases of their scatter switch (instruction-cache
+            // locality).  Bitonic sort of (key, lane) over the warp, then one gather of the 9 fields.
+            unsigned key = ((r.row >= 0 ? (unsigned)r.g.i0 : 0xffffffu) << 5) | (unsigned)lane;
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const unsigned other = __shfl_xor_sync(0xffffffffu, key, j);
+                    const bool up = ((lane & k) == 0);
+                    const bool lower = ((lane & j) == 0);
+                    const unsigned mn = min(key, other), mx = max(key, other);
+                    key = (up == lower) ? mn : mx;
+                }
+            }
+            const int src = key & 31;
+            r.row = __shfl_sync(0xffffffffu, r.row, src);
+            r.g.i0 = __shfl_sync(0xffffffffu, r.g.i0, src);
+            r.g.i1 = __shfl_sync(0xffffffffu, r.g.i1, src);
+            r.g.wx0 = __shfl_sync(0xffffffffu, r.g.wx0, src); r.g.wx1 = __shfl_sync(0xffffffffu, r.g.wx1, src);
+            r.g.wy0 = __shfl_sync(0xffffffffu, r.g.wy0, src); r.g.wy1 = __shfl_sync(0xffffffffu, r.g.wy1, src);
+            r.g.wz0 = __shfl_sync(0xffffffffu, r.g.wz0, src); r.g.wz1 = __shfl_sync(0xffffffffu, r.g.wz1, src);
+            if (n < re) {  // slots of the chunk beyond the row end hold dropped pairs (sorted last)
+                float* f = records + n;
+                f[0] = __int_as_float(r.row);
+                f[P] = __int_as_float(r.g.i0);
+                f[2 * P] = __int_as_float(r.g.i1);
+                f[3 * P] = r.g.wx0; f[4 * P] = r.g.wx1;
+                f[5 * P] = r.g.wy0; f[6 * P] = r.g.wy1;
+                f[7 * P] = r.g.wz0; f[8 * P] = r.g.wz1;
+            }
         }
     }
 }
@@ -301,7 +326,8 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
     cudaStream_t st = (cudaStream_t)stream;
     // specialised kernels (dmcf_set_kernel_options(0) forces the generic kernel; the parity tests run both)
     const int options = g_kernel_options.load(std::memory_order_relaxed);
-    p.debug_wrap_w = (options >> 8) & 7;
+    p.debug_wrap_w = (options >> 8) & 15;
+    p.use_zsplit = (options >> 2) & 1;
     if (options & 2) {  // resident-filter direct kernel for cout <= 4
         bool handled = false;
         rc = launch_cconv_direct(p, st, &handled);

@@ -13,7 +13,8 @@ struct ConvParams {
     float feat_scale;
     int ascc, skip_self, nbr_lo, nbr_hi, dense_cin, accumulate;
     int kc_conv, kc, kc_pad;  // patch columns: conv part, conv+dense, padded to 4
-    int debug_wrap_w;         // timing experiment switch (dmcf_set_kernel_options bit 8), never set in production
+    int debug_wrap_w;         // timing experiment switches (dmcf_set_kernel_options bits 8+), never set in production
+    int use_zsplit;           // option bit 2: run 4x4x4 wide layers as two z-half launches (2 CTAs/SM)
     int cip, cp;              // pow2 lane groupings for input / output channels
     const float* filters;
     const float* out_pos;
@@ -211,7 +212,7 @@ __device__ __forceinline__ void cconv_phase2_v2(const ConvParams& p, const float
         const int row4 = p.cout >> 2;                      // float4s per filter row
         const int kq_full = co_ok ? (p.kc >> 2) : 0;        // k-quads with all 4 rows present (0 disables the lane)
         const float4* wbase = reinterpret_cast<const float4*>(p.filters) + (co0 >> 2);
-        const int dbg_mask = p.debug_wrap_w ? 7 : 0x7fffffff;  // timing experiment only: every tile re-reads 8 k-quads
+        const int dbg_mask = 0x7fffffff;
         auto load_w = [&](int kq, float4 (&w)[4]) {
             if (kq < kq_full) {
                 const float4* wp = wbase + (size_t)(kq & dbg_mask) * 4 * row4;

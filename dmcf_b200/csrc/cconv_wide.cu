@@ -19,35 +19,40 @@ struct FilterGrid {
     static constexpr int NB = NBX * NBY * NBZ;  // distinct "base" cells of the 2x2x2 corner block
 };
 
-// corner weights w[c], c = bx + 2*by + 4*bz, packed as wa = (w0..w3), wb = (w4..w7)
-template <int KZ, int KY, int KX, int B>
-__device__ __forceinline__ void scatter_case(float (&acc)[KZ * KY * KX], const float4& wa, const float4& wb, float f) {
+// corner weights w[c], c = bx + 2*by + 4*bz, packed as wa = (w0..w3), wb = (w4..w7).
+// The kernel instance owns the filter z-planes [ZLO, ZLO+NZ): corners on other planes belong to another launch.
+template <int KZ, int KY, int KX, int ZLO, int NZ, int B>
+__device__ __forceinline__ void scatter_case(float (&acc)[NZ * KY * KX], const float4& wa, const float4& wb, float f) {
     using G = FilterGrid<KZ, KY, KX>;
     if constexpr (B < G::NB) {
         constexpr int x0 = B % G::NBX, y0 = (B / G::NBX) % G::NBY, z0 = B / (G::NBX * G::NBY);
-        constexpr int c000 = (z0 * KY + y0) * KX + x0;
         constexpr int sx = 1, sy = KX, sz = KY * KX;
-        acc[c000] = fmaf(wa.x, f, acc[c000]);
-        if constexpr (KX > 1) acc[c000 + sx] = fmaf(wa.y, f, acc[c000 + sx]);
-        if constexpr (KY > 1) acc[c000 + sy] = fmaf(wa.z, f, acc[c000 + sy]);
-        if constexpr (KX > 1 && KY > 1) acc[c000 + sx + sy] = fmaf(wa.w, f, acc[c000 + sx + sy]);
-        if constexpr (KZ > 1) {
-            acc[c000 + sz] = fmaf(wb.x, f, acc[c000 + sz]);
-            if constexpr (KX > 1) acc[c000 + sz + sx] = fmaf(wb.y, f, acc[c000 + sz + sx]);
-            if constexpr (KY > 1) acc[c000 + sz + sy] = fmaf(wb.z, f, acc[c000 + sz + sy]);
-            if constexpr (KX > 1 && KY > 1) acc[c000 + sz + sx + sy] = fmaf(wb.w, f, acc[c000 + sz + sx + sy]);
+        if constexpr (z0 >= ZLO && z0 < ZLO + NZ) {
+            constexpr int c000 = ((z0 - ZLO) * KY + y0) * KX + x0;
+            acc[c000] = fmaf(wa.x, f, acc[c000]);
+            if constexpr (KX > 1) acc[c000 + sx] = fmaf(wa.y, f, acc[c000 + sx]);
+            if constexpr (KY > 1) acc[c000 + sy] = fmaf(wa.z, f, acc[c000 + sy]);
+            if constexpr (KX > 1 && KY > 1) acc[c000 + sx + sy] = fmaf(wa.w, f, acc[c000 + sx + sy]);
         }
+        if constexpr (KZ > 1 && z0 + 1 >= ZLO && z0 + 1 < ZLO + NZ) {
+            constexpr int c001 = ((z0 + 1 - ZLO) * KY + y0) * KX + x0;
+            acc[c001] = fmaf(wb.x, f, acc[c001]);
+            if constexpr (KX > 1) acc[c001 + sx] = fmaf(wb.y, f, acc[c001 + sx]);
+            if constexpr (KY > 1) acc[c001 + sy] = fmaf(wb.z, f, acc[c001 + sy]);
+            if constexpr (KX > 1 && KY > 1) acc[c001 + sx + sy] = fmaf(wb.w, f, acc[c001 + sx + sy]);
+        }
+        (void)sz;
     }
 }
 
 #define DMCF_SC(i) \
     case i:        \
-        scatter_case<KZ, KY, KX, i>(acc, wa, wb, f); \
+        scatter_case<KZ, KY, KX, ZLO, NZ, i>(acc, wa, wb, f); \
         break;
 #define DMCF_SC8(i) DMCF_SC(i) DMCF_SC(i + 1) DMCF_SC(i + 2) DMCF_SC(i + 3) DMCF_SC(i + 4) DMCF_SC(i + 5) DMCF_SC(i + 6) DMCF_SC(i + 7)
 
-template <int KZ, int KY, int KX>
-__device__ __forceinline__ void scatter_switch(int b, float (&acc)[KZ * KY * KX], const float4& wa, const float4& wb, float f) {
+template <int KZ, int KY, int KX, int ZLO, int NZ>
+__device__ __forceinline__ void scatter_switch(int b, float (&acc)[NZ * KY * KX], const float4& wa, const float4& wb, float f) {
     static_assert(FilterGrid<KZ, KY, KX>::NB <= 64, "too many base cells");
     switch (b) {  // warp-uniform: every lane works on the same pair
         DMCF_SC8(0) DMCF_SC8(8) DMCF_SC8(16) DMCF_SC8(24) DMCF_SC8(32) DMCF_SC8(40) DMCF_SC8(48) DMCF_SC8(56)
@@ -69,9 +74,12 @@ __device__ __forceinline__ void base_axis(int fs, int i0, float w0, float w1, in
 
 static constexpr int kRecWords = 12;  // {row, base, pad, pad, w0..w3, w4..w7}: 48 B, 16 B aligned, conflict-free STS.128
 
-template <int KZ, int KY, int KX, int MT, int NW, bool RED_ALIAS>
-__global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
+// p.filters / p.kc_conv / p.kc / p.kc_pad describe THIS instance's slice of the filter (planes [ZLO, ZLO+NZ) followed by
+// the Dense rows if this launch carries them).
+template <int KZ, int KY, int KX, int ZLO, int NZ, int MT, int NW, int MINB, bool RED_ALIAS>
+__global__ void __launch_bounds__(NW * 32, MINB) k_cconv_wide(const ConvParams p) {
     using G = FilterGrid<KZ, KY, KX>;
+    constexpr int KL = NZ * KY * KX;  // filter cells of this instance
     extern __shared__ __align__(16) float smem[];
     float* patch = smem;  // k-quad major [kc_pad/4][MT+1][4] (also [NW][MT][32] partial sums if RED_ALIAS)
     const size_t tile_words = (size_t)(p.kc_pad / 4) * (MT + 1) * 4, red_words = (size_t)NW * MT * 32;
@@ -92,9 +100,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
             for (int k = lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
             continue;
         }
-        float acc[G::K];
+        float acc[KL];
 #pragma unroll
-        for (int c = 0; c < G::K; ++c) acc[c] = 0.0f;
+        for (int c = 0; c < KL; ++c) acc[c] = 0.0f;
         const float ox = __ldg(p.out_pos + 3 * o), oy = __ldg(p.out_pos + 3 * o + 1), oz = __ldg(p.out_pos + 3 * o + 2);
         const int64_t rs = p.row_splits[o], re = p.row_splits[o + 1];
         float fc = 0.0f;  // centre feature of the antisymmetric layer (out set == inp set)
@@ -108,20 +116,22 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
             // ---- lane-parallel geometry of up to 32 neighbours -> compact records in the warp's scratch ----
             const int64_t n = c0 + lane;
             const PairRec pr = pair_record(p, n, n < re, ox, oy, oz);
-            const int row = pr.row;
+            int row2 = pr.row;
             norm_acc += pr.norm;
             int b = 0;
             float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
-            if (row >= 0) {
+            if (row2 >= 0) {
                 int bx, by, bz;
                 float xl, xh, yl, yh, zl, zh;
                 base_axis(KX, pr.g.i0 & 0xff, pr.g.wx0, pr.g.wx1, bx, xl, xh);
                 base_axis(KY, (pr.g.i0 >> 8) & 0xff, pr.g.wy0, pr.g.wy1, by, yl, yh);
                 base_axis(KZ, (pr.g.i0 >> 16) & 0xff, pr.g.wz0, pr.g.wz1, bz, zl, zh);
+                if (NZ < KZ && (bz + 1 < ZLO || bz >= ZLO + NZ)) row2 = -1;  // touches none of this instance's planes
                 b = (bz * G::NBY + by) * G::NBX + bx;
                 wa = make_float4(xl * yl * zl, xh * yl * zl, xl * yh * zl, xh * yh * zl);
                 wb = make_float4(xl * yl * zh, xh * yl * zh, xl * yh * zh, xh * yh * zh);
             }
+            const int row = row2;
             const unsigned active = __ballot_sync(0xffffffffu, row >= 0);
             const int cnt = __popc(active);
             __syncwarp();  // previous chunk's records fully consumed
@@ -132,35 +142,38 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_wide(const ConvParams p) {
                 *reinterpret_cast<float4*>(r + 8) = wb;
             }
             __syncwarp();
-            // ---- walk the records: gather the feature row (4 in flight), scatter into the register patch ----
-            if (p.debug_wrap_w & 4) continue;  // timing experiment: geometry only
-            for (int j = 0; j < cnt; j += 4) {
-                int2 rb[4];
-                float fv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (j + u < cnt) {
-                        rb[u] = *reinterpret_cast<const int2*>(rec + (j + u) * kRecWords);
-                        fv[u] = lane_ci ? __ldg(p.inp_feat + (int64_t)rb[u].x * p.inp_stride + lane) : 0.0f;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (j + u < cnt) {
-                        const float4 wa2 = *reinterpret_cast<const float4*>(rec + (j + u) * kRecWords + 4);
-                        const float4 wb2 = *reinterpret_cast<const float4*>(rec + (j + u) * kRecWords + 8);
-                        float f = fv[u];
-                        if (p.relu_input) f = fmaxf(f, 0.0f);
-                        f = fmaf(f, p.feat_scale, fc);
-                        scatter_switch<KZ, KY, KX>(rb[u].y, acc, wa2, wb2, f);
-                    }
-                }
+            // ---- walk the records: ONE copy of the scatter switch (small code: the 27 cases stay in the instruction
+            // cache; with records sorted by base cell consecutive pairs take neighbouring cases), feature rows of the
+            // next PF pairs already in flight ----
+            auto gather = [&](int j) -> float {
+                return (j < cnt && lane_ci) ? __ldg(p.inp_feat + (int64_t)__float_as_int(rec[j * kRecWords]) * p.inp_stride + lane)
+                                            : 0.0f;
+            };
+            float fq0 = gather(0), fq1 = gather(1), fq2 = gather(2), fq3 = gather(3);
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) {
+                float f = fq0;
+                fq0 = fq1; fq1 = fq2; fq2 = fq3;
+                fq3 = gather(j + 4);
+                const int b = __float_as_int(rec[j * kRecWords + 1]);
+                const float4 wa2 = *reinterpret_cast<const float4*>(rec + j * kRecWords + 4);
+                const float4 wb2 = *reinterpret_cast<const float4*>(rec + j * kRecWords + 8);
+                if (p.relu_input) f = fmaxf(f, 0.0f);
+                f = fmaf(f, p.feat_scale, fc);
+                scatter_switch<KZ, KY, KX, ZLO, NZ>(b, acc, wa2, wb2, f);
             }
         }
         // ---- patch row -> shared memory (lane = channel: conflict-free), Dense columns, padding ----
         if (lane_ci) {
+            if ((p.cin & 3) == 0) {  // k = c*cin + lane: the k-quad advances by cin/4 per cell -> one running pointer
+                float* pp = patch + patchq_index<MT>(m, lane);
+                const int step = p.cin * (MT + 1);
 #pragma unroll
-            for (int c = 0; c < G::K; ++c) patch[patchq_index<MT>(m, c * p.cin + lane)] = acc[c];
+                for (int c = 0; c < KL; ++c) pp[c * step] = acc[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < KL; ++c) patch[patchq_index<MT>(m, c * p.cin + lane)] = acc[c];
+            }
         }
         if (p.dense_cin > 0) {
             const float* drow = p.dense_inp + o * p.dense_stride;
@@ -189,36 +202,62 @@ static size_t wide_smem_bytes(int mt, int nw, int kc_pad, int cp, bool alias) {
     return words * sizeof(float);
 }
 
-template <int KZ, int KY, int KX, int MT, int NW, bool ALIAS>
+template <int KZ, int KY, int KX, int ZLO, int NZ, int MT, int NW, int MINB, bool ALIAS>
 static int launch_wide(const ConvParams& p, cudaStream_t st) {
     static bool attr_set = false;
+    auto kern = k_cconv_wide<KZ, KY, KX, ZLO, NZ, MT, NW, MINB, ALIAS>;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_cconv_wide<KZ, KY, KX, MT, NW, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_wide)");
         attr_set = true;
     }
     const int64_t tiles = ceil_div(p.n_out, MT);
-    k_cconv_wide<KZ, KY, KX, MT, NW, ALIAS><<<(unsigned)tiles, NW * 32, wide_smem_bytes(MT, NW, p.kc_pad, p.cp, ALIAS), st>>>(p);
+    kern<<<(unsigned)tiles, NW * 32, wide_smem_bytes(MT, NW, p.kc_pad, p.cp, ALIAS), st>>>(p);
     DMCF_LAUNCH_CHECK("k_cconv_wide");
     return DMCF_OK;
 }
 
+// whole filter in one launch (one CTA per SM)
 template <int KZ, int KY, int KX>
 static int launch_wide_grid(const ConvParams& p, cudaStream_t st, bool* handled) {
     const size_t limit = 227 * 1024;
     *handled = true;
     if (p.cout <= 32) {  // partial sums may reuse the patch tile
-        if (wide_smem_bytes(32, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 32, 16, true>(p, st);
-        if (wide_smem_bytes(24, 12, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 24, 12, true>(p, st);  // 2 points per warp
-        if (wide_smem_bytes(20, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 20, 16, true>(p, st);
-        if (wide_smem_bytes(16, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 16, 16, true>(p, st);
+        if (wide_smem_bytes(32, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 0, KZ, 32, 16, 1, true>(p, st);
+        if (wide_smem_bytes(24, 12, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 0, KZ, 24, 12, 1, true>(p, st);
+        if (wide_smem_bytes(20, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 0, KZ, 20, 16, 1, true>(p, st);
+        if (wide_smem_bytes(16, 16, p.kc_pad, p.cp, true) <= limit) return launch_wide<KZ, KY, KX, 0, KZ, 16, 16, 1, true>(p, st);
     } else {
-        if (wide_smem_bytes(24, 12, p.kc_pad, p.cp, false) <= limit) return launch_wide<KZ, KY, KX, 24, 12, false>(p, st);
-        if (wide_smem_bytes(16, 16, p.kc_pad, p.cp, false) <= limit) return launch_wide<KZ, KY, KX, 16, 16, false>(p, st);
+        if (wide_smem_bytes(24, 12, p.kc_pad, p.cp, false) <= limit) return launch_wide<KZ, KY, KX, 0, KZ, 24, 12, 1, false>(p, st);
+        if (wide_smem_bytes(16, 16, p.kc_pad, p.cp, false) <= limit) return launch_wide<KZ, KY, KX, 0, KZ, 16, 16, 1, false>(p, st);
     }
     *handled = false;
     return DMCF_OK;
+}
+
+// 4x4x4 filters whose patch tile would own the SM: two launches over the z-plane halves {0,1} and {2,3}.  Half the patch
+// per point -> two CTAs (24 warps) per SM, which is what hides the feature-gather and shared-memory latencies; the pairs
+// straddling the halves are visited by both launches.  The second launch carries Dense / bias / residual and accumulates.
+static int launch_wide_444_split(const ConvParams& p, cudaStream_t st, bool* handled) {
+    constexpr int MT = 20, NW = 12;
+    *handled = false;
+    if (p.cout > 32 || p.normalize) return DMCF_OK;
+    ConvParams lo = p, hi = p;
+    const int half_rows = 2 * 16 * p.cin;
+    lo.kc_conv = lo.kc = half_rows;
+    lo.kc_pad = (lo.kc + 3) / 4 * 4;
+    lo.dense_cin = 0; lo.dense_inp = nullptr; lo.bias = nullptr; lo.residual = nullptr;
+    hi.filters = p.filters + (size_t)half_rows * p.cout;
+    hi.kc_conv = half_rows;
+    hi.kc = half_rows + p.dense_cin;
+    hi.kc_pad = (hi.kc + 3) / 4 * 4;
+    hi.accumulate = 1;
+    if (((uintptr_t)hi.filters & 15) != 0) return DMCF_OK;
+    if (2 * wide_smem_bytes(MT, NW, hi.kc_pad, p.cp, true) > 227 * 1024) return DMCF_OK;
+    *handled = true;
+    int rc = launch_wide<4, 4, 4, 0, 2, MT, NW, 2, true>(lo, st);
+    if (rc) return rc;
+    return launch_wide<4, 4, 4, 2, 2, MT, NW, 2, true>(hi, st);
 }
 
 // Tries the register-patch kernel; *handled = false means "not eligible, use the generic kernel".
@@ -226,7 +265,13 @@ int launch_cconv_wide(const ConvParams& p, cudaStream_t st, bool* handled) {
     *handled = false;
     if (p.gp.interp != DMCF_INTERP_LINEAR || p.cin > 32) return DMCF_OK;
     if (p.cout % 4 != 0 || ((uintptr_t)p.filters & 15) != 0) return DMCF_OK;  // phase 2 reads filter rows as float4
-    if (p.gp.kz == 4 && p.gp.ky == 4 && p.gp.kx == 4) return launch_wide_grid<4, 4, 4>(p, st, handled);
+    if (p.gp.kz == 4 && p.gp.ky == 4 && p.gp.kx == 4) {
+        if (p.use_zsplit && wide_smem_bytes(32, 16, p.kc_pad, p.cp, true) > 113 * 1024) {
+            int rc = launch_wide_444_split(p, st, handled);
+            if (rc || *handled) return rc;
+        }
+        return launch_wide_grid<4, 4, 4>(p, st, handled);
+    }
     if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 8) return launch_wide_grid<1, 8, 8>(p, st, handled);
     if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 1) return launch_wide_grid<1, 8, 1>(p, st, handled);
     return DMCF_OK;

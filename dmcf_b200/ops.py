@@ -256,7 +256,8 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     neighbors_row_splits = neighbors_row_splits.contiguous()
     rec = None
     if PROFILE is not None:
-        rec = dict(kernel_size=(kz, ky, kx), cin=cin, cout=cout, ascc=bool(ascc), n_inp=n_inp, n_out=n_out,
+        rec = dict(kernel=conv_kernel_name((kz, ky, kx), cin, cout, interpolation, int(dense_cin)),
+                   kernel_size=(kz, ky, kx), cin=cin, cout=cout, ascc=bool(ascc), n_inp=n_inp, n_out=n_out,
                    rows=kz * ky * kx * cin + int(dense_cin), pairs=int(neighbors_index.shape[0]),
                    residual=residual is not None, start=torch.cuda.Event(enable_timing=True),
                    end=torch.cuda.Event(enable_timing=True))
@@ -407,6 +408,17 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
 def set_kernel_options(options):
     """bit 0: register-patch kernel for wide layers (default on).  Returns the previous mask."""
     return int(_lib.load().dmcf_set_kernel_options(int(options)))
+
+
+def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0):
+    """Which kernel dmcf_cconv_forward dispatches to with the default options (mirrors csrc/cconv.cu)."""
+    kz, ky, kx = (int(k) for k in kernel_size)
+    kc = kz * ky * kx * cin + dense_cin
+    if cout <= 4 and (kc * cout + 4 + 16 * 32 * 12) * 4 <= 200 * 1024:
+        return "k_cconv_direct"
+    if interpolation == "linear" and cin <= 32 and cout % 4 == 0 and (kz, ky, kx) in ((4, 4, 4), (1, 8, 8), (1, 8, 1)):
+        return "k_cconv_wide"
+    return "k_cconv_tile"
 
 
 def launch_count():

@@ -149,7 +149,8 @@ int dmcf_cconv_prepare(const dmcf_conv_desc* desc, const float* out_positions, i
                        const float* neighbors_importance, int64_t n_pairs, float* records, void* stream);
 
 /* Kernel selection bit mask (default 3): bit 0 = register-patch kernel for compile-time filter grids (k_cconv_wide),
- * bit 1 = resident-filter direct kernel for cout <= 4 (k_cconv_direct); 0 forces the generic kernel everywhere.  Returns the previous mask.  Results agree to float32 rounding. */
+ * bit 1 = resident-filter direct kernel for cout <= 4 (k_cconv_direct), bit 2 = run 4x4x4 wide layers as two z-half
+ * launches with two CTAs per SM (measured on par with the single launch, off by default); 0 forces the generic kernel.  Returns the previous mask.  Results agree to float32 rounding. */
 int dmcf_set_kernel_options(int options);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -25,5 +25,5 @@ def run(opt, label):
         g.setdefault(k, []).append(r['start'].elapsed_time(r['end']))
     print(label, 'ms/step %.2f' % (e0.elapsed_time(e1)/3), {str(k): round(float(np.mean(v)),2) for k,v in g.items()})
 run(3, 'fast')
-run(3 | 512, 'phase1 only (timing)')
-run(3 | 512 | 1024, 'geometry only (timing)')
+run(7, 'fast + z-split')
+run(3 | 512, 'phase1 only')

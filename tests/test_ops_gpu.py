@@ -135,7 +135,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.fixture(params=[3, 0], ids=["fast-kernels", "generic-kernel"])
+@pytest.fixture(params=[3, 7, 0], ids=["fast-kernels", "fast-kernels-zsplit", "generic-kernel"])
 def kernel_options(request):
     from dmcf_b200 import ops
     prev = ops.set_kernel_options(request.param)
@@ -180,12 +180,13 @@ def test_continuous_conv_matches_oracle(cuda, case, fused_window, kernel_options
     scale = 4.0 if cin * np.prod(ks) > 4096 else 1.0  # very long float32 dot products (cin96: K = 6144)
     feat_close(got.cpu().numpy(), ref, scale)
     if not normalize and (fused_window or window is None):
-        # same conv through precomputed pair records (dmcf_cconv_prepare): bit-identical to the on-the-fly geometry
+        # same conv through precomputed pair records (dmcf_cconv_prepare; pairs reordered by filter cell)
         recs = ops.prepare_pair_records(ks, t(outp), float(extent), None, t(pts), None, t(idx), None, t(splits),
                                         align_corners=align, coordinate_mapping=mapping, interpolation=interp, window=window)
         got2 = ops.continuous_conv(t(filt), t(outp), float(extent), None, t(pts), t(feats), None, t(idx), None, t(splits),
                                    window=window, pair_records=recs, **kw)
-        assert torch.equal(got, got2)
+        feat_close(got2.cpu().numpy(), ref, scale)
+        feat_close(got2.cpu().numpy(), got.cpu().numpy(), 0.5)
 
 
 def test_continuous_conv_fused_extras(cuda, kernel_options):
