@@ -254,6 +254,8 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     out_stride = out.stride(0) if n_out > 1 else max(cout, out.stride(0))
     neighbors_index = neighbors_index.contiguous()
     neighbors_row_splits = neighbors_row_splits.contiguous()
+    if neighbors_index.numel() == 0:  # no pair at all: the ABI still wants a non-NULL list
+        neighbors_index = torch.zeros(1, dtype=torch.int32, device=out_positions.device)
     rec = None
     if PROFILE is not None:
         rec = dict(kernel=conv_kernel_name((kz, ky, kx), cin, cout, interpolation, int(dense_cin)),
