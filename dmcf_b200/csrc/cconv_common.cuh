@@ -203,11 +203,10 @@ __device__ __forceinline__ void cconv_phase2_v2(const ConvParams& p, const float
     for (int cb = 0; cb < p.cout; cb += 32) {
         const int co0 = cb + cq * 4;
         const bool co_ok = co0 < p.cout;
-        float acc[R][4];
+        // accumulators as float2 pairs: Blackwell's packed FFMA2 (fma.rn.f32x2) does two FMAs per issued instruction
+        float2 acc[R][2];
 #pragma unroll
-        for (int i = 0; i < R; ++i)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+        for (int i = 0; i < R; ++i) acc[i][0] = acc[i][1] = make_float2(0.0f, 0.0f);
         // filter rows as float4 (cout % 4 == 0, 16-byte aligned); whole k-quads below kq_full need no guards
         const int row4 = p.cout >> 2;                      // float4s per filter row
         const int kq_full = co_ok ? (p.kc >> 2) : 0;        // k-quads with all 4 rows present (0 disables the lane)
@@ -234,14 +233,16 @@ __device__ __forceinline__ void cconv_phase2_v2(const ConvParams& p, const float
 #pragma unroll
             for (int i = 0; i < R; ++i) {
                 const float4 pv = pq[i];
-                acc[i][0] = fmaf(pv.x, w[0].x, acc[i][0]); acc[i][1] = fmaf(pv.x, w[0].y, acc[i][1]);
-                acc[i][2] = fmaf(pv.x, w[0].z, acc[i][2]); acc[i][3] = fmaf(pv.x, w[0].w, acc[i][3]);
-                acc[i][0] = fmaf(pv.y, w[1].x, acc[i][0]); acc[i][1] = fmaf(pv.y, w[1].y, acc[i][1]);
-                acc[i][2] = fmaf(pv.y, w[1].z, acc[i][2]); acc[i][3] = fmaf(pv.y, w[1].w, acc[i][3]);
-                acc[i][0] = fmaf(pv.z, w[2].x, acc[i][0]); acc[i][1] = fmaf(pv.z, w[2].y, acc[i][1]);
-                acc[i][2] = fmaf(pv.z, w[2].z, acc[i][2]); acc[i][3] = fmaf(pv.z, w[2].w, acc[i][3]);
-                acc[i][0] = fmaf(pv.w, w[3].x, acc[i][0]); acc[i][1] = fmaf(pv.w, w[3].y, acc[i][1]);
-                acc[i][2] = fmaf(pv.w, w[3].z, acc[i][2]); acc[i][3] = fmaf(pv.w, w[3].w, acc[i][3]);
+                const float2 px = make_float2(pv.x, pv.x), py = make_float2(pv.y, pv.y), pz = make_float2(pv.z, pv.z),
+                             pw = make_float2(pv.w, pv.w);
+                acc[i][0] = __ffma2_rn(px, make_float2(w[0].x, w[0].y), acc[i][0]);
+                acc[i][1] = __ffma2_rn(px, make_float2(w[0].z, w[0].w), acc[i][1]);
+                acc[i][0] = __ffma2_rn(py, make_float2(w[1].x, w[1].y), acc[i][0]);
+                acc[i][1] = __ffma2_rn(py, make_float2(w[1].z, w[1].w), acc[i][1]);
+                acc[i][0] = __ffma2_rn(pz, make_float2(w[2].x, w[2].y), acc[i][0]);
+                acc[i][1] = __ffma2_rn(pz, make_float2(w[2].z, w[2].w), acc[i][1]);
+                acc[i][0] = __ffma2_rn(pw, make_float2(w[3].x, w[3].y), acc[i][0]);
+                acc[i][1] = __ffma2_rn(pw, make_float2(w[3].z, w[3].w), acc[i][1]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) w[j] = wn[j];
@@ -251,7 +252,7 @@ __device__ __forceinline__ void cconv_phase2_v2(const ConvParams& p, const float
 #pragma unroll
         for (int i = 0; i < R; ++i)
             *reinterpret_cast<float4*>(red + ((size_t)warp * MT + pg * R + i) * 32 + cq * 4) =
-                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
         __syncthreads();
         for (int t = tid; t < MT * 32; t += NW * 32) {
             const int m = t >> 5, c = t & 31;
