@@ -172,9 +172,8 @@ class PBFNet(BaseModel):
     def set_slab(self, slab):
         """Multi-GPU: this rank owns one spatial slab; convs see [owned | ghost] inputs (dmcf_b200/slab.py)."""
         if slab is not None and slab.world > 1:
-            if len(self.strides) != 1 or self.strides[0] != 1:
-                raise NotImplementedError("slab decomposition currently covers single-scale nets (strides: [1]); "
-                                          "multi-scale lattices need per-scale ownership (SURVEY 8e)")
+            if self.voxel_size is None and any(s != 1 for s in self.strides):
+                raise NotImplementedError("slab decomposition needs voxel-grid multi-scale sampling")
             if not self.use_bnds:
                 raise NotImplementedError("slab decomposition with use_bnds=False")
             self.fused = True
@@ -321,10 +320,13 @@ class PBFNet(BaseModel):
             x[n_f:, cf:] = box_feats
             w, b = self._input_weights(cf, cb)
             all_in = all_pos
+            self._halo = None
             if slab is not None:  # ghosts of the two neighbouring slabs: positions once per step, features per layer
-                all_in = torch.cat([all_pos, slab.position_halo(all_pos, 0.5 * ext0)], dim=0)
-                x = slab.with_ghosts(x)
-            self._all_in = all_in
+                # halo width = the largest radius any conv applies to these points (coarse scales read scale 0 with it)
+                self._halo = [slab.make_halo(all_pos, max(self.particle_radii))]
+                all_in = torch.cat([all_pos, self._halo[0].ghost_pos], dim=0)
+                x = self._halo[0].with_ghosts(x)
+            self._pos_in = [all_in]
             nns = self._step.search((0, 0), all_in, all_pos, 0.5 * ext0)
             win = self.fluid_convs.window_function
             recs = self._step.records((0, 0), nns, self.kernel_size, all_in, all_pos, ext0, self.coordinate_mapping,
@@ -336,10 +338,42 @@ class PBFNet(BaseModel):
                 feat_scale=self.part_scale, skip_self=self.ignore_query_points, bias=b, dense_inp=x,
                 dense_cin=cf + cb, kernel_size=self.kernel_size, pair_records=recs)
         src = all_pos if self.use_bnds else pos
-        dilated_pos, _, idx = get_dilated_pos(src, self.strides, voxel_size=self.voxel_size,
-                                              centralize=self.centralize, pad=self.sample_pad, hyst=self.sample_hyst)
+        if slab is not None and self.fused:
+            dilated_pos, idx = self._slab_dilated_pos(slab, all_pos, all_in), [None] * len(self.strides)
+        else:
+            dilated_pos, _, idx = get_dilated_pos(src, self.strides, voxel_size=self.voxel_size,
+                                                  centralize=self.centralize, pad=self.sample_pad, hyst=self.sample_hyst)
         self.dilated_pos = dilated_pos
         return [dilated_pos, feats_out, idx, None]
+
+    def _slab_dilated_pos(self, slab, all_own, all_in):
+        """Multi-scale lattices under slab decomposition: every rank builds the lattice from its owned + ghost particles
+        (all particles within one coarse voxel of the slab are among the ghosts), keeps the lattice points whose
+        coordinate falls in its slab (ownership by coordinate makes the per-rank sets a partition of the global
+        lattice) and receives the neighbours' lattice points near the faces as ghosts of that scale."""
+        from .losses import grid_pos
+        out = []
+        center = None
+        for si, stride in enumerate(self.strides):
+            if stride == 1:
+                out.append(all_own)
+                continue
+            if self.centralize and center is None:  # global mean, float64 accumulate, rounded once (losses.point_mean)
+                acc = torch.cat([all_own.to(torch.float64).sum(dim=0),
+                                 torch.tensor([float(all_own.shape[0])], dtype=torch.float64, device=all_own.device)])
+                acc = slab.all_reduce_sum(acc)
+                center = (acc[:3] / acc[3]).to(torch.float32)
+            vs = torch.as_tensor(self.voxel_size, dtype=torch.float32) * float(stride)
+            lat = grid_pos(all_in, vs, self.centralize, self.sample_pad, self.sample_hyst, center)
+            own = lat[slab.owned_mask(lat)].contiguous()
+            plan = slab.make_halo(own, max(self.particle_radii))
+            while len(self._halo) <= si:
+                self._halo.append(None)
+                self._pos_in.append(None)
+            self._halo[si] = plan
+            self._pos_in[si] = torch.cat([own, plan.ghost_pos], dim=0)
+            out.append(own)
+        return out
 
     def _ensure_built_inputs(self, cf, cb, device):
         if self.fluid_convs.kernel is None:
@@ -398,7 +432,7 @@ class PBFNet(BaseModel):
         return w, b
 
     def conv_block(self, conv, dense, x, inp_pos, out_pos, extent, key, *, relu=True, scale=1.0, same_set=False,
-                   residual=None, out=None, accumulate=False, ascc=False):
+                   residual=None, out=None, accumulate=False, ascc=False, inp_scale=0):
         """relu -> conv (+ Dense on the same relu'd features) (+ residual), the unit models/hrnet.py:81-99 and
         models/cconv.py:60-67 repeat; fused into one kernel launch."""
         if conv.kernel is None:
@@ -408,8 +442,8 @@ class PBFNet(BaseModel):
         w, b = self._block_weights(conv, dense)
         if self.slab is not None and self.slab.world > 1:
             # owned rows out, [owned | ghost] rows in: refresh the ghost rows of this layer's input from the neighbours
-            x = self.slab.with_ghosts(x)
-            inp_pos = self._all_in
+            x = self._halo[inp_scale].with_ghosts(x)
+            inp_pos = self._pos_in[inp_scale]
         nns = self._step.search(key, inp_pos, out_pos, 0.5 * float(extent))
         win = conv.window_function
         skip = bool(conv.radius_search_ignore_query_points and same_set)
@@ -640,7 +674,7 @@ class HRNet(PBFNet):
                                         self.denses[layer][scale][0][inp_scale] if same else None, x, pos[inp_scale],
                                         pos[scale], ext, (inp_scale, scale), relu=True, scale=importance,
                                         same_set=same, residual=res, out=o,
-                                        accumulate=self.add_merge and inp_scale > 0)
+                                        accumulate=self.add_merge and inp_scale > 0, inp_scale=inp_scale)
                     ans.append(buf)
                 else:
                     inp = []
@@ -668,7 +702,7 @@ class HRNet(PBFNet):
                     if self.fused:
                         ans[-1] = self.conv_block(self.convs[layer][scale][i][0], self.denses[layer][scale][i][0], x,
                                                   pos[scale], pos[scale], ext, (scale, scale), relu=False,
-                                                  scale=importance, same_set=True, residual=res)
+                                                  scale=importance, same_set=True, residual=res, inp_scale=scale)
                     else:
                         a = self.convs[layer][scale][i][0](x * importance, pos[scale], pos[scale], ext, None)
                         a = a + self.denses[layer][scale][i][0](x)

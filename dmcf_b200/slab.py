@@ -32,8 +32,7 @@ class SlabContext:
         self.lo, self.hi = self.faces[self.rank], self.faces[self.rank + 1]
         self.left = self.rank - 1 if self.rank > 0 else None
         self.right = self.rank + 1 if self.rank < self.world - 1 else None
-        self.send_left = self.send_right = None  # halo row lists of the current step
-        self.n_from_left = self.n_from_right = 0
+        self._plan = None
         self.bytes_exchanged = 0
 
     # -- ownership -------------------------------------------------------------------------------------------
@@ -107,26 +106,32 @@ class SlabContext:
         return from_left, from_right, n_from_left, n_from_right
 
     # -- halos -----------------------------------------------------------------------------------------------
-    def position_halo(self, pos, radius):
-        """Fixes the halo row lists for this step from the owned positions and returns the ghost positions
-        [from left ; from right].  A point within ``radius`` (padded like the search) of a face is sent."""
+    def make_halo(self, pos, radius):
+        """Halo plan of one point set (particles, or the lattice points of one scale) for this step: which owned rows
+        go to which neighbour, how many arrive, and the ghost positions [from left ; from right].  A point within
+        ``radius`` (padded like the search) of a face is sent."""
         x = pos[:, self.axis]
         pad = float(radius) * 1.0001 + 1e-6 * max(abs(self.lo) if self.lo > -1e30 else 0.0, abs(self.hi) if self.hi < 1e30 else 0.0)
         empty = torch.zeros(0, dtype=torch.int64, device=pos.device)
-        self.send_left = torch.nonzero(x < self.lo + pad).flatten() if self.left is not None else empty
-        self.send_right = torch.nonzero(x >= self.hi - pad).flatten() if self.right is not None else empty
-        gl, gr, self.n_from_left, self.n_from_right = self._exchange(pos[self.send_left], pos[self.send_right])
-        return torch.cat([gl, gr], dim=0)
+        plan = HaloPlan(self)
+        plan.send_left = torch.nonzero(x < self.lo + pad).flatten() if self.left is not None else empty
+        plan.send_right = torch.nonzero(x >= self.hi - pad).flatten() if self.right is not None else empty
+        gl, gr, plan.n_from_left, plan.n_from_right = self._exchange(pos[plan.send_left], pos[plan.send_right])
+        plan.ghost_pos = torch.cat([gl, gr], dim=0)
+        return plan
+
+    # single-plan convenience API (one point set per step)
+    def position_halo(self, pos, radius):
+        self._plan = self.make_halo(pos, radius)
+        return self._plan.ghost_pos
 
     def feature_halo(self, feats):
-        """Ghost rows of ``feats`` (same order as the ghost positions of this step)."""
-        gl, gr, _, _ = self._exchange(feats[self.send_left], feats[self.send_right], self.n_from_left, self.n_from_right)
-        return torch.cat([gl, gr], dim=0)
+        return self._plan.feature_halo(feats)
 
     def with_ghosts(self, feats):
         if self.world == 1:
             return feats
-        return torch.cat([feats, self.feature_halo(feats)], dim=0)
+        return self._plan.with_ghosts(feats)
 
     # -- migration -------------------------------------------------------------------------------------------
     def migrate(self, pos, *others):
@@ -147,3 +152,23 @@ class SlabContext:
             outs.append(new[:, c:c + w].reshape(-1, *t.shape[1:]))
             c += w
         return tuple(outs)
+
+
+class HaloPlan:
+    """Row lists / counts of one point set's halo, fixed for a step; refreshes ghost FEATURE rows on demand."""
+
+    def __init__(self, slab):
+        self.slab = slab
+        self.send_left = self.send_right = None
+        self.n_from_left = self.n_from_right = 0
+        self.ghost_pos = None
+
+    def feature_halo(self, feats):
+        """Ghost rows of ``feats`` (same order as ``ghost_pos``)."""
+        gl, gr, _, _ = self.slab._exchange(feats[self.send_left], feats[self.send_right], self.n_from_left, self.n_from_right)
+        return torch.cat([gl, gr], dim=0)
+
+    def with_ghosts(self, feats):
+        if self.slab.world == 1:
+            return feats
+        return torch.cat([feats, self.feature_halo(feats)], dim=0)
