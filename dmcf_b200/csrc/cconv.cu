@@ -176,6 +176,7 @@ static int launch_cconv(const ConvParams& p, cudaStream_t st) {
     }
 }
 
+int launch_cconv_lean(const ConvParams& p, cudaStream_t st, bool* handled);    // cconv_lean.cu
 int launch_cconv_wide(const ConvParams& p, cudaStream_t st, bool* handled);    // cconv_wide.cu
 int launch_cconv_direct(const ConvParams& p, cudaStream_t st, bool* handled);  // cconv_direct.cu
 std::atomic<int> g_kernel_options{3};
@@ -242,7 +243,16 @@ __global__ void __launch_bounds__(256) k_cconv_prepare(const ConvParams p, float
             // Order the chunk by the corner block's base cell (dropped pairs last): the conv kernels walk the records
             // in order, so consecutive pairs land in neighbouring cases of their scatter switch (instruction-cache
             // locality).  Bitonic sort of (key, lane) over the warp, then one gather of the 9 fields.
-            unsigned key = ((r.row >= 0 ? (unsigned)r.g.i0 : 0xffffffu) << 5) | (unsigned)lane;
+            // (key = linear index of the block's base cell, the corner-0 cell clamped to <= fs-2 per axis: exactly the
+            // case index of the register-patch kernels, so their merge walk consumes a chunk in one sweep)
+            unsigned cellkey = 0xffffffu;
+            if (r.row >= 0) {
+                const int nbx = max(p.gp.kx - 1, 1), nby = max(p.gp.ky - 1, 1);
+                const int bx = min(r.g.i0 & 0xff, nbx - 1), by = min((r.g.i0 >> 8) & 0xff, nby - 1);
+                const int bz = min((r.g.i0 >> 16) & 0xff, max(p.gp.kz - 1, 1) - 1);
+                cellkey = (unsigned)((bz * nby + by) * nbx + bx);
+            }
+            unsigned key = (cellkey << 5) | (unsigned)lane;
 #pragma unroll
             for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
@@ -331,6 +341,11 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
     if (options & 2) {  // resident-filter direct kernel for cout <= 4
         bool handled = false;
         rc = launch_cconv_direct(p, st, &handled);
+        if (rc || handled) return rc;
+    }
+    if ((options & 1) && !(options & 8)) {  // lean register-patch kernel (production path of the wide layers)
+        bool handled = false;
+        rc = launch_cconv_lean(p, st, &handled);
         if (rc || handled) return rc;
     }
     if (options & 1) {

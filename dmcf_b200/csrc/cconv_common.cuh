@@ -91,13 +91,17 @@ __device__ __forceinline__ PairRec load_pair(const ConvParams& p, int64_t n, boo
     if (!in_range) return r;
     const float* f = p.records + n;
     const int64_t P = p.n_pairs;
+    // all nine fields in flight together (no early return on a dropped pair: that would serialise two round trips)
     r.row = __float_as_int(__ldg(f));
-    if (r.row < 0) return r;
     r.g.i0 = __float_as_int(__ldg(f + P));
     r.g.i1 = __float_as_int(__ldg(f + 2 * P));
     r.g.wx0 = __ldg(f + 3 * P); r.g.wx1 = __ldg(f + 4 * P);
     r.g.wy0 = __ldg(f + 5 * P); r.g.wy1 = __ldg(f + 6 * P);
     r.g.wz0 = __ldg(f + 7 * P); r.g.wz1 = __ldg(f + 8 * P);
+    if (r.row < 0) {  // dropped pair: same all-zero record as eval_pair returns
+        r.g.i0 = r.g.i1 = 0;
+        r.g.wx0 = r.g.wx1 = r.g.wy0 = r.g.wy1 = r.g.wz0 = r.g.wz1 = 0.0f;
+    }
     return r;
 }
 

@@ -1,0 +1,514 @@
+// continuous_conv forward, "lean" register-patch kernel: the production path for the wide layers of a DMCF step
+// (compile-time filter grids 4x4x4 / 1x8x8 / 1x8x1, linear interpolation, cin <= 32, cout <= 32, cout % 4 == 0).
+//
+// Same algorithm as k_cconv_wide (cconv_wide.cu: one warp per out point, lane = input channel, the whole trilinear
+// patch of the point in registers, then patch x filter with split-K over the warps), rebuilt around what the round-1
+// measurements showed to bound that kernel (profiles/README.md):
+//   phase 1 was LATENCY bound: the register queue of gathered feature rows was shifted every pair, and a MOV of a
+//   register with a load in flight waits for the load, so every pair paid an L2 round trip (~500 cycles per pair and
+//   warp).  Here
+//     * the feature rows travel global -> shared memory with cp.async (LDGSTS) into a per-warp ring, four pairs ahead,
+//       and no register is tied to a load in flight;
+//     * NO indirect branch: the pairs of a chunk are ordered by the base cell of their corner block (done by
+//       dmcf_cconv_prepare, or by a warp bitonic sort here when the geometry is evaluated in-kernel) and the walk is a
+//       merge over the compile-time list of base cells -- `while (b == c) { 8 FFMA on static registers }`, cells that do
+//       not occur in the chunk skipped by a uniform bit test.  (nvcc lowers a 27-way switch to a compare tree plus
+//       three-entry jump tables: ~10 instructions and two dependent branches per pair.)  The order is verified when a
+//       chunk is built (one shuffle + vote) and restored by the in-kernel sort if a caller's records are not ordered;
+//     * feature rows are addressed with 32-bit byte offsets computed once per chunk; per-pair metadata
+//       {offset of pair j+4, base cell of pair j+1} is one LDS.64; chunks are null padded: no per-pair bounds checks;
+//     * the raw pair records of the NEXT chunk (also across the warp's points) are loaded before the walk.
+//   phase 2 was bound by the shared-memory -> register path (128 B/clk/SM = one word per lane and cycle for the whole
+//   SM): with 24 outputs per thread every FMA pair needed ~0.46 operand words.  Here
+//     * thread tile 6 points x 16 output channels (96 accumulators), the four quarter-warps take the four k of a
+//       k-quad: 22 operand words per 96 FMA (0.23), which puts the FFMA2 pipe and the operand path in balance;
+//       the quarter-warp partial sums meet in a two-step shuffle reduce-scatter, the warps' in shared memory;
+//     * the filter streams L2 -> shared memory through a per-warp cp.async ring, two k-quads ahead
+//       (one LDGSTS per k-quad per warp, no registers held by the prefetch).
+// Tensor cores are deliberately not used: with N = cout <= 32 a tcgen05 tile would be bound by the same shared-memory
+// operand reads, and float32 accuracy needs 3xTF32.
+#include <cuda_pipeline_primitives.h>
+
+#include "cconv_scatter.cuh"
+
+namespace dmcf {
+
+namespace lean {
+
+static constexpr int kGatherSlots = 4;    // feature rows in flight per warp (ring of 128-byte slots, 512-byte aligned)
+static constexpr int kMetaSlots = 40;     // int2 {byte offset of pair j+4 (or -1), base cell of pair j+1}
+static constexpr int kHeadWords = 8;      // offsets of pairs 0..3
+static constexpr int kWgtSlots = 36;      // 8 corner weights per pair
+static constexpr int kRecWords = 2 * kMetaSlots + kHeadWords + 8 * kWgtSlots;  // 376 words per warp
+static constexpr int kFilterSlots = 3;    // phase 2: filter k-quads in flight per warp (slots of 128 words): slot 0 is the
+                                          // warp's gather ring, slots 1..2 the head of its record block
+static constexpr int kScratchWords = kGatherSlots * 32 + kRecWords;            // per warp, both phases
+static_assert(kGatherSlots * 32 >= 128 && (kFilterSlots - 1) * 128 <= kRecWords, "the filter ring reuses the phase-1 scratch");
+
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+// next 128-byte slot of a 512-byte aligned ring of kGatherSlots slots
+__device__ __forceinline__ uint32_t ring_next(uint32_t saddr) {
+    return (saddr & ~(kGatherSlots * 128u - 1u)) | ((saddr + 128u) & (kGatherSlots * 128u - 1u));
+}
+
+// State of the walk over one chunk of compacted pair records.  Everything the current pair needs is already in
+// registers (loaded while the previous pair was scattered), so no shared-memory latency sits on the per-pair chain.
+struct Walk {
+    const int2* m2;   // metadata entry of the NEXT pair
+    const float* w;   // weights of the current pair
+    int2 mm;          // metadata of the current pair j: {offset of pair j+4 or -1, base cell of pair j+1}
+    float f;          // gathered feature of the current pair
+    uint32_t sa;      // this lane's word in the ring slot of the current pair
+    uint32_t sa_next; // ... and of the next pair
+    float4 wa, wb;    // corner weights of the current pair
+};
+
+// Pairs of base cell C: scatter the 8 corner weights of the current pair while the feature / metadata / weights of the
+// next one are fetched, and start the gather of pair j+4 into the slot of pair j.
+template <int KZ, int KY, int KX, bool RELU, bool FX, int C>
+__device__ __forceinline__ void merge_case(Walk& wk, float (&acc)[KZ * KY * KX], const char* fbase, int gate, float scale, float fc) {
+    int b_next;
+    do {
+        float f = wk.f;
+        const int2 mj = wk.mm;
+        const uint32_t sj = wk.sa;
+        cp_wait<kGatherSlots - 2>();  // the gather of pair j+1 has landed
+        wk.sa = wk.sa_next;
+        wk.f = lds_f32(wk.sa);
+        wk.sa_next = ring_next(wk.sa);
+        wk.mm = *wk.m2;
+        ++wk.m2;
+        if (RELU) f = fmaxf(f, 0.0f);
+        if (FX) f = fmaf(f, scale, fc);
+        scatter_case<KZ, KY, KX, 0, KZ, C>(acc, wk.wa, wk.wb, f);
+        wk.w += 8;
+        wk.wa = *reinterpret_cast<const float4*>(wk.w);
+        wk.wb = *reinterpret_cast<const float4*>(wk.w + 4);
+        if ((mj.x | gate) >= 0) cp_async4(sj, fbase + (unsigned)mj.x);
+        cp_commit();
+        b_next = mj.y;
+    } while (b_next == C);
+}
+
+// The chunk is ordered by base cell (checked when it is built), so a cell that occurs in the chunk (`present`, a warp-
+// uniform mask) is the current one when the merge reaches it: cells without pairs cost one uniform bit test.
+template <int KZ, int KY, int KX, bool RELU, bool FX, int C0, int N>
+__device__ __forceinline__ void merge_group(Walk& wk, unsigned present, float (&acc)[KZ * KY * KX], const char* fbase, int gate, float scale, float fc) {
+    if constexpr (N > 0) {
+        if (present & (1u << (C0 & 31))) merge_case<KZ, KY, KX, RELU, FX, C0>(wk, acc, fbase, gate, scale, fc);
+        merge_group<KZ, KY, KX, RELU, FX, C0 + 1, N - 1>(wk, present, acc, fbase, gate, scale, fc);
+    }
+}
+
+// One sweep over all base cells in ascending order; `present_*` = bit mask of the cells that occur in the chunk.
+template <int KZ, int KY, int KX, bool RELU, bool FX>
+__device__ __forceinline__ void sweep(Walk& wk, unsigned present_lo, unsigned present_hi, float (&acc)[KZ * KY * KX],
+                                      const char* fbase, int gate, float scale, float fc) {
+    using G = FilterGrid<KZ, KY, KX>;
+    constexpr int N_LO = G::NB < 32 ? G::NB : 32;
+    merge_group<KZ, KY, KX, RELU, FX, 0, N_LO>(wk, present_lo, acc, fbase, gate, scale, fc);
+    if constexpr (G::NB > 32) merge_group<KZ, KY, KX, RELU, FX, 32, G::NB - 32>(wk, present_hi, acc, fbase, gate, scale, fc);
+}
+
+}  // namespace lean
+
+template <int KZ, int KY, int KX, int MT, int NW, bool RELU, bool FX>
+__global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
+    using G = FilterGrid<KZ, KY, KX>;
+    constexpr int K = G::K;
+    constexpr int PPW = MT / NW;  // points per warp
+    static_assert(MT % NW == 0 && MT % 8 == 0, "tile shape");
+    constexpr int MTP = MT + 1;
+    extern __shared__ __align__(1024) float smem[];
+    // [NW gather rings of 512 B][patch tile, k-quad major [kc_pad/4][MT+1][4]; later [NW][MT][32]][NW record blocks][norm]
+    float* rings = smem;
+    float* patch = rings + (size_t)NW * lean::kGatherSlots * 32;
+    const size_t tile_words = (size_t)(p.kc_pad / 4) * MTP * 4, red_words = (size_t)NW * MT * 32;
+    float* recs = patch + (tile_words > red_words ? tile_words : red_words);
+    float* norm = recs + (size_t)NW * lean::kRecWords;  // [MT]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile_base = (int64_t)blockIdx.x * MT;
+    float* wrec = recs + (size_t)warp * lean::kRecWords;
+    int2* meta = reinterpret_cast<int2*>(wrec);                      // [kMetaSlots]
+    int* metai = reinterpret_cast<int*>(wrec);
+    int* head = metai + 2 * lean::kMetaSlots;                        // [kHeadWords]
+    float* wgt = wrec + 2 * lean::kMetaSlots + lean::kHeadWords;     // [kWgtSlots][8]
+    const bool lane_ci = lane < p.cin;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int stride_b = (int)p.inp_stride * 4;
+    const int gate = lane_ci ? 0 : (int)0x80000000;  // lanes beyond cin start no gathers (their patch column is never stored)
+    const char* fbase = reinterpret_cast<const char*>(p.inp_feat) + 4 * (lane_ci ? lane : p.cin - 1);
+    asm volatile("" : "+l"(fbase));  // keep base + lane offset as ONE 64-bit register: a gather address is a single 64-bit add
+    // this lane's word of the current gather slot (shared-window address; the ring is 512-byte aligned)
+    uint32_t sa = (uint32_t)__cvta_generic_to_shared(rings + (size_t)warp * lean::kGatherSlots * 32 + lane);
+
+    // ================= phase 1: patch rows of this warp's points =================
+    int64_t o = tile_base + warp;
+    bool o_ok = o < p.n_out;
+    int64_t rs = 0, re = 0;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (o_ok) {
+        rs = p.row_splits[o]; re = p.row_splits[o + 1];
+        ox = __ldg(p.out_pos + 3 * o); oy = __ldg(p.out_pos + 3 * o + 1); oz = __ldg(p.out_pos + 3 * o + 2);
+    }
+    PairRec cur = pair_record(p, rs + lane, rs + lane < re, ox, oy, oz);
+
+#pragma unroll 1
+    for (int i = 0; i < PPW; ++i) {
+        const int m = warp + i * NW;
+        // the warp's next point
+        const int64_t o_n = o + NW;
+        const bool n_ok = (i + 1 < PPW) && o_n < p.n_out;
+        int64_t rs_n = 0, re_n = 0;
+        float ox_n = 0.f, oy_n = 0.f, oz_n = 0.f;
+        if (n_ok) {
+            rs_n = p.row_splits[o_n]; re_n = p.row_splits[o_n + 1];
+            ox_n = __ldg(p.out_pos + 3 * o_n); oy_n = __ldg(p.out_pos + 3 * o_n + 1); oz_n = __ldg(p.out_pos + 3 * o_n + 2);
+        }
+        // first chunk of the next point: in flight during this whole point (a short last chunk would not cover it)
+        const PairRec first_n = pair_record(p, rs_n + lane, n_ok && rs_n + lane < re_n, ox_n, oy_n, oz_n);
+        float acc[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) acc[c] = 0.0f;
+        float fc = 0.0f;  // centre feature of the antisymmetric layer (out point o == input row o)
+        if (p.ascc && o_ok && lane_ci) {
+            fc = __ldg(p.inp_feat + o * p.inp_stride + lane);
+            if (RELU) fc = fmaxf(fc, 0.0f);
+            fc *= p.feat_scale;
+        }
+        float norm_acc = 0.0f;
+#pragma unroll 1
+        for (int64_t c0 = rs;; c0 += 32) {
+            const bool last = c0 + 32 >= re;
+            // ---- this chunk: raw records -> base form, compacted into the warp's scratch ----
+            int row = cur.row;
+            norm_acc += cur.norm;
+            int b = 0;
+            float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+            if (row >= 0) {
+                int bx, by, bz;
+                float xl, xh, yl, yh, zl, zh;
+                base_axis(KX, cur.g.i0 & 0xff, cur.g.wx0, cur.g.wx1, bx, xl, xh);
+                base_axis(KY, (cur.g.i0 >> 8) & 0xff, cur.g.wy0, cur.g.wy1, by, yl, yh);
+                base_axis(KZ, (cur.g.i0 >> 16) & 0xff, cur.g.wz0, cur.g.wz1, bz, zl, zh);
+                b = (bz * G::NBY + by) * G::NBX + bx;
+                wa = make_float4(xl * yl * zl, xh * yl * zl, xl * yh * zl, xh * yh * zl);
+                wb = make_float4(xl * yl * zh, xh * yl * zh, xl * yh * zh, xh * yh * zh);
+            }
+            // The walk needs the chunk ordered by base cell, dropped pairs last.  dmcf_cconv_prepare writes its records in
+            // that order; geometry evaluated in-kernel arrives in neighbour-list order.  Check, and sort if needed (warp
+            // bitonic sort of (cell, lane), then pull the fields from the source lane).
+            const unsigned cellkey = row >= 0 ? (unsigned)b : 0xffffffu;
+            const unsigned prevkey = __shfl_up_sync(0xffffffffu, cellkey, 1);
+            if (!__all_sync(0xffffffffu, lane == 0 || prevkey <= cellkey)) {
+                unsigned key = (cellkey << 5) | (unsigned)lane;
+#pragma unroll
+                for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        const unsigned other = __shfl_xor_sync(0xffffffffu, key, j);
+                        const bool up = ((lane & k) == 0), lower = ((lane & j) == 0);
+                        const unsigned mn = min(key, other), mx = max(key, other);
+                        key = (up == lower) ? mn : mx;
+                    }
+                }
+                const int src = key & 31;
+                row = __shfl_sync(0xffffffffu, row, src);
+                b = __shfl_sync(0xffffffffu, b, src);
+                wa.x = __shfl_sync(0xffffffffu, wa.x, src); wa.y = __shfl_sync(0xffffffffu, wa.y, src);
+                wa.z = __shfl_sync(0xffffffffu, wa.z, src); wa.w = __shfl_sync(0xffffffffu, wa.w, src);
+                wb.x = __shfl_sync(0xffffffffu, wb.x, src); wb.y = __shfl_sync(0xffffffffu, wb.y, src);
+                wb.z = __shfl_sync(0xffffffffu, wb.z, src); wb.w = __shfl_sync(0xffffffffu, wb.w, src);
+            }
+            const bool valid = row >= 0;
+            const unsigned present_lo = __reduce_or_sync(0xffffffffu, (valid && b < 32) ? 1u << b : 0u);
+            const unsigned present_hi = G::NB > 32 ? __reduce_or_sync(0xffffffffu, (valid && b >= 32) ? 1u << (b - 32) : 0u) : 0u;
+            const unsigned active = __ballot_sync(0xffffffffu, valid);
+            const int cnt = __popc(active);
+            __syncwarp();  // previous chunk fully consumed
+            // pair at compacted position pos: offset -> entry pos-4 (.x), base cell -> entry pos-1 (.y); the first four
+            // offsets and the first base cell go to `head`
+            auto put_meta = [&](int pos, int off, int bb) {
+                if (pos >= lean::kGatherSlots) metai[2 * (pos - lean::kGatherSlots)] = off; else head[pos] = off;
+                if (pos >= 1) metai[2 * (pos - 1) + 1] = bb; else head[4] = bb;
+            };
+            if (valid) {
+                const int pos = __popc(active & lt_mask);
+                put_meta(pos, row * stride_b, b);
+                *reinterpret_cast<float4*>(wgt + pos * 8) = wa;
+                *reinterpret_cast<float4*>(wgt + pos * 8 + 4) = wb;
+            }
+            if (lane < 8) put_meta(cnt + lane, -1, G::NB);  // eight null pairs: no gather, cell NB = end of chunk
+            __syncwarp();
+            // ---- raw records of this point's next chunk: in flight during the walk ----
+            if (!last) cur = pair_record(p, c0 + 32 + lane, c0 + 32 + lane < re, ox, oy, oz);
+            // ---- walk the chunk: merge over the base cells ----
+            if (cnt > 0) {
+                lean::Walk wk;
+                {
+                    // gathers of pairs 0..3 into the ring slots following the current one (every earlier gather of this
+                    // warp has been consumed: null pairs never start one)
+                    const int4 h = *reinterpret_cast<const int4*>(head);
+                    uint32_t s = sa;
+                    if ((h.x | gate) >= 0) lean::cp_async4(s, fbase + (unsigned)h.x);
+                    lean::cp_commit(); s = lean::ring_next(s);
+                    if ((h.y | gate) >= 0) lean::cp_async4(s, fbase + (unsigned)h.y);
+                    lean::cp_commit(); s = lean::ring_next(s);
+                    if ((h.z | gate) >= 0) lean::cp_async4(s, fbase + (unsigned)h.z);
+                    lean::cp_commit(); s = lean::ring_next(s);
+                    if ((h.w | gate) >= 0) lean::cp_async4(s, fbase + (unsigned)h.w);
+                    lean::cp_commit();
+                    lean::cp_wait<lean::kGatherSlots - 1>();  // pair 0 has landed
+                    wk.sa = sa;
+                    wk.sa_next = lean::ring_next(sa);
+                    wk.f = lean::lds_f32(sa);
+                    wk.mm = meta[0];
+                    wk.m2 = meta + 1;
+                    wk.w = wgt;
+                    wk.wa = *reinterpret_cast<const float4*>(wgt);
+                    wk.wb = *reinterpret_cast<const float4*>(wgt + 4);
+                }
+                const float scale = p.feat_scale;
+                lean::sweep<KZ, KY, KX, RELU, FX>(wk, present_lo, present_hi, acc, fbase, gate, scale, fc);
+                sa = wk.sa;
+            }
+            if (last) break;
+        }
+        // ---- patch row -> shared memory (lane = channel: conflict free), Dense columns, padding ----
+        if (!o_ok) {
+            for (int k = lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
+        } else {
+            if (lane_ci) {
+                if ((p.cin & 3) == 0) {  // k = c*cin + lane: the k-quad advances by cin/4 per cell -> one running pointer
+                    float* pp = patch + patchq_index<MT>(m, lane);
+                    const int step = p.cin * MTP;
+#pragma unroll
+                    for (int c = 0; c < K; ++c) pp[c * step] = acc[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < K; ++c) patch[patchq_index<MT>(m, c * p.cin + lane)] = acc[c];
+                }
+            }
+            if (p.dense_cin > 0) {
+                const float* drow = p.dense_inp + o * p.dense_stride;
+                for (int ci = lane; ci < p.dense_cin; ci += 32) {
+                    float f = __ldg(drow + ci);
+                    if (p.relu_input) f = fmaxf(f, 0.0f);
+                    patch[patchq_index<MT>(m, p.kc_conv + ci)] = f;
+                }
+            }
+            for (int k = p.kc + lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
+            if (p.normalize) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) norm_acc += __shfl_xor_sync(0xffffffffu, norm_acc, off);
+                if (lane == 0) norm[m] = norm_acc;
+            }
+        }
+        o = o_n; o_ok = n_ok; rs = rs_n; re = re_n; ox = ox_n; oy = oy_n; oz = oz_n;
+        cur = first_n;
+    }
+    lean::cp_wait<0>();
+
+    // ================= phase 2: [MT x kc] x [kc x cout], split-K over the warps and over the quarter-warps =================
+    // lane = (q = lane / 8: k = 4*kq + q, pr = (lane / 2) % 4: points 6*pr..6*pr+5, cc = lane % 2: channels 16*cc..16*cc+15)
+    static_assert(MT == 24, "phase 2 thread tile assumes 24 points per CTA");
+    const int kq_total = p.kc_pad / 4;
+    const int cout = p.cout;
+    // filter ring [kFilterSlots][4 rows][cout] in this warp's phase-1 scratch (its phase 1 is complete, nobody else
+    // touches it): slot 0 = the gather ring, slots 1.. = the record block
+    float* gring = rings + (size_t)warp * lean::kGatherSlots * 32;
+    float* const slot0 = gring, * const slot1 = wrec, * const slot2 = wrec + 128;
+    const int n_it = kq_total > warp ? (kq_total - warp + NW - 1) / NW : 0;
+    // lane L moves the L-th float4 of a k-quad (4 consecutive filter rows = cout float4s).  Rows >= kc exist only in the
+    // last k-quad; they are read from row kc-1 instead (their patch columns are zero).
+    const bool cp_lane = lane < cout;
+    const int cp_row = (lane * 4) / cout;
+    const float* fsrc = p.filters + (size_t)warp * 4 * cout + lane * 4;  // this lane's float4 of the next k-quad to fetch
+    const size_t fstep = (size_t)NW * 4 * cout;
+    const int it_last = (kq_total - 1) / NW;
+    const int last_fix = ((kq_total - 1) % NW == warp && (kq_total - 1) * 4 + cp_row > p.kc - 1)
+                             ? ((kq_total - 1) * 4 + cp_row - (p.kc - 1)) * cout : 0;
+    auto issue = [&](int it, float* slot) {  // fetch k-quad warp + it*NW into `slot`
+        const float* src = fsrc - (it == it_last ? last_fix : 0);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + lane * 4);
+        const int pred = (it < n_it) && cp_lane;
+        asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.cg.shared.global [%0], [%1], 16; }"
+                     ::"r"(dst), "l"(src), "r"(pred));
+        lean::cp_commit();
+        fsrc += fstep;
+    };
+    __syncwarp();
+    issue(0, slot0); issue(1, slot1);
+    __syncthreads();  // patch tile complete
+    if (p.debug_wrap_w & 2) {  // timing experiment: phase 1 only
+        lean::cp_wait<0>();
+        return;
+    }
+
+    const int q = lane >> 3, pr = (lane >> 1) & 3, cc = lane & 1;
+    // this thread's four float4s of filter row q in each ring slot (channel offsets clamped: lanes beyond cout recompute
+    // the last quad)
+    const float4* fw0[4]; const float4* fw1[4]; const float4* fw2[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        const int off = q * cout + min(cc * 16 + 4 * h, cout - 4);
+        fw0[h] = reinterpret_cast<const float4*>(slot0 + off);
+        fw1[h] = reinterpret_cast<const float4*>(slot1 + off);
+        fw2[h] = reinterpret_cast<const float4*>(slot2 + off);
+    }
+    float2 acc2[6][8];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int h = 0; h < 8; ++h) acc2[i][h] = make_float2(0.0f, 0.0f);
+    const float* pw = patch + ((size_t)warp * MTP + pr * 6) * 4 + q;  // word q of point 6*pr of k-quad `warp`
+    // one k-quad: operands of slot FR, refill of the slot consumed in the previous step (WS) with k-quad it+2
+#define DMCF_LEAN_STEP(FR, WS)                                                                                   \
+    {                                                                                                            \
+        lean::cp_wait<1>();                                                                                      \
+        __syncwarp(); /* every lane's part of this slot landed; every lane is done with the previous slot */    \
+        float4 w[4];                                                                                             \
+        _Pragma("unroll") for (int h = 0; h < 4; ++h) w[h] = *FR[h];                                              \
+        float pv[6];                                                                                             \
+        _Pragma("unroll") for (int i = 0; i < 6; ++i) pv[i] = pw[i * 4];                                          \
+        issue(it + 2, WS);                                                                                       \
+        pw += (size_t)NW * MTP * 4;                                                                              \
+        _Pragma("unroll") for (int i = 0; i < 6; ++i) {                                                          \
+            const float2 pp = make_float2(pv[i], pv[i]);                                                         \
+            _Pragma("unroll") for (int h = 0; h < 4; ++h) {                                                      \
+                acc2[i][2 * h] = __ffma2_rn(pp, make_float2(w[h].x, w[h].y), acc2[i][2 * h]);                    \
+                acc2[i][2 * h + 1] = __ffma2_rn(pp, make_float2(w[h].z, w[h].w), acc2[i][2 * h + 1]);            \
+            }                                                                                                    \
+        }                                                                                                        \
+        ++it;                                                                                                    \
+    }
+    {
+        int it = 0;
+#pragma unroll 1
+        while (it + 3 <= n_it) {
+            DMCF_LEAN_STEP(fw0, slot2)
+            DMCF_LEAN_STEP(fw1, slot0)
+            DMCF_LEAN_STEP(fw2, slot1)
+        }
+        if (it < n_it) DMCF_LEAN_STEP(fw0, slot2)
+        if (it < n_it) DMCF_LEAN_STEP(fw1, slot0)
+    }
+#undef DMCF_LEAN_STEP
+    lean::cp_wait<0>();
+    // ---- quarter-warp partial sums: reduce-scatter over lanes ^16 (keeps 3 of the 6 points) and ^8 (8 of the 16 channels)
+    float2 a1[3][8];
+    {
+        const bool hi = (q & 2) != 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+                const float2 keep = hi ? acc2[i + 3][h] : acc2[i][h];
+                const float2 send = hi ? acc2[i][h] : acc2[i + 3][h];
+                a1[i][h].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 16);
+                a1[i][h].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 16);
+            }
+    }
+    float2 a2[3][4];
+    {
+        const bool hi = (q & 1) != 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float2 keep = hi ? a1[i][h + 4] : a1[i][h];
+                const float2 send = hi ? a1[i][h] : a1[i][h + 4];
+                a2[i][h].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 8);
+                a2[i][h].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 8);
+            }
+    }
+    __syncthreads();  // the patch is dead: partial sums reuse its storage
+    float* red = patch;  // [NW][MT][32]
+    {
+        // this thread now owns points 6*pr + 3*(q>>1) + i, channels 16*cc + 8*(q&1) + 0..7
+        const int m0 = pr * 6 + 3 * (q >> 1), c0 = cc * 16 + 8 * (q & 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float* r = red + ((size_t)warp * MT + m0 + i) * 32 + c0;
+            if (c0 < cout) *reinterpret_cast<float4*>(r) = make_float4(a2[i][0].x, a2[i][0].y, a2[i][1].x, a2[i][1].y);
+            if (c0 + 4 < cout) *reinterpret_cast<float4*>(r + 4) = make_float4(a2[i][2].x, a2[i][2].y, a2[i][3].x, a2[i][3].y);
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < MT * 32; t += NW * 32) {
+        const int m = t >> 5, c = t & 31;
+        const int64_t oo = tile_base + m;
+        if (oo < p.n_out && c < cout) {
+            float v = 0.0f;
+#pragma unroll
+            for (int w2 = 0; w2 < NW; ++w2) v += red[((size_t)w2 * MT + m) * 32 + c];
+            if (p.normalize) {
+                const float nv = norm[m];
+                if (nv != 0.0f) v /= nv;
+            }
+            if (p.bias) v += __ldg(p.bias + c);
+            if (p.residual) v += __ldg(p.residual + oo * p.residual_stride + c);
+            float* dst = p.out + oo * p.out_stride + c;
+            if (p.accumulate) v += *dst;
+            *dst = v;
+        }
+    }
+}
+
+static size_t lean_smem_bytes(int mt, int nw, int kc_pad) {
+    const size_t tile = (size_t)(kc_pad / 4) * (mt + 1) * 4, red = (size_t)nw * mt * 32;
+    return ((tile > red ? tile : red) + (size_t)nw * lean::kScratchWords + mt) * sizeof(float);
+}
+
+template <int KZ, int KY, int KX>
+static int launch_lean_grid(const ConvParams& p, cudaStream_t st, bool* handled) {
+    constexpr int MT = 24, NW = 12;
+    *handled = false;
+    if (lean_smem_bytes(MT, NW, p.kc_pad) > 227 * 1024) return DMCF_OK;
+    static bool attr_set = false;
+    // [relu on the input][feature scale and/or the antisymmetric centre term]
+    void (*kerns[2][2])(const ConvParams) = {
+        {k_cconv_lean<KZ, KY, KX, MT, NW, false, false>, k_cconv_lean<KZ, KY, KX, MT, NW, false, true>},
+        {k_cconv_lean<KZ, KY, KX, MT, NW, true, false>, k_cconv_lean<KZ, KY, KX, MT, NW, true, true>}};
+    if (!attr_set) {
+        for (int i = 0; i < 4; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kerns[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_lean)");
+        }
+        attr_set = true;
+    }
+    *handled = true;
+    const int64_t tiles = ceil_div(p.n_out, MT);
+    const bool fx = p.ascc || p.feat_scale != 1.0f;
+    kerns[p.relu_input ? 1 : 0][fx ? 1 : 0]<<<(unsigned)tiles, NW * 32, lean_smem_bytes(MT, NW, p.kc_pad), st>>>(p);
+    DMCF_LAUNCH_CHECK("k_cconv_lean");
+    return DMCF_OK;
+}
+
+// Tries the lean kernel; *handled = false means "not eligible" (the caller falls back to k_cconv_wide / k_cconv_tile).
+int launch_cconv_lean(const ConvParams& p, cudaStream_t st, bool* handled) {
+    *handled = false;
+    if (p.gp.interp != DMCF_INTERP_LINEAR || p.cin > 32) return DMCF_OK;
+    if (p.cout % 4 != 0 || p.cout > 32 || ((uintptr_t)p.filters & 15) != 0) return DMCF_OK;
+    // feature rows are addressed with 32-bit byte offsets
+    if ((p.n_inp > 0 ? p.n_inp : 1) * p.inp_stride * 4 >= ((int64_t)1 << 31)) return DMCF_OK;
+    if (p.gp.kz == 4 && p.gp.ky == 4 && p.gp.kx == 4) return launch_lean_grid<4, 4, 4>(p, st, handled);
+    if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 8) return launch_lean_grid<1, 8, 8>(p, st, handled);
+    if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 1) return launch_lean_grid<1, 8, 1>(p, st, handled);
+    return DMCF_OK;
+}
+
+}  // namespace dmcf

@@ -408,7 +408,9 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
 
 
 def set_kernel_options(options):
-    """bit 0: register-patch kernel for wide layers (default on).  Returns the previous mask."""
+    """bit 0: register-patch kernels for wide layers (k_cconv_lean, default on), bit 1: direct kernel for cout <= 4,
+    bit 2: z-split launches of the legacy k_cconv_wide, bit 3: legacy k_cconv_wide instead of k_cconv_lean.
+    Returns the previous mask."""
     return int(_lib.load().dmcf_set_kernel_options(int(options)))
 
 
@@ -419,7 +421,9 @@ def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0):
     if cout <= 4 and (kc * cout + 4 + 16 * 32 * 12) * 4 <= 200 * 1024:
         return "k_cconv_direct"
     if interpolation == "linear" and cin <= 32 and cout % 4 == 0 and (kz, ky, kx) in ((4, 4, 4), (1, 8, 8), (1, 8, 1)):
-        return "k_cconv_wide"
+        kc_pad = (kc + 3) // 4 * 4
+        lean_smem = (max(kc_pad // 4 * 25 * 4, 12 * 24 * 32) + 12 * 384 + 24) * 4
+        return "k_cconv_lean" if cout <= 32 and lean_smem <= 227 * 1024 else "k_cconv_wide"
     return "k_cconv_tile"
 
 

@@ -148,9 +148,11 @@ int dmcf_cconv_prepare(const dmcf_conv_desc* desc, const float* out_positions, i
                        const int32_t* neighbors_index, const int64_t* neighbors_row_splits,
                        const float* neighbors_importance, int64_t n_pairs, float* records, void* stream);
 
-/* Kernel selection bit mask (default 3): bit 0 = register-patch kernel for compile-time filter grids (k_cconv_wide),
- * bit 1 = resident-filter direct kernel for cout <= 4 (k_cconv_direct), bit 2 = run 4x4x4 wide layers as two z-half
- * launches with two CTAs per SM (measured on par with the single launch, off by default); 0 forces the generic kernel.  Returns the previous mask.  Results agree to float32 rounding. */
+/* Kernel selection bit mask (default 3): bit 0 = register-patch kernels for compile-time filter grids (k_cconv_lean;
+ * k_cconv_wide where the lean kernel is not eligible), bit 1 = resident-filter direct kernel for cout <= 4
+ * (k_cconv_direct), bit 2 = run 4x4x4 layers of the legacy k_cconv_wide as two z-half launches, bit 3 = use the legacy
+ * k_cconv_wide instead of k_cconv_lean (kept for A/B measurements); 0 forces the generic kernel.  Returns the previous
+ * mask.  Results agree to float32 rounding. */
 int dmcf_set_kernel_options(int options);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -132,10 +132,16 @@ CONV_CASES = [
     ("direct_cout1_cin40", (3, 3, 3), 40, 1, "ball_to_cube_radial", "linear", True, True, "poly6", False),
     ("direct_cout2_188", (1, 8, 8), 32, 2, "ball_to_cube_volume_preserving", "linear", True, False, "peak", True),
     ("direct_cout4_border", (3, 3, 3), 6, 4, "ball_to_cube_radial", "linear_border", False, False, "peak", True),
+    # long neighbour rows (mean ~60, max > 96: several 32-pair chunks per out point, chunk prefetch across points)
+    ("wide444_long_rows", (4, 4, 4), 32, 32, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False, 0.5),
+    ("wide188_long_rows", (1, 8, 8), 16, 24, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", True, 0.3),
+    ("wide444_cin7_cout12", (4, 4, 4), 7, 12, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False, 0.4),
+    # lattice without jitter: neighbours exactly on the filter border (g == fs-1), ties in the cell order
+    ("wide444_lattice", (4, 4, 4), 8, 8, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False, "lattice"),
 ]
 
 
-@pytest.fixture(params=[3, 7, 0], ids=["fast-kernels", "fast-kernels-zsplit", "generic-kernel"])
+@pytest.fixture(params=[3, 11, 15, 0], ids=["fast-kernels", "legacy-wide", "legacy-wide-zsplit", "generic-kernel"])
 def kernel_options(request):
     from dmcf_b200 import ops
     prev = ops.set_kernel_options(request.param)
@@ -147,7 +153,8 @@ def kernel_options(request):
 @pytest.mark.parametrize("fused_window", [False, True])
 def test_continuous_conv_matches_oracle(cuda, case, fused_window, kernel_options):
     from dmcf_b200 import ops
-    name, ks, cin, cout, mapping, interp, align, normalize, window, ignore_q = case
+    name, ks, cin, cout, mapping, interp, align, normalize, window, ignore_q = case[:10]
+    variant = case[10] if len(case) > 10 else None
     rng = np.random.default_rng(zlib.crc32(name.encode()))
     n_in, n_out = 900, 700
     pts = rng.random((n_in, 3)).astype(np.float32)
@@ -158,9 +165,13 @@ def test_continuous_conv_matches_oracle(cuda, case, fused_window, kernel_options
     outp = pts[:n_out].copy()
     outp[n_out // 2:] += rng.normal(0, 0.01, (n_out - n_out // 2, 3)).astype(np.float32) * (pts[:1] * 0 + (np.array(ks[::-1]) > 1))
     outp = outp.astype(np.float32)
+    if variant == "lattice":  # 10x10x9 lattice of pitch 1/16, extent = 4 pitches: neighbours at exactly r along the axes
+        g = np.stack(np.meshgrid(np.arange(10), np.arange(10), np.arange(9), indexing="ij"), -1).reshape(-1, 3)
+        pts = (g.astype(np.float32) * np.float32(0.0625))
+        outp = pts[:n_out].copy()
     feats = rng.standard_normal((n_in, cin)).astype(np.float32)
     filt = rng.uniform(-0.5, 0.5, ks + (cin, cout)).astype(np.float32)
-    extent = np.float32(0.25)
+    extent = np.float32(variant if isinstance(variant, float) else 0.25)
     radius = np.float32(0.5) * extent
     idx, splits, d2 = o64.fixed_radius_search(pts, outp, radius, ignore_query_point=ignore_q)
     imp = None
