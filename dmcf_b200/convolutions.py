@@ -185,7 +185,8 @@ class ContinuousConv(torch.nn.Module):
                                   align_corners=self.align_corners, coordinate_mapping=self.coordinate_mapping,
                                   normalize=self.normalize, interpolation=self.interpolation,
                                   window=fused_window.typ if fused_window else None,
-                                  window_fac=fused_window.fac if fused_window else 1.0, ascc=self.symmetric)
+                                  window_fac=fused_window.fac if fused_window else 1.0, ascc=self.symmetric,
+                                  antisymmetric_filter=self.symmetric and not self.circular)
         self._conv_output = out
         if self.use_dense_layer_for_center:
             out = out + ops.dense(inp_features, self.dense_kernel)

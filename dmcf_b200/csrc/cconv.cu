@@ -177,6 +177,7 @@ static int launch_cconv(const ConvParams& p, cudaStream_t st) {
 }
 
 int launch_cconv_lean(const ConvParams& p, cudaStream_t st, bool* handled);    // cconv_lean.cu
+int launch_cconv_apatch(const ConvParams& p, cudaStream_t st, bool* handled);  // cconv_apatch.cu
 int launch_cconv_wide(const ConvParams& p, cudaStream_t st, bool* handled);    // cconv_wide.cu
 int launch_cconv_direct(const ConvParams& p, cudaStream_t st, bool* handled);  // cconv_direct.cu
 std::atomic<int> g_kernel_options{3};
@@ -214,7 +215,7 @@ static int fill_params(const dmcf_conv_desc* d, const float* filters, const floa
     }
     p.relu_input = d->relu_input; p.feat_scale = d->feat_scale;
     p.ascc = d->ascc; p.skip_self = d->skip_self; p.nbr_lo = d->nbr_lo; p.nbr_hi = d->nbr_hi;
-    p.dense_cin = d->dense_cin; p.accumulate = d->accumulate;
+    p.dense_cin = d->dense_cin; p.accumulate = d->accumulate; p.filter_antisym = d->filter_antisym;
     const int64_t cells = (int64_t)p.gp.kx * p.gp.ky * p.gp.kz;
     DMCF_REQUIRE(cells * d->cin + d->dense_cin < (1 << 24), "cconv: filter too large");
     p.kc_conv = (int)(cells * d->cin);
@@ -338,6 +339,11 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
     const int options = g_kernel_options.load(std::memory_order_relaxed);
     p.debug_wrap_w = (options >> 8) & 15;
     p.use_zsplit = (options >> 2) & 1;
+    if ((options & 2) && !(options & 16)) {  // folded half-patch kernel for the antisymmetric output layer
+        bool handled = false;
+        rc = launch_cconv_apatch(p, st, &handled);
+        if (rc || handled) return rc;
+    }
     if (options & 2) {  // resident-filter direct kernel for cout <= 4
         bool handled = false;
         rc = launch_cconv_direct(p, st, &handled);

@@ -14,6 +14,7 @@ struct ConvParams {
     int ascc, skip_self, nbr_lo, nbr_hi, dense_cin, accumulate;
     int kc_conv, kc, kc_pad;  // patch columns: conv part, conv+dense, padded to 4
     int debug_wrap_w;         // timing experiment switches (dmcf_set_kernel_options bits 8+), never set in production
+    int filter_antisym;       // desc flag: filters[rev(cell)] == -filters[cell]
     int use_zsplit;           // option bit 2: run 4x4x4 wide layers as two z-half launches (2 CTAs/SM)
     int cip, cp;              // pow2 lane groupings for input / output channels
     const float* filters;

@@ -29,100 +29,10 @@
 // operand reads, and float32 accuracy needs 3xTF32.
 #include <cuda_pipeline_primitives.h>
 
-#include "cconv_scatter.cuh"
+#include "cconv_walk.cuh"
 
 namespace dmcf {
 
-namespace lean {
-
-static constexpr int kGatherSlots = 4;    // feature rows in flight per warp (ring of 128-byte slots, 512-byte aligned)
-static constexpr int kMetaSlots = 40;     // int2 {byte offset of pair j+4 (or -1), base cell of pair j+1}
-static constexpr int kHeadWords = 8;      // offsets of pairs 0..3
-static constexpr int kWgtSlots = 36;      // 8 corner weights per pair
-static constexpr int kRecWords = 2 * kMetaSlots + kHeadWords + 8 * kWgtSlots;  // 376 words per warp
-static constexpr int kFilterSlots = 3;    // phase 2: filter k-quads in flight per warp (slots of 128 words): slot 0 is the
-                                          // warp's gather ring, slots 1..2 the head of its record block
-static constexpr int kScratchWords = kGatherSlots * 32 + kRecWords;            // per warp, both phases
-static_assert(kGatherSlots * 32 >= 128 && (kFilterSlots - 1) * 128 <= kRecWords, "the filter ring reuses the phase-1 scratch");
-
-__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* gptr) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr));
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N));
-}
-__device__ __forceinline__ float lds_f32(uint32_t saddr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
-    return v;
-}
-// next 128-byte slot of a 512-byte aligned ring of kGatherSlots slots
-__device__ __forceinline__ uint32_t ring_next(uint32_t saddr) {
-    return (saddr & ~(kGatherSlots * 128u - 1u)) | ((saddr + 128u) & (kGatherSlots * 128u - 1u));
-}
-
-// State of the walk over one chunk of compacted pair records.  Everything the current pair needs is already in
-// registers (loaded while the previous pair was scattered), so no shared-memory latency sits on the per-pair chain.
-struct Walk {
-    const int2* m2;   // metadata entry of the NEXT pair
-    const float* w;   // weights of the current pair
-    int2 mm;          // metadata of the current pair j: {offset of pair j+4 or -1, base cell of pair j+1}
-    float f;          // gathered feature of the current pair
-    uint32_t sa;      // this lane's word in the ring slot of the current pair
-    uint32_t sa_next; // ... and of the next pair
-    float4 wa, wb;    // corner weights of the current pair
-};
-
-// Pairs of base cell C: scatter the 8 corner weights of the current pair while the feature / metadata / weights of the
-// next one are fetched, and start the gather of pair j+4 into the slot of pair j.
-template <int KZ, int KY, int KX, bool RELU, bool FX, int C>
-__device__ __forceinline__ void merge_case(Walk& wk, float (&acc)[KZ * KY * KX], const char* fbase, int gate, float scale, float fc) {
-    int b_next;
-    do {
-        float f = wk.f;
-        const int2 mj = wk.mm;
-        const uint32_t sj = wk.sa;
-        cp_wait<kGatherSlots - 2>();  // the gather of pair j+1 has landed
-        wk.sa = wk.sa_next;
-        wk.f = lds_f32(wk.sa);
-        wk.sa_next = ring_next(wk.sa);
-        wk.mm = *wk.m2;
-        ++wk.m2;
-        if (RELU) f = fmaxf(f, 0.0f);
-        if (FX) f = fmaf(f, scale, fc);
-        scatter_case<KZ, KY, KX, 0, KZ, C>(acc, wk.wa, wk.wb, f);
-        wk.w += 8;
-        wk.wa = *reinterpret_cast<const float4*>(wk.w);
-        wk.wb = *reinterpret_cast<const float4*>(wk.w + 4);
-        if ((mj.x | gate) >= 0) cp_async4(sj, fbase + (unsigned)mj.x);
-        cp_commit();
-        b_next = mj.y;
-    } while (b_next == C);
-}
-
-// The chunk is ordered by base cell (checked when it is built), so a cell that occurs in the chunk (`present`, a warp-
-// uniform mask) is the current one when the merge reaches it: cells without pairs cost one uniform bit test.
-template <int KZ, int KY, int KX, bool RELU, bool FX, int C0, int N>
-__device__ __forceinline__ void merge_group(Walk& wk, unsigned present, float (&acc)[KZ * KY * KX], const char* fbase, int gate, float scale, float fc) {
-    if constexpr (N > 0) {
-        if (present & (1u << (C0 & 31))) merge_case<KZ, KY, KX, RELU, FX, C0>(wk, acc, fbase, gate, scale, fc);
-        merge_group<KZ, KY, KX, RELU, FX, C0 + 1, N - 1>(wk, present, acc, fbase, gate, scale, fc);
-    }
-}
-
-// One sweep over all base cells in ascending order; `present_*` = bit mask of the cells that occur in the chunk.
-template <int KZ, int KY, int KX, bool RELU, bool FX>
-__device__ __forceinline__ void sweep(Walk& wk, unsigned present_lo, unsigned present_hi, float (&acc)[KZ * KY * KX],
-                                      const char* fbase, int gate, float scale, float fc) {
-    using G = FilterGrid<KZ, KY, KX>;
-    constexpr int N_LO = G::NB < 32 ? G::NB : 32;
-    merge_group<KZ, KY, KX, RELU, FX, 0, N_LO>(wk, present_lo, acc, fbase, gate, scale, fc);
-    if constexpr (G::NB > 32) merge_group<KZ, KY, KX, RELU, FX, 32, G::NB - 32>(wk, present_hi, acc, fbase, gate, scale, fc);
-}
-
-}  // namespace lean
 
 template <int KZ, int KY, int KX, int MT, int NW, bool RELU, bool FX>
 __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
@@ -142,18 +52,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile_base = (int64_t)blockIdx.x * MT;
     float* wrec = recs + (size_t)warp * lean::kRecWords;
-    int2* meta = reinterpret_cast<int2*>(wrec);                      // [kMetaSlots]
-    int* metai = reinterpret_cast<int*>(wrec);
-    int* head = metai + 2 * lean::kMetaSlots;                        // [kHeadWords]
-    float* wgt = wrec + 2 * lean::kMetaSlots + lean::kHeadWords;     // [kWgtSlots][8]
     const bool lane_ci = lane < p.cin;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int stride_b = (int)p.inp_stride * 4;
-    const int gate = lane_ci ? 0 : (int)0x80000000;  // lanes beyond cin start no gathers (their patch column is never stored)
-    const char* fbase = reinterpret_cast<const char*>(p.inp_feat) + 4 * (lane_ci ? lane : p.cin - 1);
-    asm volatile("" : "+l"(fbase));  // keep base + lane offset as ONE 64-bit register: a gather address is a single 64-bit add
-    // this lane's word of the current gather slot (shared-window address; the ring is 512-byte aligned)
-    uint32_t sa = (uint32_t)__cvta_generic_to_shared(rings + (size_t)warp * lean::kGatherSlots * 32 + lane);
+    lean::WarpCtx cx;
+    cx.init(rings + (size_t)warp * lean::kGatherSlots * 32, wrec, p, lane);
 
     // ================= phase 1: patch rows of this warp's points =================
     int64_t o = tile_base + warp;
@@ -189,104 +90,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
             if (RELU) fc = fmaxf(fc, 0.0f);
             fc *= p.feat_scale;
         }
-        float norm_acc = 0.0f;
-#pragma unroll 1
-        for (int64_t c0 = rs;; c0 += 32) {
-            const bool last = c0 + 32 >= re;
-            // ---- this chunk: raw records -> base form, compacted into the warp's scratch ----
-            int row = cur.row;
-            norm_acc += cur.norm;
-            int b = 0;
-            float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
-            if (row >= 0) {
-                int bx, by, bz;
-                float xl, xh, yl, yh, zl, zh;
-                base_axis(KX, cur.g.i0 & 0xff, cur.g.wx0, cur.g.wx1, bx, xl, xh);
-                base_axis(KY, (cur.g.i0 >> 8) & 0xff, cur.g.wy0, cur.g.wy1, by, yl, yh);
-                base_axis(KZ, (cur.g.i0 >> 16) & 0xff, cur.g.wz0, cur.g.wz1, bz, zl, zh);
-                b = (bz * G::NBY + by) * G::NBX + bx;
-                wa = make_float4(xl * yl * zl, xh * yl * zl, xl * yh * zl, xh * yh * zl);
-                wb = make_float4(xl * yl * zh, xh * yl * zh, xl * yh * zh, xh * yh * zh);
-            }
-            // The walk needs the chunk ordered by base cell, dropped pairs last.  dmcf_cconv_prepare writes its records in
-            // that order; geometry evaluated in-kernel arrives in neighbour-list order.  Check, and sort if needed (warp
-            // bitonic sort of (cell, lane), then pull the fields from the source lane).
-            const unsigned cellkey = row >= 0 ? (unsigned)b : 0xffffffu;
-            const unsigned prevkey = __shfl_up_sync(0xffffffffu, cellkey, 1);
-            if (!__all_sync(0xffffffffu, lane == 0 || prevkey <= cellkey)) {
-                unsigned key = (cellkey << 5) | (unsigned)lane;
-#pragma unroll
-                for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-                    for (int j = k >> 1; j > 0; j >>= 1) {
-                        const unsigned other = __shfl_xor_sync(0xffffffffu, key, j);
-                        const bool up = ((lane & k) == 0), lower = ((lane & j) == 0);
-                        const unsigned mn = min(key, other), mx = max(key, other);
-                        key = (up == lower) ? mn : mx;
-                    }
-                }
-                const int src = key & 31;
-                row = __shfl_sync(0xffffffffu, row, src);
-                b = __shfl_sync(0xffffffffu, b, src);
-                wa.x = __shfl_sync(0xffffffffu, wa.x, src); wa.y = __shfl_sync(0xffffffffu, wa.y, src);
-                wa.z = __shfl_sync(0xffffffffu, wa.z, src); wa.w = __shfl_sync(0xffffffffu, wa.w, src);
-                wb.x = __shfl_sync(0xffffffffu, wb.x, src); wb.y = __shfl_sync(0xffffffffu, wb.y, src);
-                wb.z = __shfl_sync(0xffffffffu, wb.z, src); wb.w = __shfl_sync(0xffffffffu, wb.w, src);
-            }
-            const bool valid = row >= 0;
-            const unsigned present_lo = __reduce_or_sync(0xffffffffu, (valid && b < 32) ? 1u << b : 0u);
-            const unsigned present_hi = G::NB > 32 ? __reduce_or_sync(0xffffffffu, (valid && b >= 32) ? 1u << (b - 32) : 0u) : 0u;
-            const unsigned active = __ballot_sync(0xffffffffu, valid);
-            const int cnt = __popc(active);
-            __syncwarp();  // previous chunk fully consumed
-            // pair at compacted position pos: offset -> entry pos-4 (.x), base cell -> entry pos-1 (.y); the first four
-            // offsets and the first base cell go to `head`
-            auto put_meta = [&](int pos, int off, int bb) {
-                if (pos >= lean::kGatherSlots) metai[2 * (pos - lean::kGatherSlots)] = off; else head[pos] = off;
-                if (pos >= 1) metai[2 * (pos - 1) + 1] = bb; else head[4] = bb;
-            };
-            if (valid) {
-                const int pos = __popc(active & lt_mask);
-                put_meta(pos, row * stride_b, b);
-                *reinterpret_cast<float4*>(wgt + pos * 8) = wa;
-                *reinterpret_cast<float4*>(wgt + pos * 8 + 4) = wb;
-            }
-            if (lane < 8) put_meta(cnt + lane, -1, G::NB);  // eight null pairs: no gather, cell NB = end of chunk
-            __syncwarp();
-            // ---- raw records of this point's next chunk: in flight during the walk ----
-            if (!last) cur = pair_record(p, c0 + 32 + lane, c0 + 32 + lane < re, ox, oy, oz);
-            // ---- walk the chunk: merge over the base cells ----
-            if (cnt > 0) {
-                lean::Walk wk;
-                {
-                    // gathers of pairs 0..3 into the ring slots following the current one (every earlier gather of this
-                    // warp has been consumed: null pairs never start one)
-                    const int4 h = *reinterpret_cast<const int4*>(head);
-                    uint32_t s = sa;
-                    if ((h.x | gate) >= 0) lean::cp_async4(s, fbase + (unsigned)h.x);
-                    lean::cp_commit(); s = lean::ring_next(s);
-                    if ((h.y | gate) >= 0) lean::cp_async4(s, fbase + (unsigned)h.y);
-                    lean::cp_commit(); s = lean::ring_next(s);
-                    if ((h.z | gate) >= 0) lean::cp_async4(s, fbase + (unsigned)h.z);
-                    lean::cp_commit(); s = lean::ring_next(s);
-                    if ((h.w | gate) >= 0) lean::cp_async4(s, fbase + (unsigned)h.w);
-                    lean::cp_commit();
-                    lean::cp_wait<lean::kGatherSlots - 1>();  // pair 0 has landed
-                    wk.sa = sa;
-                    wk.sa_next = lean::ring_next(sa);
-                    wk.f = lean::lds_f32(sa);
-                    wk.mm = meta[0];
-                    wk.m2 = meta + 1;
-                    wk.w = wgt;
-                    wk.wa = *reinterpret_cast<const float4*>(wgt);
-                    wk.wb = *reinterpret_cast<const float4*>(wgt + 4);
-                }
-                const float scale = p.feat_scale;
-                lean::sweep<KZ, KY, KX, RELU, FX>(wk, present_lo, present_hi, acc, fbase, gate, scale, fc);
-                sa = wk.sa;
-            }
-            if (last) break;
-        }
+        float norm_acc = lean::point_patch<lean::FullPatch<KZ, KY, KX>, RELU, FX>(p, cx, cur, rs, re, ox, oy, oz, fc, acc);
         // ---- patch row -> shared memory (lane = channel: conflict free), Dense columns, padding ----
         if (!o_ok) {
             for (int k = lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;

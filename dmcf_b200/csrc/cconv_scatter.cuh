@@ -8,6 +8,7 @@ namespace dmcf {
 
 template <int KZ, int KY, int KX>
 struct FilterGrid {
+    static constexpr int KZ_ = KZ, KY_ = KY, KX_ = KX;
     static constexpr int K = KZ * KY * KX;
     static constexpr int NBX = KX > 1 ? KX - 1 : 1, NBY = KY > 1 ? KY - 1 : 1, NBZ = KZ > 1 ? KZ - 1 : 1;
     static constexpr int NB = NBX * NBY * NBZ;  // distinct "base" cells of the 2x2x2 corner block

@@ -456,7 +456,8 @@ class PBFNet(BaseModel):
             relu_input=relu, feat_scale=scale, ascc=ascc,
             skip_self=skip, bias=b,
             dense_inp=x if dense is not None else None, dense_cin=x.shape[1] if dense is not None else 0,
-            residual=residual, out=out, accumulate=accumulate, kernel_size=conv.kernel_size, pair_records=recs)
+            residual=residual, out=out, accumulate=accumulate, kernel_size=conv.kernel_size, pair_records=recs,
+            antisymmetric_filter=bool(getattr(conv, "symmetric", False)) and not getattr(conv, "circular", False))
 
     # -- postprocess: models/pbf_model.py:440-489 -----------------------------------------------------------------
     def postprocess(self, prev, data, training=False, **kwargs):

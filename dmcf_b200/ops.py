@@ -173,7 +173,8 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
                     coordinate_mapping="ball_to_cube_radial", normalize=False, interpolation="linear",
                     max_temp_mem_MB=64, *, window=None, window_fac=1.0, relu_input=False, feat_scale=1.0,
                     ascc=False, skip_self=False, nbr_range=None, bias=None, dense_inp=None, dense_cin=0,
-                    residual=None, out=None, accumulate=False, kernel_size=None, pair_records=None):
+                    residual=None, out=None, accumulate=False, kernel_size=None, pair_records=None,
+                    antisymmetric_filter=False):
     """``ml3d.ops.continuous_conv`` (kwargs as assembled at utils/convolutions.py:414-429) plus keyword-only fused
     extras (see include/dmcf_b200.h).  ``filters`` is [kz,ky,kx,Cin,Cout] or, with a fused Dense, the flattened
     [(kz*ky*kx*Cin + dense_cin), Cout] matrix together with ``kernel_size``."""
@@ -235,6 +236,7 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     d.nbr_lo, d.nbr_hi = (0, 0) if nbr_range is None else (int(nbr_range[0]), int(nbr_range[1]))
     d.dense_cin = int(dense_cin)
     d.accumulate = int(bool(accumulate))
+    d.filter_antisym = int(bool(antisymmetric_filter))  # promise: filters[rev(cell)] == -filters[cell] exactly
     dense_stride = 0
     if dense_cin:
         dense_inp, dense_stride = _rows(dense_inp, "dense_inp")
@@ -258,7 +260,7 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
         neighbors_index = torch.zeros(1, dtype=torch.int32, device=out_positions.device)
     rec = None
     if PROFILE is not None:
-        rec = dict(kernel=conv_kernel_name((kz, ky, kx), cin, cout, interpolation, int(dense_cin)),
+        rec = dict(kernel=conv_kernel_name((kz, ky, kx), cin, cout, interpolation, int(dense_cin), bool(antisymmetric_filter)),
                    kernel_size=(kz, ky, kx), cin=cin, cout=cout, ascc=bool(ascc), n_inp=n_inp, n_out=n_out,
                    rows=kz * ky * kx * cin + int(dense_cin), pairs=int(neighbors_index.shape[0]),
                    residual=residual is not None, start=torch.cuda.Event(enable_timing=True),
@@ -414,10 +416,13 @@ def set_kernel_options(options):
     return int(_lib.load().dmcf_set_kernel_options(int(options)))
 
 
-def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0):
+def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0, antisymmetric_filter=False):
     """Which kernel dmcf_cconv_forward dispatches to with the default options (mirrors csrc/cconv.cu)."""
     kz, ky, kx = (int(k) for k in kernel_size)
     kc = kz * ky * kx * cin + dense_cin
+    if (antisymmetric_filter and interpolation == "linear" and cin <= 32
+            and ((kz, ky, kx), cout) == ((1, 8, 8), 2)):
+        return "k_cconv_apatch"
     if cout <= 4 and (kc * cout + 4 + 16 * 32 * 12) * 4 <= 200 * 1024:
         return "k_cconv_direct"
     if interpolation == "linear" and cin <= 32 and cout % 4 == 0 and (kz, ky, kx) in ((4, 4, 4), (1, 8, 8), (1, 8, 1)):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DMCF_B200_VERSION 100
+#define DMCF_B200_VERSION 101
 
 enum dmcf_status {
     DMCF_OK = 0,
@@ -123,6 +123,9 @@ typedef struct dmcf_conv_desc {
                                nbr_hi <= nbr_lo means "all" */
     int32_t dense_cin;      /* 0 = no fused Dense */
     int32_t accumulate;     /* out += result instead of out = result */
+    int32_t filter_antisym; /* the caller guarantees filters[kz-1-z][ky-1-y][kx-1-x] == -filters[z][y][x] (bit exact), as
+                               the antisymmetric layer builds its effective kernel (utils/convolutions.py:410-412):
+                               allows the folded half-patch kernel k_cconv_apatch.  0 is always safe */
 } dmcf_conv_desc;
 
 int dmcf_cconv_forward(const dmcf_conv_desc* desc, const float* filters,
@@ -150,8 +153,9 @@ int dmcf_cconv_prepare(const dmcf_conv_desc* desc, const float* out_positions, i
 
 /* Kernel selection bit mask (default 3): bit 0 = register-patch kernels for compile-time filter grids (k_cconv_lean;
  * k_cconv_wide where the lean kernel is not eligible), bit 1 = resident-filter direct kernel for cout <= 4
- * (k_cconv_direct), bit 2 = run 4x4x4 layers of the legacy k_cconv_wide as two z-half launches, bit 3 = use the legacy
- * k_cconv_wide instead of k_cconv_lean (kept for A/B measurements); 0 forces the generic kernel.  Returns the previous
+ * (k_cconv_direct) and the folded half-patch kernel for antisymmetric filters (k_cconv_apatch), bit 2 = run 4x4x4 layers of
+ * the legacy k_cconv_wide as two z-half launches, bit 3 = use the legacy k_cconv_wide instead of k_cconv_lean, bit 4 = do
+ * not use k_cconv_apatch (bits 3 and 4 are kept for A/B measurements); 0 forces the generic kernel.  Returns the previous
  * mask.  Results agree to float32 rounding. */
 int dmcf_set_kernel_options(int options);
 

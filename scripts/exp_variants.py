@@ -24,7 +24,6 @@ def run(opt, label):
         k = (r['kernel_size'], r['cin'], r['cout'])
         g.setdefault(k, []).append(r['start'].elapsed_time(r['end']))
     print(label, 'ms/step %.2f' % (e0.elapsed_time(e1)/3), {str(k): round(float(np.mean(v)),2) for k,v in g.items()})
-run(3, 'lean')
-run(11, 'legacy wide')
+run(3, 'lean + apatch')
+run(27, 'legacy wide + direct')
 run(3 | 512, 'lean, phase 1 only')
-run(11 | 512, 'legacy wide, phase 1 only')

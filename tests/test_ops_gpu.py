@@ -141,7 +141,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.fixture(params=[3, 11, 15, 0], ids=["fast-kernels", "legacy-wide", "legacy-wide-zsplit", "generic-kernel"])
+@pytest.fixture(params=[3, 27, 31, 0], ids=["fast-kernels", "legacy-wide-direct", "legacy-wide-zsplit-direct", "generic-kernel"])
 def kernel_options(request):
     from dmcf_b200 import ops
     prev = ops.set_kernel_options(request.param)
@@ -268,6 +268,50 @@ def test_ascc_fused_matches_reference_form_and_conserves(cuda, kernel_options):
     feat_close(got, ref)
     total = np.abs(got).sum(axis=0)
     assert np.all(np.abs(got.sum(axis=0)) <= 1e-5 * total + 1e-5), (got.sum(axis=0), total)
+    # the same layer with the antisymmetry promise (folded half-patch kernel k_cconv_apatch), also through pair records
+    recs = ops.prepare_pair_records((6, 6, 6), t(pts), float(extent), None, t(pts), None, nns.neighbors_index, None,
+                                    nns.neighbors_row_splits, align_corners=True,
+                                    coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear", window="peak")
+    for rec in (None, recs):
+        got2 = ops.continuous_conv(t(full), t(pts), float(extent), None, t(pts), t(feats), None, nns.neighbors_index, None,
+                                   nns.neighbors_row_splits, align_corners=True,
+                                   coordinate_mapping="ball_to_cube_volume_preserving", normalize=False,
+                                   interpolation="linear", window="peak", relu_input=True, ascc=True,
+                                   antisymmetric_filter=True, pair_records=rec).cpu().numpy().astype(np.float64)
+        feat_close(got2, ref)
+        feat_close(got2, got, 0.5)
+        assert np.all(np.abs(got2.sum(axis=0)) <= 1e-5 * total + 1e-5), (got2.sum(axis=0), total)
+
+
+def test_ascc_2d_half_patch(cuda, kernel_options):
+    """2-D antisymmetric layer (WBC-SPH: stored [1,4,8,32,2], effective 1x8x8, sym_axis 1), long rows, fused Dense, bias,
+    residual: folded half-patch kernel vs the oracle's two-pass form."""
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(29)
+    n, cin, cout = 1200, 32, 2
+    pts = rng.random((n, 3)).astype(np.float32) * 0.5
+    pts[:, 2] = 0
+    feats = rng.standard_normal((n, cin)).astype(np.float32)
+    half = rng.uniform(-0.5, 0.5, (1, 4, 8, cin, cout)).astype(np.float32)
+    extent = np.float32(0.12)
+    ref = o64.cconv_layer(np.maximum(feats, 0), pts, pts, extent, half, None, align_corners=True,
+                          coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear", normalize=False,
+                          ignore_query_points=True, window_name="peak", symmetric=True, sym_axis=1)
+    dk = rng.uniform(-0.3, 0.3, (cin, cout)).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32)
+    resid = rng.standard_normal((n, cout)).astype(np.float32)
+    ref = ref + np.maximum(feats, 0).astype(np.float64) @ dk + bias + resid
+    full = o64.symmetric_kernel(half, 1).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    nns = ops.fixed_radius_search(t(pts), t(pts), float(np.float32(0.5) * extent), ignore_query_point=True)
+    assert int(np.diff(nns.neighbors_row_splits.cpu().numpy()).max()) > 32  # several chunks per row
+    w_ext = torch.cat([t(full).reshape(-1, cout), t(dk)], dim=0)
+    got = ops.continuous_conv(w_ext, t(pts), float(extent), None, t(pts), t(feats), None, nns.neighbors_index, None,
+                              nns.neighbors_row_splits, align_corners=True,
+                              coordinate_mapping="ball_to_cube_volume_preserving", normalize=False, interpolation="linear",
+                              window="peak", relu_input=True, ascc=True, antisymmetric_filter=True, bias=t(bias),
+                              dense_inp=t(feats), dense_cin=cin, residual=t(resid), kernel_size=(1, 8, 8)).cpu().numpy()
+    feat_close(got, ref)
 
 
 def test_dense_and_elementwise(cuda):
