@@ -183,6 +183,11 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner at the first
+    # communicator) are sent to stderr until the result line is written
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -328,7 +333,10 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": breakdown,
             "cpu_baseline": cpu, "finite": ok,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,0 +1,45 @@
+"""Per-step timing of the BASELINE configs 2 and 3 (WBC-SPH 2-D ~10k particles, Liquid3d 3-D ~100k particles) with the
+shipped checkpoints (tests/golden/ckpt_*.npz): ms/step and the time per conv kernel group.
+  python scripts/bench_configs.py [liquid3d|wbc] [steps]"""
+import os, sys
+sys.path.insert(0, '.')
+sys.path.insert(0, 'tests')
+import numpy as np, torch
+from dmcf_b200 import ops, config, scenes
+from dmcf_b200.simulator import Simulator
+import test_models_gpu as T
+which = sys.argv[1] if len(sys.argv) > 1 else 'liquid3d'
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+dev = torch.device('cuda')
+if which == 'liquid3d':
+    cfg, scene, wname = T.liquid3d_cfg(), scenes.lattice_scene((46, 46, 46), dx=0.05, seed=2, open_top=True), 'ckpt_Liquid3d.npz'
+    acc = None
+else:
+    cfg, scene, wname = T.wbc_cfg(), scenes.lattice_scene((100, 100, 1), dx=0.005, seed=3, vel_sigma=0.05), 'ckpt_WBC-SPH.npz'
+    acc = np.tile(np.array([[0.0, -9.81, 0.0]], np.float32), (scene['pos'].shape[0], 1))
+model = config.build_model(cfg)
+model.load_weights(T.load_npz_weights(wname), device=dev)
+sim = Simulator(model, device='cuda')
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+sample = [t(scene['pos']), t(scene['vel']), None if acc is None else t(acc), None, t(scene['box']), t(scene['box_normals'])]
+print(which, 'fluid', scene['pos'].shape[0], 'boundary', scene['box'].shape[0])
+for _ in range(3): sim.step(sample)
+ops.PROFILE = []
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(steps): out = sim.step(sample)
+e1.record(); torch.cuda.synchronize()
+prof, ops.PROFILE = ops.PROFILE, None
+ms = e0.elapsed_time(e1) / steps
+print('ms/step %.2f  particles*steps/s %.3e' % (ms, scene['pos'].shape[0] / ms * 1e3))
+g = {}
+for r in prof:
+    k = (r['kernel'], r['kernel_size'], r['cin'], r['cout'], r['n_inp'], r['n_out'], r['pairs'])
+    g.setdefault(k, []).append(r['start'].elapsed_time(r['end']))
+tot = 0
+for k, v in sorted(g.items(), key=lambda kv: -sum(kv[1])):
+    per = sum(v) / steps
+    tot += per
+    print('%-15s %s %3d->%-3d n_in %7d n_out %7d pairs %9d : %6.3f ms/step (%d launches/step)' % (k[0], k[1], k[2], k[3], k[4], k[5], k[6], per, len(v) // steps))
+print('conv kernels total %.2f ms/step' % tot)
