@@ -194,3 +194,29 @@ def test_canyon_inflow_rollout_growing_particle_set(cuda):
     # the jet moves along +x / -z with the prescribed inflow velocity (10, 0, -6) * dt per step
     d = (sample[0][:1280].mean(0) - in_pos.mean(0)).cpu().numpy()
     assert d[0] > 0.5 and d[2] < -0.3
+
+
+def test_run_sample_rollout_cli_body(cuda):
+    """run_sample.run_rollout (the body of the reference's run_sample.py:140-181) on the canyon crop: per-particle
+    acceleration tensor like the reference, inflow every odd step, results are the position sets per frame."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import run_sample
+    from dmcf_b200 import config
+    from dmcf_b200.simulator import Simulator
+    import test_models_gpu as T
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "canyon_crop.npz"))
+    model = config.build_model(T.liquid3d_cfg())
+    sim = Simulator(model, device="cuda")
+    model.load_weights(T.load_npz_weights("ckpt_Liquid3d.npz"), device=cuda)
+    frame = dict(pos=z["pos"], vel=z["vel"], box=z["box"], box_normals=z["box_normals"])
+    with torch.no_grad():
+        res = run_sample.run_rollout(sim, model, frame, timesteps=6, inflow=4)
+    assert [r.shape[0] for r in res] == [1280, 1280, 1280, 2560, 2560, 3840]
+    assert all(torch.isfinite(r).all() for r in res)
+    # first step equals Simulator.step with the same inputs (acc tensor == constant gravity vector)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(cuda)
+    ref = sim.step([t(z["pos"]), t(z["vel"] + np.array([10.0, 0, -6.0], np.float32)), None, None, t(z["box"]), t(z["box_normals"])])
+    assert torch.allclose(res[1], ref[0], rtol=0, atol=2e-6)
