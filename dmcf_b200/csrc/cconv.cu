@@ -254,18 +254,32 @@ __global__ void __launch_bounds__(256) k_cconv_prepare(const ConvParams p, float
                 cellkey = (unsigned)((bz * nby + by) * nbx + bx);
             }
             unsigned key = (cellkey << 5) | (unsigned)lane;
+            int src;
+            if (re - c0 <= 8) {
+                // short chunk (the tail of a 33..40-pair row is the common case): rank of this lane's key among the
+                // first eight lanes instead of the full 32-lane bitonic network
+                int rank = 0;
 #pragma unroll
-            for (int k = 2; k <= 32; k <<= 1) {
+                for (int j = 0; j < 8; ++j) rank += __shfl_sync(0xffffffffu, key, j) < key ? 1 : 0;
+                // lane `rank` must pull from this lane: invert the permutation (lanes >= 8 hold no pairs and stay put)
+                src = lane;
 #pragma unroll
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    const unsigned other = __shfl_xor_sync(0xffffffffu, key, j);
-                    const bool up = ((lane & k) == 0);
-                    const bool lower = ((lane & j) == 0);
-                    const unsigned mn = min(key, other), mx = max(key, other);
-                    key = (up == lower) ? mn : mx;
+                for (int j = 0; j < 8; ++j)
+                    if (__shfl_sync(0xffffffffu, rank, j) == lane && lane < 8) src = j;
+            } else {
+#pragma unroll
+                for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        const unsigned other = __shfl_xor_sync(0xffffffffu, key, j);
+                        const bool up = ((lane & k) == 0);
+                        const bool lower = ((lane & j) == 0);
+                        const unsigned mn = min(key, other), mx = max(key, other);
+                        key = (up == lower) ? mn : mx;
+                    }
                 }
+                src = key & 31;
             }
-            const int src = key & 31;
             r.row = __shfl_sync(0xffffffffu, r.row, src);
             r.g.i0 = __shfl_sync(0xffffffffu, r.g.i0, src);
             r.g.i1 = __shfl_sync(0xffffffffu, r.g.i1, src);

@@ -249,11 +249,28 @@ __global__ void __launch_bounds__(256) k_frs(GridView g, const float* __restrict
         int count = 0;
         int64_t base = 0;
         if (FILL) base = row_splits[q];
-        for (int z = z0; z <= z1; ++z) {
-            for (int y = y0; y <= y1; ++y) {
-                const int64_t crow = ((int64_t)z * g.ny + y) * g.nx;
-                const int s = __ldg(g.cell_start + crow + x0);
-                const int e = __ldg(g.cell_start + crow + x1 + 1);
+        // candidate runs of the (z,y) cell rows: lane r fetches the bounds of row r (up to 32 rows: 3x3 when the cell edge
+        // is the radius), so the loads are in flight together instead of one dependent pair per row
+        const int ny_rows = y1 - y0 + 1, n_rows = (z1 - z0 + 1) * ny_rows;
+        int rs_lane = 0, re_lane = 0;
+        if (lane < n_rows && n_rows <= 32) {
+            const int z = z0 + lane / ny_rows, y = y0 + lane % ny_rows;
+            const int64_t crow = ((int64_t)z * g.ny + y) * g.nx;
+            rs_lane = __ldg(g.cell_start + crow + x0);
+            re_lane = __ldg(g.cell_start + crow + x1 + 1);
+        }
+        for (int r = 0; r < n_rows; ++r) {
+            {
+                int s, e;
+                if (n_rows <= 32) {
+                    s = __shfl_sync(0xffffffffu, rs_lane, r);
+                    e = __shfl_sync(0xffffffffu, re_lane, r);
+                } else {
+                    const int z = z0 + r / ny_rows, y = y0 + r % ny_rows;
+                    const int64_t crow = ((int64_t)z * g.ny + y) * g.nx;
+                    s = __ldg(g.cell_start + crow + x0);
+                    e = __ldg(g.cell_start + crow + x1 + 1);
+                }
                 for (int i0 = s; i0 < e; i0 += 32) {
                     const int i = i0 + lane;
                     bool hit = false;
