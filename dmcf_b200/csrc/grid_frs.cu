@@ -167,28 +167,59 @@ __global__ void __launch_bounds__(256) k_cell_scatter(int n, const int32_t* __re
     sorted_index[cell_start[c] + slot] = i;
 }
 
-// one thread per cell: order the ids of the cell ascending so that the layout (and every neighbour row
-// built from it) is deterministic and independent of atomic arrival order.
-__global__ void __launch_bounds__(256) k_cell_sort(int64_t n_cells, const int32_t* __restrict__ cell_start,
-                                                     int32_t* __restrict__ sorted_index) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per cell: order the ids of the cell ascending so that the layout (and every neighbour row built from it) is
+// deterministic and independent of atomic arrival order.  Up to 32 ids: bitonic network on registers; up to 1024 (the
+// coarse cells of the multi-scale nets hold ~500 points): bitonic sort in the warp's shared-memory buffer; beyond that
+// (clamped border cells of degenerate inputs) one lane runs a heap sort in place.
+static constexpr int kCellSortWarps = 8, kCellSortMax = 1024;
+
+__global__ void __launch_bounds__(kCellSortWarps * 32) k_cell_sort(int64_t n_cells, const int32_t* __restrict__ cell_start,
+                                                                    int32_t* __restrict__ sorted_index) {
+    __shared__ int32_t buf[kCellSortWarps][kCellSortMax];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * kCellSortWarps + warp;
     if (c >= n_cells) return;
     const int s = cell_start[c], e = cell_start[c + 1];
     const int m = e - s;
     if (m < 2) return;
     int32_t* a = sorted_index + s;
-    if (m <= 48) {
-        for (int i = 1; i < m; ++i) {
-            const int32_t v = a[i];
-            int j = i - 1;
-            while (j >= 0 && a[j] > v) {
-                a[j + 1] = a[j];
-                --j;
+    if (m <= 32) {
+        int32_t v = lane < m ? a[lane] : 0x7fffffff;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const int32_t other = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool up = ((lane & k) == 0), lower = ((lane & j) == 0);
+                v = (up == lower) ? min(v, other) : max(v, other);
             }
-            a[j + 1] = v;
         }
+        if (lane < m) a[lane] = v;
         return;
     }
+    if (m <= kCellSortMax) {
+        int32_t* b = buf[warp];
+        int P = 64;
+        while (P < m) P <<= 1;
+        for (int i = lane; i < P; i += 32) b[i] = i < m ? a[i] : 0x7fffffff;
+        __syncwarp();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < P / 2; t += 32) {
+                    // t-th compare-exchange of this step: partner indices i < l = i ^ j
+                    const int i = 2 * t - (t & (j - 1));
+                    const int l = i + j;
+                    const int32_t x = b[i], y = b[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { b[i] = y; b[l] = x; }
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < m; i += 32) a[i] = b[i];
+        return;
+    }
+    if (lane != 0) return;
     // heap sort for crowded cells (clamped border cells, degenerate inputs)
     for (int start = m / 2 - 1; start >= 0; --start) {
         int root = start;
@@ -445,7 +476,7 @@ extern "C" int dmcf_grid_build(const float* points, dmcf_grid* grid, void* works
         if (rc) return rc;
         k_cell_scatter<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, cell_of, grid->cell_start, cell_count, grid->sorted_index);
         DMCF_LAUNCH_CHECK("k_cell_scatter");
-        k_cell_sort<<<(unsigned)ceil_div(n_cells, 256), 256, 0, st>>>(n_cells, grid->cell_start, grid->sorted_index);
+        k_cell_sort<<<(unsigned)ceil_div(n_cells, kCellSortWarps), kCellSortWarps * 32, 0, st>>>(n_cells, grid->cell_start, grid->sorted_index);
         DMCF_LAUNCH_CHECK("k_cell_sort");
         k_cell_gather_pos<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, points, grid->sorted_index, (float4*)grid->sorted_pos);
         DMCF_LAUNCH_CHECK("k_cell_gather_pos");
