@@ -1,4 +1,6 @@
-// continuous_conv forward for the 2-D antisymmetric output layer of SymNet (utils/convolutions.py:242-254, 410-458;
+// continuous_conv forward for layers with <= 4 output channels whose (folded) patch fits the registers of a warp.
+//
+// First use -- the 2-D antisymmetric output layer of SymNet (utils/convolutions.py:242-254, 410-458;
 // models/sym_net.py:39-67; configs/WBC-SPH.yml): 2 output channels, a 1x8x8 filter that the layer builds by mirroring and
 // negating its stored half, F[rev(cell)] = -F[cell].
 //
@@ -16,16 +18,18 @@
 // The 3-D layer (6x6x6, 125 base cells, 108 folded cells) was measured too and is NOT routed here: one walk body per base
 // cell is 68 KB of code and thrashes the instruction cache (26 ms against 5.0 ms for k_cconv_direct); a single body with a
 // per-pair 125-way switch is 8.0 ms (the compare tree nvcc builds costs several dependent branches per pair).
+//
+// Second use -- any 4x4x4 / 1x8x8 / 1x8x1 layer with <= 4 output channels (lean::FullPatch: the whole patch in registers,
+// the same in-warp phase 2 against the whole resident filter): the 4-channel coarse scales of the multi-scale nets.
 #include "cconv_walk.cuh"
 
 namespace dmcf {
 
-template <int KZ, int KY, int KX, int COUT, int NW, bool RELU>
+template <class S, int COUT, int NW, bool RELU>
 __global__ void __launch_bounds__(NW * 32, 1) k_cconv_apatch(const ConvParams p) {
-    using S = lean::AntiPatch<KZ, KY, KX>;
     constexpr int NACC = S::NACC;
     extern __shared__ __align__(1024) float smem[];
-    // [NW gather rings of 512 B][NW record blocks][half filter [K/2][cin][COUT]][Dense kernel [dense_cin][COUT]]
+    // [NW gather rings of 512 B][NW record blocks][(half) filter [NACC][cin][COUT]][Dense kernel [dense_cin][COUT]]
     float* rings = smem;
     float* recs = rings + (size_t)NW * lean::kGatherSlots * 32;
     float* fh = recs + (size_t)NW * lean::kRecWords;
@@ -129,15 +133,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_apatch(const ConvParams p)
     lean::cp_wait<0>();
 }
 
-template <int KZ, int KY, int KX, int COUT>
+template <class S, int COUT>
 static int launch_apatch(const ConvParams& p, cudaStream_t st, bool* handled) {
-    constexpr int NW = 16;
-    constexpr int NACC = KZ * KY * KX / 2;
+    constexpr int NW = S::NACC > 32 ? 12 : 16;
+    constexpr int NACC = S::NACC;
     const size_t words = (size_t)NW * lean::kScratchWords + (((size_t)NACC * p.cin * COUT + 3) & ~(size_t)3) + (size_t)p.dense_cin * COUT;
     *handled = false;
     if (words * sizeof(float) > 200 * 1024) return DMCF_OK;
     static bool attr_set = false;
-    void (*kerns[2])(const ConvParams) = {k_cconv_apatch<KZ, KY, KX, COUT, NW, false>, k_cconv_apatch<KZ, KY, KX, COUT, NW, true>};
+    void (*kerns[2])(const ConvParams) = {k_cconv_apatch<S, COUT, NW, false>, k_cconv_apatch<S, COUT, NW, true>};
     if (!attr_set) {
         for (int i = 0; i < 2; ++i) {
             cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -153,12 +157,33 @@ static int launch_apatch(const ConvParams& p, cudaStream_t st, bool* handled) {
     return DMCF_OK;
 }
 
-// Tries the antisymmetric register-patch kernel; *handled = false means "not eligible".
+template <int KZ, int KY, int KX>
+static int launch_rpatch_grid(const ConvParams& p, cudaStream_t st, bool* handled) {
+    using S = lean::FullPatch<KZ, KY, KX>;
+    switch (p.cout) {
+        case 1: return launch_apatch<S, 1>(p, st, handled);
+        case 2: return launch_apatch<S, 2>(p, st, handled);
+        case 3: return launch_apatch<S, 3>(p, st, handled);
+        case 4: return launch_apatch<S, 4>(p, st, handled);
+        default: return DMCF_OK;
+    }
+}
+
+// Tries the register-patch kernels for layers with <= 4 output channels; *handled = false means "not eligible".
+//   antisymmetric 1x8x8 filter (descriptor promise) -> folded half patch;
+//   4x4x4 / 1x8x8 / 1x8x1 filters                   -> full patch in registers (the multi-scale nets' 4-channel scales:
+//   their fine -> coarse convs see ~1600 pairs per out point, where the walk's 28 instructions per pair beat
+//   k_cconv_direct's ~110: 4.6 -> 2.0 ms for the 24->4 conv of a Liquid3d step).
 int launch_cconv_apatch(const ConvParams& p, cudaStream_t st, bool* handled) {
     *handled = false;
-    if (!p.filter_antisym || p.normalize || p.gp.interp != DMCF_INTERP_LINEAR || p.cin > 32) return DMCF_OK;
+    if (p.normalize || p.gp.interp != DMCF_INTERP_LINEAR || p.cin > 32 || p.cout > 4) return DMCF_OK;
     if ((p.n_inp > 0 ? p.n_inp : 1) * p.inp_stride * 4 >= ((int64_t)1 << 31)) return DMCF_OK;  // 32-bit gather offsets
-    if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 8 && p.cout == 2) return launch_apatch<1, 8, 8, 2>(p, st, handled);
+    const bool g444 = p.gp.kz == 4 && p.gp.ky == 4 && p.gp.kx == 4, g188 = p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 8;
+    const bool g181 = p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 1;
+    if (p.filter_antisym && g188 && p.cout == 2) return launch_apatch<lean::AntiPatch<1, 8, 8>, 2>(p, st, handled);
+    if (g444) return launch_rpatch_grid<4, 4, 4>(p, st, handled);
+    if (g188) return launch_rpatch_grid<1, 8, 8>(p, st, handled);
+    if (g181) return launch_rpatch_grid<1, 8, 1>(p, st, handled);
     return DMCF_OK;
 }
 

@@ -423,6 +423,8 @@ def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0, antisym
     if (antisymmetric_filter and interpolation == "linear" and cin <= 32
             and ((kz, ky, kx), cout) == ((1, 8, 8), 2)):
         return "k_cconv_apatch"
+    if (cout <= 4 and interpolation == "linear" and cin <= 32 and (kz, ky, kx) in ((4, 4, 4), (1, 8, 8), (1, 8, 1))):
+        return "k_cconv_apatch"
     if cout <= 4 and (kc * cout + 4 + 16 * 32 * 12) * 4 <= 200 * 1024:
         return "k_cconv_direct"
     if interpolation == "linear" and cin <= 32 and cout % 4 == 0 and (kz, ky, kx) in ((4, 4, 4), (1, 8, 8), (1, 8, 1)):
