@@ -19,7 +19,7 @@ import torch
 
 from . import ops
 from .convolutions import ContinuousConv, PointSampling, _init
-from .losses import get_dilated_pos, get_window_func
+from .losses import compute_density, get_dilated_pos, get_window_func
 
 __all__ = ["BaseModel", "PBFNet", "HRNet", "SymNet", "CConv", "Dense", "align_vector"]
 
@@ -126,11 +126,16 @@ class PBFNet(BaseModel):
                  rest_dens=3.5, stiffness=20.0, voxel_size=None, centralize=False, out_scale=[0.01, 0.01, 0.01],
                  sample_pad=0, sample_hyst=0.1, part_scale=1.0, fused=True, **kwargs):
         super().__init__(name=name, **kwargs)
-        for flag, val in (("dens_feats", dens_feats), ("pres_feats", pres_feats), ("equivar", equivar),
-                          ("use_pre_adv", use_pre_adv), ("dens_norm", dens_norm), ("use_feats", use_feats)):
-            if val:
-                raise NotImplementedError(f"{flag}=True is disabled in every shipped config and not implemented "
-                                          "(SURVEY 8 a16)")
+        if equivar:
+            raise NotImplementedError("equivar=True is disabled in every shipped config and not implemented (SURVEY 8 a16)")
+        # Optional input branches (off in every shipped main config): density / pressure input features
+        # (models/pbf_model.py:351-367), extra per-particle features, the pre-advection conv (:154-175, 388-399) and the
+        # density pyramid for dens_norm (:177-181, 421-435).  They run on the layer-by-layer path (the reference's own
+        # sequence of layer calls on the CUDA layers), not on the fused step.
+        self.dens_feats, self.pres_feats, self.dens_norm = bool(dens_feats), bool(pres_feats), bool(dens_norm)
+        self.use_pre_adv, self.use_feats = bool(use_pre_adv), bool(use_feats)
+        if self.dens_feats or self.pres_feats or self.dens_norm or self.use_pre_adv or self.use_feats:
+            fused = False
         self.kernel_size = list(kernel_size)
         self.channel = channels
         self.strides = list(strides)
@@ -163,6 +168,14 @@ class PBFNet(BaseModel):
         self.fluid_dense = Dense(channels, name="fluid_dense")
         self.obs_convs = self.get_cconv(name="obs_conv", filters=channels, window_func=self.window, circular=circular)
         self.obs_dense = Dense(channels, name="obs_dense")
+        if self.use_pre_adv:  # models/pbf_model.py:154-175 (adv_conv1 / adv_dense1 are constructed but never called)
+            self.adv_convs = torch.nn.ModuleList([
+                self.get_cconv(name="adv_conv0", filters=channels, window_func=self.window, circular=circular),
+                self.get_cconv(name="adv_conv1", filters=channels, window_func=self.window, circular=circular)])
+            self.adv_dense = torch.nn.ModuleList([Dense(channels, name="adv_dense0"), Dense(channels, name="adv_dense1")])
+            self.adv_convs[0]._aliases, self.adv_convs[1]._aliases = ["adv_convs/0"], ["adv_convs/1"]
+        if self.dens_norm:  # :177-181
+            self.sampling = PointSampling(name="sampling", window_function=get_window_func(self.window_dens), normalize=True)
         self.setup()
         self._convs_ml = torch.nn.ModuleList([c for _, c in self._all_convs])
 
@@ -294,13 +307,28 @@ class PBFNet(BaseModel):
             if acc is None:
                 raise ValueError("use_acc=True needs the per-particle acceleration (data[2])")
             fluid_feats.append(acc)
+        if self.use_feats:
+            if feats is None:
+                raise ValueError("use_feats=True needs the per-particle features (data[3])")
+            fluid_feats.append(feats)
         box_feats = [torch.ones_like(box[:, :1])]
         if self.use_box_feats:
             box_feats.append(bfeats)
-        fluid_feats = torch.cat(fluid_feats, dim=-1)
-        box_feats = torch.cat(box_feats, dim=-1)
         all_pos = torch.cat([pos, box], dim=0)
         self.all_pos = all_pos
+        dens0 = None
+        if self.dens_feats or self.dens_norm or self.pres_feats:  # models/pbf_model.py:351-367
+            win_d = get_window_func(self.window_dens)
+            dens0 = compute_density(all_pos, all_pos, float(self.dens_radius[0]), win=win_d)
+            if self.dens_feats:
+                fluid_feats.append(dens0[:pos.shape[0]].unsqueeze(-1))
+                box_feats.append(dens0[pos.shape[0]:].unsqueeze(-1))
+            if self.pres_feats:  # utils/tools/losses.py:367-377
+                pres = torch.relu(self.stiffness * ((dens0 / self.rest_dens) ** 7 - 1))
+                fluid_feats.append(pres[:pos.shape[0]].unsqueeze(-1))
+                box_feats.append(pres[pos.shape[0]:].unsqueeze(-1))
+        fluid_feats = torch.cat(fluid_feats, dim=-1)
+        box_feats = torch.cat(box_feats, dim=-1)
         self.inp_feats, self.inp_bfeats = fluid_feats, box_feats
         self._n_fluid = n_f
         self._step = _StepCache()
@@ -311,7 +339,16 @@ class PBFNet(BaseModel):
             ans_dense = self.fluid_dense(fluid_feats)
             ans_obs = self.obs_convs(box_feats * self.part_scale, box, all_pos, ext0, None)  # :382
             ans_dense_obs = self.obs_dense(box_feats)
-            feats_out = torch.cat([ans_conv, ans_obs, torch.cat([ans_dense, ans_dense_obs], dim=0)], dim=-1)  # :411
+            ans_dense = torch.cat([ans_dense, ans_dense_obs], dim=0)
+            if self.use_pre_adv:  # :388-399: a third input conv from the positions BEFORE the advection step
+                pre_adv_feats = torch.ones_like(_pos[:, :1])
+                if self.use_vel:
+                    pre_adv_feats = torch.cat([pre_adv_feats, _vel], dim=-1)
+                ans_adv = self.adv_convs[0](pre_adv_feats * self.part_scale, _pos, all_pos, ext0, None)
+                ans_dens_adv = torch.cat([self.adv_dense[0](pre_adv_feats), ans_dense_obs], dim=0)
+                feats_out = torch.cat([ans_conv, ans_obs, ans_adv, ans_dense, ans_dens_adv], dim=-1)
+            else:
+                feats_out = torch.cat([ans_conv, ans_obs, ans_dense], dim=-1)  # :411
         else:
             cf, cb = fluid_feats.shape[1], box_feats.shape[1]
             self._ensure_built_inputs(cf, cb, pos.device)
@@ -344,7 +381,13 @@ class PBFNet(BaseModel):
             dilated_pos, _, idx = get_dilated_pos(src, self.strides, voxel_size=self.voxel_size,
                                                   centralize=self.centralize, pad=self.sample_pad, hyst=self.sample_hyst)
         self.dilated_pos = dilated_pos
-        return [dilated_pos, feats_out, idx, None]
+        dens = None
+        if self.dens_norm:  # :421-435: density pyramid, resampled scale to scale (the radius is passed as the extent)
+            dens = [(dens0 if self.use_bnds else dens0[:n_f]).unsqueeze(-1)]
+            for sc in range(1, len(self.dens_radius)):
+                d = self.sampling(dens[-1], dilated_pos[sc - 1], dilated_pos[sc], float(self.dens_radius[sc]), None)
+                dens.append(torch.clamp(d, min=1e-2))
+        return [dilated_pos, feats_out, idx, dens]
 
     def _slab_dilated_pos(self, slab, all_own, all_in):
         """Multi-scale lattices under slab decomposition: every rank builds the lattice from its owned + ghost particles
@@ -494,6 +537,8 @@ class PBFNet(BaseModel):
         for n, (_, conv) in enumerate(self._all_convs):
             if n >= 2:
                 out["_all_convs/%d" % n] = conv
+        if self.use_pre_adv:
+            out["adv_dense/0"], out["adv_dense/1"] = self.adv_dense[0], self.adv_dense[1]
         return out
 
     def load_weights(self, weights, device="cuda"):
@@ -682,6 +727,8 @@ class HRNet(PBFNet):
                     for inp_scale in range(n_inp):
                         f = torch.relu(ans_convs[-1][inp_scale])
                         ext = filter_extent[max(inp_scale, scale)]
+                        if self.dens_norm and inp_scale < len(dens):  # models/hrnet.py:87-89
+                            f = torch.cat([f, f / dens[inp_scale] ** 2], dim=-1)
                         a = self.convs[layer][scale][0][inp_scale](f * importance, pos[inp_scale], pos[scale], ext, None)
                         if scale == inp_scale:
                             a = a + self.denses[layer][scale][0][inp_scale](f)

@@ -339,6 +339,15 @@ def point_sampling(inp_features, inp_positions, out_positions, extents, window_n
 # ----------------------------------------------------------------------------------------------------------
 # multi-scale sampling -- utils/tools/losses.py:136-181, 249-284
 # ----------------------------------------------------------------------------------------------------------
+def compute_density(out_pos, in_pos, radius, window_name=None):
+    """utils/tools/losses.py:287-308: sum over neighbours (self included) of win(d^2/r^2); identity window if None."""
+    idx, splits, d2 = fixed_radius_search(np.asarray(in_pos, F32), np.asarray(out_pos, F32), F32(radius))
+    q = d2.astype(np.float64) / (np.float64(F32(radius)) ** 2)
+    w = window(window_name, q) if window_name is not None else q
+    rows = np.repeat(np.arange(len(splits) - 1), np.diff(splits))
+    return np.bincount(rows, weights=w, minlength=len(splits) - 1)
+
+
 def grid_pos(pos, voxel_size, centralize=False, pad=0, hyst=0.1):
     """Lattice points of the voxel grid touched by any particle (utils/tools/losses.py:136-181).
     float32 arithmetic like the reference; first-occurrence order like ``tf.unique``."""
@@ -414,7 +423,9 @@ class ModelO64:
                  ignore_query_points=False, grav=-9.81, transformation={}, timestep=0.01, use_vel=True,
                  use_acc=True, use_box_feats=True, use_bnds=True, voxel_size=None, centralize=False,
                  out_scale=[0.01, 0.01, 0.01], sample_pad=0, sample_hyst=0.1, part_scale=1.0,
-                 add_merge=False, sym_kernel_size=[6, 6, 6], sym_axis=2, window_sym=None)
+                 add_merge=False, sym_kernel_size=[6, 6, 6], sym_axis=2, window_sym=None, window_dens=None,
+                 dens_feats=False, pres_feats=False, dens_norm=False, use_pre_adv=False, use_feats=False,
+                 dens_radius=None, rest_dens=3.5, stiffness=20.0)
         d.update(cfg)
         self.c = d
         self.w = weights
@@ -435,7 +446,7 @@ class ModelO64:
         return self.B.dense(x, self.w[key + "/kernel"], self.w[key + "/bias"])
 
     # -- BaseModel.call: models/base_model.py:23-29 -----------------------------------------------------------
-    def __call__(self, pos, vel, acc, box, bfeats):
+    def __call__(self, pos, vel, acc, box, bfeats, feats=None):
         c = self.c
         pos = np.asarray(pos, np.float64); vel = np.asarray(vel, np.float64)
         acc = None if acc is None else np.asarray(acc, np.float64)
@@ -471,24 +482,50 @@ class ModelO64:
             ff.append(vel2)
         if c["use_acc"]:
             ff.append(acc)
-        fluid_feats = np.concatenate(ff, axis=1)
+        if c["use_feats"]:
+            ff.append(np.asarray(feats, np.float64))
         bf = [np.ones((box_c.shape[0], 1))]
         if c["use_box_feats"]:
             bf.append(bfeats_c)
-        box_feats = np.concatenate(bf, axis=1)
         all_pos = np.concatenate([pos2, box_c], axis=0).astype(F32)
         pos2_32 = pos2.astype(F32); box_32 = box_c.astype(F32)
+        n_f = pos2.shape[0]
+        dens_radius = c["dens_radius"] if c["dens_radius"] is not None else c["particle_radii"]
+        dens0 = None
+        if c["dens_feats"] or c["dens_norm"] or c["pres_feats"]:  # models/pbf_model.py:351-367
+            dens0 = compute_density(all_pos, all_pos, dens_radius[0], c["window_dens"])
+            if c["dens_feats"]:
+                ff.append(dens0[:n_f, None]); bf.append(dens0[n_f:, None])
+            if c["pres_feats"]:  # utils/tools/losses.py:367-377
+                pres = np.maximum(c["stiffness"] * ((dens0 / c["rest_dens"]) ** 7 - 1), 0.0)
+                ff.append(pres[:n_f, None]); bf.append(pres[n_f:, None])
+        fluid_feats = np.concatenate(ff, axis=1)
+        box_feats = np.concatenate(bf, axis=1)
         ps = c["part_scale"]
         ans_conv, self.nns_fluid = self._conv("fluid_convs", fluid_feats * ps, pos2_32, all_pos, ext[0],
                                               return_nns=True)  # :378
         ans_dense = self._dense("fluid_dense", fluid_feats)
         ans_obs = self._conv("obs_convs", box_feats * ps, box_32, all_pos, ext[0])  # :382
         ans_dense_obs = self._dense("obs_dense", box_feats)
-        feats = np.concatenate([ans_conv, ans_obs, np.concatenate([ans_dense, ans_dense_obs], axis=0)], axis=1)
+        ans_dense = np.concatenate([ans_dense, ans_dense_obs], axis=0)
+        if c["use_pre_adv"]:  # :388-399
+            pre = np.ones((n_f, 1))
+            if c["use_vel"]:
+                pre = np.concatenate([pre, vel], axis=1)
+            ans_adv = self._conv("adv_convs/0", pre * ps, pos.astype(F32), all_pos, ext[0])
+            ans_dens_adv = np.concatenate([self._dense("adv_dense/0", pre), ans_dense_obs], axis=0)
+            feats = np.concatenate([ans_conv, ans_obs, ans_adv, ans_dense, ans_dens_adv], axis=1)
+        else:
+            feats = np.concatenate([ans_conv, ans_obs, ans_dense], axis=1)
         dil = get_dilated_pos(all_pos if c["use_bnds"] else pos2_32, c["strides"], c["voxel_size"],
                               c["centralize"], c["sample_pad"], c["sample_hyst"])  # :413-419
         self.dilated_pos = dil
-        n_f = pos2.shape[0]
+        self.dens = None
+        if c["dens_norm"]:  # :421-435 (the radius is passed as the sampling extent)
+            self.dens = [(dens0 if c["use_bnds"] else dens0[:n_f])[:, None]]
+            for sc in range(1, len(dens_radius)):
+                d = point_sampling(self.dens[-1], dil[sc - 1], dil[sc], F32(dens_radius[sc]), c["window_dens"], True)
+                self.dens.append(np.maximum(d, 1e-2))
         # forward
         if self.name == "CConv":
             out = self._forward_cconv(dil, feats, ext, n_f)
@@ -524,7 +561,7 @@ class ModelO64:
             lc = lc[:-1]
         if not c["use_bnds"]:
             feats = feats[:n_f]
-        n = 2  # _all_convs numbering: 0 fluid_obs, 1 obs_conv (models/pbf_model.py:223)
+        n = 4 if c["use_pre_adv"] else 2  # _all_convs numbering: 0 fluid_obs, 1 obs_conv (, 2-3 adv_conv0/1) (models/pbf_model.py:223)
         ans_convs = [[feats]]
         for i in range(1, len(lc)):
             ans = []
@@ -536,6 +573,8 @@ class ModelO64:
                 for l in range(len(lc[i - 1])):
                     fe = np.maximum(ans_convs[-1][l], 0.0)
                     e = ext[max(l, j)]
+                    if c["dens_norm"] and l < len(self.dens):  # models/hrnet.py:87-89
+                        fe = np.concatenate([fe, fe / self.dens[l] ** 2], axis=1)
                     key = "_all_convs/%d" % n
                     n += 1
                     a = self._conv(key, fe * imp, pos[l], pos[j], e,

@@ -200,3 +200,40 @@ def test_rollout_pipeline(cuda):
     # physically sane: particles stay inside the box (walls half a pitch outside [0, 0.4]) and fall under gravity
     assert p[-1][:, 1].mean() < p[0][:, 1].mean() + 1e-3
     assert p.min() > -0.2 and p[:, :, [0, 2]].max() < 0.6
+
+
+@pytest.mark.parametrize("flags", [dict(dens_feats=True, pres_feats=True), dict(use_pre_adv=True), dict(dens_norm=True),
+                                   dict(dens_feats=True, pres_feats=True, use_pre_adv=True, dens_norm=True, add_merge=False)],
+                         ids=["dens+pres feats", "pre_adv", "dens_norm", "all, concat merge"])
+def test_a16_optional_input_branches(cuda, flags):
+    """density / pressure input features, the pre-advection conv and the density pyramid of dens_norm
+    (models/pbf_model.py:351-367, 388-399, 421-435; models/hrnet.py:87-89) on the layer-by-layer path vs the oracle."""
+    from dmcf_b200 import config, scenes
+    cfg = dict(name="SymNet", layer_channels=[[[8]], [[8], [4]], [[8]], [[3]]], kernel_size=[4, 4, 4],
+               sym_kernel_size=[6, 6, 6], coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear",
+               window="poly6", window_sym="peak", window_dens="poly6", strides=[1, 2], particle_radii=[0.1, 0.2],
+               timestep=0.02, grav=-9.81, out_scale=[0.0078125] * 3, centralize=True, voxel_size=[0.025] * 3, sym_axis=1,
+               rest_dens=8.0, add_merge=True, use_acc=False)
+    cfg.update(flags)
+    scene = scenes.lattice_scene((9, 8, 7), dx=0.05, seed=5, open_top=True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(cuda)
+    torch.manual_seed(3)
+    model = config.build_model(cfg)
+    assert model.fused is False
+    data = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
+    model(data)  # builds the layers lazily (Keras-style initialisers)
+    gen = torch.Generator().manual_seed(11)
+    for layer in model.named_layers().values():  # non-trivial biases too
+        if layer.bias is not None:
+            layer.bias.data = ((torch.rand(layer.bias.shape, generator=gen) * 2 - 1) * 0.1).to(cuda)
+    pos_u, vel_u = model(data)
+    ref = o64.ModelO64(cfg, oracle_weights(model))
+    pos_r, vel_r = ref(scene["pos"], scene["vel"], None, scene["box"], scene["box_normals"])
+    n_f = scene["pos"].shape[0]
+    net = model.net_out.cpu().numpy()
+    scale = np.abs(ref.net_out).max()
+    tol = (2e-5 * scale + 1e-6) * 8
+    assert np.abs(net[:n_f] - ref.net_out[:n_f]).max() <= tol
+    assert np.abs(pos_u.cpu().numpy() - pos_r).max() <= tol * 0.0078125 + 4e-7 * max(np.abs(pos_r).max(), 1.0)
+    if flags.get("dens_norm"):
+        assert len(ref.dens) == 2 and ref.dens[1].min() >= 1e-2
