@@ -220,3 +220,27 @@ def test_run_sample_rollout_cli_body(cuda):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(cuda)
     ref = sim.step([t(z["pos"]), t(z["vel"] + np.array([10.0, 0, -6.0], np.float32)), None, None, t(z["box"]), t(z["box_normals"])])
     assert torch.allclose(res[1], ref[0], rtol=0, atol=2e-6)
+
+
+def test_density_loss_and_rollout_metrics(cuda):
+    """utils/tools/losses.py:380-398 on the GPU vs the oracle's density; run_valid's metric dict is finite."""
+    from dmcf_b200 import metrics
+    from dmcf_b200.losses import get_window_func
+    rng = np.random.default_rng(3)
+    gt = (rng.random((700, 3)) * 0.3).astype(np.float32)
+    pred = (gt + rng.normal(0, 0.004, gt.shape)).astype(np.float32)
+    box = (rng.random((100, 3)) * 0.3).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    r = 0.05
+    got = float(metrics.density_loss(t(gt), t(pred), torch.cat([t(pred), t(box)]), torch.cat([t(gt), t(box)]), radius=r,
+                                     win=get_window_func("poly6")))
+    dp = o64.compute_density(pred, np.concatenate([gt, box]), r, "poly6")
+    dg = o64.compute_density(gt, np.concatenate([pred, box]), r, "poly6")
+    ref = np.maximum(dp - dg.max() - 0.01, 0).mean()
+    assert abs(got - ref) <= 1e-5 * max(abs(ref), 1.0)
+    got_max = float(metrics.density_loss(t(gt), t(pred), radius=r, win=get_window_func("poly6"), use_max=True))
+    d1, d2 = o64.compute_density(pred, pred, r, "poly6"), o64.compute_density(gt, gt, r, "poly6")
+    assert abs(got_max - abs(d1.max() - d2.max()) / d2.max()) <= 1e-5
+    vel = rng.standard_normal(gt.shape).astype(np.float32)
+    m = metrics.rollout_metrics(t(pred), t(vel), t(gt), t(vel * 1.1), t(box), split="valid")
+    assert set(m) >= {"mse_val", "chamfer_val", "dens_val", "chamfer_val_2", "vel_diff_val"} and all(np.isfinite(v) for v in m.values())
