@@ -47,6 +47,8 @@ SIGNATURES = {
     "dmcf_exclusive_scan_i32_i32": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "dmcf_cconv_forward": (c_i32, [C.POINTER(ConvDesc), c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp,
                                    c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
+    "dmcf_cconv_patches": (c_i32, [C.POINTER(ConvDesc), c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                   c_i64, c_vp, c_i64, c_vp]),
     "dmcf_cconv_records_bytes": (c_sz, [c_i64]),
     "dmcf_cconv_prepare": (c_i32, [C.POINTER(ConvDesc), c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
                                    c_vp]),
@@ -77,7 +79,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dmcf_version() < 101:
+    if lib.dmcf_version() < 102:
         raise DmcfError("libdmcf_b200.so is older than this package")
     _lib = lib
     return lib

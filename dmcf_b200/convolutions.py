@@ -177,9 +177,13 @@ class ContinuousConv(torch.nn.Module):
                 r = torch.tensor(radius, dtype=torch.float32, device=inp_positions.device)
                 neighbors_importance = win(self.nns.neighbors_distance / (r * r))
         self._avg_neighbors = neighbors_index.shape[0] / max(out_positions.shape[0], 1)
-        kernel = self.effective_kernel()
         if self.symmetric and inp_positions.shape[0] != out_positions.shape[0]:
             raise ValueError("an antisymmetric ContinuousConv needs inp_positions == out_positions")
+        if torch.is_grad_enabled() and (self.kernel.requires_grad or inp_features.requires_grad
+                                        or (self.bias is not None and self.bias.requires_grad)):
+            return self._forward_with_grad(inp_features, inp_positions, out_positions, extent, inp_importance,
+                                           neighbors_index, neighbors_row_splits, neighbors_importance, fused_window)
+        kernel = self.effective_kernel()
         out = ops.continuous_conv(kernel, out_positions, extent, self.offset, inp_positions, inp_features,
                                   inp_importance, neighbors_index, neighbors_importance, neighbors_row_splits,
                                   align_corners=self.align_corners, coordinate_mapping=self.coordinate_mapping,
@@ -190,6 +194,39 @@ class ContinuousConv(torch.nn.Module):
         self._conv_output = out
         if self.use_dense_layer_for_center:
             out = out + ops.dense(inp_features, self.dense_kernel)
+        if self.use_bias:
+            out = out + self.bias
+        if self.activation is not None:
+            out = self.activation(out)
+        return out
+
+    def _forward_with_grad(self, inp_features, inp_positions, out_positions, extent, inp_importance, neighbors_index,
+                           neighbors_row_splits, neighbors_importance, fused_window):
+        """Training path: the same layer through ``dmcf_b200.autograd`` (gradients w.r.t. the stored kernel, the bias and
+        the input features).  The antisymmetric layer runs in the reference's two-pass form (utils/convolutions.py:431-458),
+        which is a composition of plain convs and a batched matmul."""
+        from . import autograd
+        if self.circular or self.normalize or inp_importance is not None or neighbors_importance is not None or (
+                self.offset is not None and float(torch.as_tensor(self.offset).abs().sum()) != 0.0):
+            raise NotImplementedError("gradients: circular / normalize / importances / offset are not supported")
+        k = self.kernel
+        kernel = torch.cat([-torch.flip(k, dims=(0, 1, 2)), k], dim=self.sym_axis) if self.symmetric else k
+        kw = dict(align_corners=self.align_corners, coordinate_mapping=self.coordinate_mapping,
+                  interpolation=self.interpolation, window=fused_window.typ if fused_window else None,
+                  window_fac=fused_window.fac if fused_window else 1.0)
+        drop_self = self.radius_search_ignore_query_points
+        out = autograd.continuous_conv(kernel.contiguous(), out_positions, extent, inp_positions, inp_features,
+                                       neighbors_index, neighbors_row_splits, drop_self=drop_self, **kw)
+        if self.symmetric:
+            kz, ky, kx, cin, cout = kernel.shape
+            weights = kernel.reshape(kz, ky, kx, 1, cin * cout).contiguous()
+            ones = torch.ones_like(inp_features[..., :1])
+            w_values = autograd.continuous_conv(weights, out_positions, extent, inp_positions, ones, neighbors_index,
+                                                neighbors_row_splits, drop_self=drop_self, **kw)
+            out = out + torch.bmm(inp_features.unsqueeze(1), w_values.reshape(-1, cin, cout)).squeeze(1)
+        self._conv_output = out
+        if self.use_dense_layer_for_center:
+            out = out + inp_features @ self.dense_kernel
         if self.use_bias:
             out = out + self.bias
         if self.activation is not None:

@@ -136,6 +136,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_tile(const ConvParams p) {
         }
     }
     __syncthreads();
+    if (p.patch_out) {  // dmcf_cconv_patches: export the patch rows instead of multiplying them with the filter
+        for (int idx = tid; idx < MT * p.kc_conv; idx += NW * 32) {
+            const int m = idx / p.kc_conv, k = idx - m * p.kc_conv;
+            const int64_t o = tile_base + m;
+            if (o < p.n_out) p.patch_out[o * p.patch_stride + k] = patch[(size_t)m * p.kc_pad + k];
+        }
+        return;
+    }
 
     cconv_phase2<MT, NW, false>(p, patch, red, norm, tile_base);
 }
@@ -382,6 +390,44 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
     if (conv_smem_bytes(8, 16, p.kc_pad, p.cp) <= limit) return launch_cconv<8, 16>(p, st);
     return set_error(DMCF_ERR_UNSUPPORTED, "cconv: filter %dx%dx%dx%d needs %zu B of shared memory per 8 points (> %zu)",
                      p.gp.kz, p.gp.ky, p.gp.kx, d->cin, conv_smem_bytes(8, 16, p.kc_pad, p.cp), limit);
+}
+
+// Patch rows only: the trilinear "patch" of every out point, B[o][cell*cin + ci] = sum_n a_n w_cell(n,o) g(f_n)[ci], i.e. the
+// matrix whose product with the flattened filter is the conv output.  This is what the gradient w.r.t. the filter needs
+// (dW = B^T dOut, a plain GEMM), see dmcf_b200/autograd.py.
+extern "C" int dmcf_cconv_patches(const dmcf_conv_desc* d, const float* out_positions, int64_t n_out, const float* inp_positions,
+                                  const float* inp_features, int64_t inp_stride, int64_t n_inp, const float* inp_importance,
+                                  const int32_t* neighbors_index, const int64_t* neighbors_row_splits,
+                                  const float* neighbors_importance, const float* pair_records, int64_t n_pairs,
+                                  float* patches, int64_t patch_stride, void* stream) {
+    ConvParams p;
+    int rc = fill_params(d, nullptr, out_positions, n_out, inp_positions, inp_features, inp_stride, n_inp, inp_importance,
+                         neighbors_index, neighbors_row_splits, neighbors_importance, &p);
+    if (rc) return rc;
+    DMCF_REQUIRE(d->dense_cin == 0 && !d->normalize && !d->ascc, "cconv_patches: dense / normalize / ascc are not supported");
+    if (n_out == 0) return DMCF_OK;
+    DMCF_REQUIRE(out_positions && neighbors_row_splits && patches, "cconv_patches: NULL buffer");
+    DMCF_REQUIRE(n_inp == 0 || (inp_features && (pair_records || (inp_positions && neighbors_index))), "cconv_patches: NULL input buffer");
+    DMCF_REQUIRE(inp_stride >= d->cin && patch_stride >= p.kc_conv, "cconv_patches: row stride smaller than the row");
+    p.records = pair_records; p.n_pairs = n_pairs;
+    p.patch_out = patches; p.patch_stride = patch_stride;
+    p.cout = 4;  // unused by phase 1; keeps the launch heuristics (shared-memory sizes) in their usual range
+    p.cp = 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int options = g_kernel_options.load(std::memory_order_relaxed);
+    if ((options & 1) && !(options & 8)) {
+        bool handled = false;
+        rc = launch_cconv_lean(p, st, &handled);
+        if (rc || handled) return rc;
+    }
+    const size_t limit = 227 * 1024;
+    if (conv_smem_bytes(32, 8, p.kc_pad, p.cp) <= limit / 2) return launch_cconv<32, 8>(p, st);
+    if (conv_smem_bytes(32, 16, p.kc_pad, p.cp) <= limit) return launch_cconv<32, 16>(p, st);
+    if (conv_smem_bytes(24, 16, p.kc_pad, p.cp) <= limit) return launch_cconv<24, 16>(p, st);
+    if (conv_smem_bytes(16, 16, p.kc_pad, p.cp) <= limit) return launch_cconv<16, 16>(p, st);
+    if (conv_smem_bytes(8, 16, p.kc_pad, p.cp) <= limit) return launch_cconv<8, 16>(p, st);
+    return set_error(DMCF_ERR_UNSUPPORTED, "cconv_patches: filter %dx%dx%dx%d needs too much shared memory", p.gp.kz, p.gp.ky,
+                     p.gp.kx, d->cin);
 }
 
 extern "C" int dmcf_set_kernel_options(int options) {

@@ -38,6 +38,9 @@ struct ConvParams {
     // {row, i0, i1, wx0, wx1, wy0, wy1, wz0*a, wz1*a}; row < 0 marks a dropped pair
     const float* records;
     int64_t n_pairs;
+    // dmcf_cconv_patches: stop after phase 1 and write the patch rows [n_out, kc_conv] here (filters is not read)
+    float* patch_out;
+    int64_t patch_stride;
 };
 
 static constexpr int kRecordFields = 9;

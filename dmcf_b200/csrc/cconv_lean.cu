@@ -155,8 +155,29 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         fsrc += fstep;
     };
     __syncwarp();
-    issue(0, slot0); issue(1, slot1);
+    if (!p.patch_out) { issue(0, slot0); issue(1, slot1); }
     __syncthreads();  // patch tile complete
+    if (p.patch_out) {
+        // dmcf_cconv_patches: the patch tile goes to global memory (row o = [kc_conv] floats), consecutive threads take
+        // consecutive k-quads of one point: conflict-free LDS.128, coalesced 16-byte stores
+        const float4* p4 = reinterpret_cast<const float4*>(patch);
+        const int kq_conv = (p.kc_conv + 3) / 4;
+        const bool vec = (p.kc_conv & 3) == 0 && (p.patch_stride & 3) == 0 && ((uintptr_t)p.patch_out & 15) == 0;
+        for (int idx = tid; idx < MT * kq_conv; idx += NW * 32) {
+            const int m = idx / kq_conv, kq = idx - m * kq_conv;
+            const int64_t oo = tile_base + m;
+            if (oo >= p.n_out) continue;
+            const float4 v = p4[(size_t)kq * MTP + m];
+            float* dst = p.patch_out + oo * p.patch_stride + 4 * kq;
+            if (vec) {
+                *reinterpret_cast<float4*>(dst) = v;
+            } else {
+                const float e[4] = {v.x, v.y, v.z, v.w};
+                for (int j = 0; j < 4 && 4 * kq + j < p.kc_conv; ++j) dst[j] = e[j];
+            }
+        }
+        return;
+    }
     if (p.debug_wrap_w & 2) {  // timing experiment: phase 1 only
         lean::cp_wait<0>();
         return;

@@ -284,6 +284,56 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     return out
 
 
+def conv_patches(kernel_size, out_positions, extents, inp_positions, inp_features, neighbors_index, neighbors_row_splits,
+                 align_corners=True, coordinate_mapping="ball_to_cube_radial", interpolation="linear", *, window=None,
+                 window_fac=1.0, relu_input=False, feat_scale=1.0, skip_self=False, neighbors_importance=None, out=None):
+    """The patch matrix of a conv (dmcf_cconv_patches): ``[n_out, kz*ky*kx*cin]`` with
+    ``continuous_conv(filters, ...) == patches @ filters.reshape(-1, cout)``; the gradient of the conv w.r.t. its filter
+    is ``patches.T @ d_out``.  ``out_positions`` / ``neighbors_row_splits`` may be a slice [a:b] / [a:b+1] of the full
+    arrays (row_splits hold absolute offsets into ``neighbors_index``)."""
+    lib = _lib.load()
+    out_positions = _pos(out_positions, "out_positions")
+    inp_positions = _pos(inp_positions, "inp_positions")
+    inp_features, inp_stride = _rows(inp_features, "inp_features")
+    _req(neighbors_index, "neighbors_index", torch.int32, 1)
+    _req(neighbors_row_splits, "neighbors_row_splits", torch.int64, 1)
+    neighbors_index = neighbors_index.contiguous()
+    neighbors_row_splits = neighbors_row_splits.contiguous()
+    n_out, n_inp, cin = out_positions.shape[0], inp_positions.shape[0], inp_features.shape[1]
+    if neighbors_row_splits.shape[0] != n_out + 1:
+        raise ValueError("neighbors_row_splits must have n_out+1 entries")
+    kz, ky, kx = (int(k) for k in kernel_size)
+    d = ConvDesc()
+    d.kernel_size[:] = [kz, ky, kx]
+    d.cin, d.cout = cin, 4
+    d.mapping = MAPPINGS[coordinate_mapping]
+    d.interpolation = INTERPOLATIONS[interpolation]
+    d.align_corners = int(bool(align_corners))
+    d.normalize = 0
+    d.window = WINDOWS[window]
+    d.window_fac = float(window_fac)
+    d.extent = float(torch.as_tensor(extents).reshape(-1)[0])
+    d.offset[:] = [0.0, 0.0, 0.0]
+    d.relu_input = int(bool(relu_input))
+    d.feat_scale = float(feat_scale)
+    d.skip_self = int(bool(skip_self))
+    if neighbors_importance is not None:
+        _req(neighbors_importance, "neighbors_importance", dim=1)
+        neighbors_importance = neighbors_importance.contiguous()
+    kc = kz * ky * kx * cin
+    if out is None:
+        out = torch.empty((n_out, kc), dtype=torch.float32, device=out_positions.device)
+    _req(out, "out", dim=2)
+    if out.shape[0] != n_out or out.shape[1] != kc or out.stride(1) != 1:
+        raise ValueError("out has the wrong shape / layout")
+    if neighbors_index.numel() == 0:
+        neighbors_index = torch.zeros(1, dtype=torch.int32, device=out_positions.device)
+    check(lib.dmcf_cconv_patches(C.byref(d), _p(out_positions), n_out, _p(inp_positions), _p(inp_features), inp_stride,
+                                 n_inp, None, _p(neighbors_index), _p(neighbors_row_splits), _p(neighbors_importance), None,
+                                 0, _p(out), out.stride(0) if n_out > 1 else kc, _stream()))
+    return out
+
+
 def prepare_pair_records(kernel_size, out_positions, extents, offset, inp_positions, inp_importance, neighbors_index,
                          neighbors_importance, neighbors_row_splits, align_corners=True,
                          coordinate_mapping="ball_to_cube_radial", interpolation="linear", *, window=None, window_fac=1.0,

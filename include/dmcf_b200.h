@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DMCF_B200_VERSION 101
+#define DMCF_B200_VERSION 102
 
 enum dmcf_status {
     DMCF_OK = 0,
@@ -150,6 +150,17 @@ int dmcf_cconv_prepare(const dmcf_conv_desc* desc, const float* out_positions, i
                        const float* inp_positions, int64_t n_inp, const float* inp_importance,
                        const int32_t* neighbors_index, const int64_t* neighbors_row_splits,
                        const float* neighbors_importance, int64_t n_pairs, float* records, void* stream);
+
+/* The "patch" rows of a continuous_conv (no reference counterpart as a separate op: Open3D materialises the same matrix
+ * inside continuous_conv / continuous_conv_backprop_filter): patches[o, cell*cin + ci] = sum_n a_n w_cell(n,o) g(f_n)[ci] with
+ * a_n, g as in dmcf_cconv_forward (window, relu_input, feat_scale, skip_self, nbr range).  out = patches @ filters, so the
+ * gradient of a conv w.r.t. its filter is patches^T @ d_out (dmcf_b200/autograd.py).  patch_stride >= kz*ky*kx*cin floats.
+ * desc->cout is ignored; dense_cin, normalize and ascc must be 0. */
+int dmcf_cconv_patches(const dmcf_conv_desc* desc, const float* out_positions, int64_t n_out,
+                       const float* inp_positions, const float* inp_features, int64_t inp_stride, int64_t n_inp,
+                       const float* inp_importance, const int32_t* neighbors_index, const int64_t* neighbors_row_splits,
+                       const float* neighbors_importance, const float* pair_records, int64_t n_pairs,
+                       float* patches, int64_t patch_stride, void* stream);
 
 /* Kernel selection bit mask (default 3): bit 0 = register-patch kernels for compile-time filter grids (k_cconv_lean;
  * k_cconv_wide where the lean kernel is not eligible), bit 1 = resident-filter direct kernel for cout <= 4
