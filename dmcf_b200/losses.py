@@ -97,3 +97,31 @@ def compute_density(out_pos, in_pos=None, radius=0.005, win=None):
     csum[1:] = torch.cumsum(w.to(torch.float64), 0)
     rs = nns.neighbors_row_splits
     return (csum[rs[1:]] - csum[rs[:-1]]).to(torch.float32)
+
+
+def get_loss(typ, fac=1.0, **kwargs):
+    """Training losses of utils/tools/losses.py:47-134 that need nothing but the predicted / target positions:
+    'mse', 'weighted_mse', 'vel', and 'dense' (density_loss)."""
+    gamma = kwargs.get("gamma", 0.5)
+
+    def pre_factor(kw):
+        return math.exp(-kwargs.get("pre_scale", 0.0) * float(kw.get("pre_steps") or 0))
+
+    if typ == "mse":
+        return lambda target, pred, **kw: fac * (pre_factor(kw) * (((target - pred) ** 2).sum(-1) + 1e-9) ** gamma).mean()
+    if typ == "weighted_mse":
+        def f(target, pred, **kw):
+            importance = torch.exp(-kwargs.get("neighbor_scale", 1.0) * kw.get("num_fluid_neighbors"))
+            return fac * (pre_factor(kw) * importance * (((target - pred) ** 2).sum(-1) + 1e-9) ** gamma).mean()
+        return f
+    if typ == "vel":
+        def f(target, pred, **kw):
+            inp, prev = kw.get("input")[0], kw.get("target_prev")
+            return fac * ((((target - prev) - (pred - inp)) ** 2).sum(-1) + 1e-9).pow(gamma).mean()
+        return f
+    if typ == "dense":
+        from functools import partial
+        from .metrics import density_loss
+        kw2 = dict(kwargs)
+        return partial(density_loss, win=get_window_func(kw2.pop("win", None)), **kw2)
+    raise NotImplementedError(f"loss {typ!r}")

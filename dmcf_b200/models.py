@@ -43,6 +43,8 @@ class Dense(torch.nn.Module):
     def forward(self, x, relu_input=False):
         if self.kernel is None:
             self.build(x.shape[-1], x.device)
+        if torch.is_grad_enabled() and (self.kernel.requires_grad or self.bias.requires_grad or x.requires_grad):
+            return (torch.relu(x) if relu_input else x) @ self.kernel + self.bias  # training path: plain torch ops
         return ops.dense(x, self.kernel, self.bias, relu_input=relu_input)
 
 
@@ -250,8 +252,9 @@ class PBFNet(BaseModel):
 
     # -- full step ------------------------------------------------------------------------------------------
     def call(self, data, training=False, **kwargs):
-        if training:
-            raise NotImplementedError("training is out of scope (SURVEY 8f rank 1)")
+        if training and self.fused:
+            raise NotImplementedError("training=True runs on the layer-by-layer path: call set_trainable(True) (or set "
+                                      "fused=False) first; the fused step has no backward")
         data = list(data)
         if len(data) != 6:
             raise ValueError("data must be [pos, vel, acc, feats, box, box_normals]")
@@ -510,8 +513,38 @@ class PBFNet(BaseModel):
         self.net_out = out
         pos2, vel2 = self.integrate_pos_vel(pos, vel, acc)
         scale = self.out_scale
+        if torch.is_grad_enabled() and out.requires_grad:  # training path: the same arithmetic in torch ops (:466-487)
+            o = out.repeat(1, 3) if out.shape[-1] == 1 else (torch.cat([out, out[:, :1]], dim=-1) if out.shape[-1] == 2 else out)
+            pos_new = pos2 + torch.tensor(scale, dtype=torch.float32, device=out.device) * o[:pcnt]
+            return [pos_new, (pos_new - pos) / self.timestep]
         pos_new, vel_new = ops.correct(pos, pos2, out, scale, self.timestep)
         return [pos_new, vel_new]
+
+    # -- training hooks: models/pbf_model.py:491-517 --------------------------------------------------------------
+    def set_trainable(self, flag=True):
+        """Training runs on the layer-by-layer path through ``dmcf_b200.autograd`` (layers must be built: load or init
+        weights first)."""
+        if flag:
+            self.fused = False
+        for prm in self.parameters():
+            prm.requires_grad_(flag)
+        self._wcache = {}
+        return self
+
+    def loss(self, results, data, loss_fn=None):
+        """``results`` = [pos, vel] of a model call, ``data`` = [inputs, target, target_prev, pre_steps] (:494-509)."""
+        from .losses import get_loss
+        fns = loss_fn if loss_fn is not None else (getattr(self, "loss_fn", None) or {"mse": get_loss("mse")})
+        return {n: l(data[1], results[0], num_fluid_neighbors=self.fluid_neighbor_counts(), input=data[0],
+                     target_prev=data[2], pre_steps=data[3], pos_correction=None) for n, l in fns.items()}
+
+    def get_optimizer(self, cfg):
+        """Adam(eps=1e-6) with the piecewise-constant learning-rate schedule of the YAML (:511-517)."""
+        bounds, values = list(cfg["lr_boundaries"]), list(cfg["lr_values"])
+        opt = torch.optim.Adam([p for p in self.parameters() if p.requires_grad], lr=values[0], eps=1e-6)
+        import bisect
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: values[bisect.bisect_right(bounds, it)] / values[0])
+        return opt, sched
 
     @property
     def pos_correction(self):

@@ -127,3 +127,59 @@ def test_layer_training_path_incl_antisymmetric_layer(cuda):
         opt.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < losses[0]
+
+
+def test_model_gradients_and_train_step(cuda):
+    """Whole SymNet on the layer-by-layer path: d loss / d parameters from autograd vs central differences of the float64
+    oracle model along random directions (a conv kernel of the stack, a Dense kernel, the antisymmetric half kernel, an
+    input-conv bias), then a few optimisation steps of training.train_step reduce the loss."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import test_models_gpu as T
+    from dmcf_b200 import config, scenes, training
+    cfg = dict(name="SymNet", layer_channels=[[[4]], [[8]], [[8]], [[3]]], kernel_size=[4, 4, 4], sym_kernel_size=[6, 6, 6],
+               coordinate_mapping=MAP, interpolation="linear", window="poly6", window_sym="peak", strides=[1],
+               particle_radii=[0.1], timestep=0.02, grav=-9.81, out_scale=[0.0078125] * 3, sym_axis=1, add_merge=True,
+               use_acc=False)
+    scene = scenes.lattice_scene((6, 5, 5), dx=0.05, seed=9, open_top=True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(cuda)
+    model = config.build_model(cfg)
+    model.init_weights(seed=4, device=cuda, scale=0.2)
+    model.set_trainable(True)
+    sample = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
+    rng = np.random.default_rng(1)
+    target = scene["pos"] + np.array([0, -0.004, 0], np.float32) + rng.normal(0, 0.002, scene["pos"].shape).astype(np.float32)
+    pos, vel = model(sample, training=True)
+    loss = model.loss([pos, vel], [sample, t(target), sample[0], 0])["mse"]
+    loss.backward()
+    names = {n: l for n, l in model.named_layers().items()}
+    weights = T.oracle_weights(model)
+
+    def oracle_loss(w):
+        p, _ = o64.ModelO64(cfg, w)(scene["pos"], scene["vel"], None, scene["box"], scene["box_normals"])
+        return np.mean((((target.astype(np.float64) - p) ** 2).sum(-1) + 1e-9) ** 0.5)
+
+    assert abs(float(loss.detach()) - oracle_loss(weights)) <= 1e-5 * oracle_loss(weights) + 1e-7
+    picks = [("_all_convs/3", "kernel"), ("denses/0/0/0/0", "kernel"), ("sym_convs/0", "kernel"), ("fluid_convs", "bias")]
+    for lname, attr in picks:
+        # a layer is addressed by its checkpoint name or one of its aliases; the oracle's weight dict holds both
+        name, layer = next((n, l) for n, l in names.items() if n == lname or lname in getattr(l, "_aliases", []))
+        keys = [k + "/" + attr for k in [name] + list(getattr(layer, "_aliases", [])) if k + "/" + attr in weights]
+        g = getattr(layer, attr).grad.double().cpu().numpy()
+        base = weights[keys[0]].astype(np.float64)
+        d = rng.standard_normal(base.shape)
+        eps = 1e-3 * max(np.abs(base).max(), 1e-2)
+        wp, wm = dict(weights), dict(weights)
+        for k in keys:
+            wp[k], wm[k] = base + eps * d, base - eps * d
+        fd = (oracle_loss(wp) - oracle_loss(wm)) / (2 * eps)
+        for k in keys:
+            wp[k], wm[k] = base + 0.25 * eps * d, base - 0.25 * eps * d
+        fd2 = (oracle_loss(wp) - oracle_loss(wm)) / (0.5 * eps)
+        an = (g * d).sum()
+        # the loss is piecewise smooth (relu): accept the spread of the two difference quotients as their uncertainty
+        assert abs(an - fd2) <= 5e-3 * max(abs(fd2), abs(an)) + 2 * abs(fd - fd2) + 1e-8, (lname, an, fd, fd2)
+    opt, sched = model.get_optimizer({"lr_boundaries": [1000], "lr_values": [1e-3, 1e-4]})
+    tgt = torch.stack([sample[0], t(target)])
+    losses = [training.train_step(model, opt, [sample], [tgt], grad_clip_norm=1.0, scheduler=sched)[0] for _ in range(6)]
+    assert losses[-1] < losses[0]
