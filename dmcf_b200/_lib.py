@@ -60,6 +60,12 @@ SIGNATURES = {
     "dmcf_grid_pos_emit": (c_i32, [c_vp, c_vp, C.POINTER(c_f32), C.POINTER(c_f32), C.POINTER(c_i32), C.POINTER(c_i32),
                                    c_vp, c_vp]),
     "dmcf_correct": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_i64, c_vp, c_vp, c_vp]),
+    "dmcf_farthest_point_sample": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
+    "dmcf_approx_match_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "dmcf_approx_match": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "dmcf_match_cost_workspace_bytes": (c_sz, [c_i32, c_i32]),
+    "dmcf_match_cost": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "dmcf_nn_distance": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
 }
 
 _lib = None
@@ -79,7 +85,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dmcf_version() < 102:
+    if lib.dmcf_version() < 103:
         raise DmcfError("libdmcf_b200.so is older than this package")
     _lib = lib
     return lib

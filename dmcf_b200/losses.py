@@ -64,8 +64,9 @@ def grid_pos(pos, voxel_size, centralize=False, pad=0, hyst=0.1, center=None):
 
 
 def get_dilated_pos(pos, strides, voxel_size=None, centralize=False, pad=0, hyst=0.1):
-    """utils/tools/losses.py:249-284 (voxel mode).  Returns (positions per scale, counts per scale, idx) like the
-    reference; ``idx`` is unused in voxel mode."""
+    """utils/tools/losses.py:249-284.  Returns (positions per scale, counts per scale, idx) like the reference: voxel
+    lattices (``grid_pos``) when ``voxel_size`` is given, else nested farthest-point subsets with ``idx[s]`` = int32
+    [1, N_s] indices of scale s inside scale s-1 (``idx`` is only filled in that mode, like the reference)."""
     dilated, pcnt, idx = [], [], []
     center = None
     for stride in strides:
@@ -74,8 +75,13 @@ def get_dilated_pos(pos, strides, voxel_size=None, centralize=False, pad=0, hyst
             pcnt.append(pos.shape[0])
             idx.append(None)
         else:
-            if voxel_size is None:
-                raise NotImplementedError("farthest-point sub-sampling (voxel_size: null) is out of scope (SURVEY 8f)")
+            if voxel_size is None:  # :274-282: N // stride farthest points of the PREVIOUS scale (nested subsets)
+                from .pointops import farthest_point_sample, gather_point
+                sample_cnt = max(pos.shape[0] // int(stride), 1)
+                pcnt.append(sample_cnt)
+                idx.append(farthest_point_sample(sample_cnt, dilated[-1].unsqueeze(0)))
+                dilated.append(gather_point(dilated[-1].unsqueeze(0), idx[-1])[0])
+                continue
             if centralize and center is None:
                 center = point_mean(pos)
             vs = torch.as_tensor(voxel_size, dtype=torch.float32).reshape(3) * float(stride)

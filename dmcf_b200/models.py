@@ -138,6 +138,8 @@ class PBFNet(BaseModel):
         self.use_pre_adv, self.use_feats = bool(use_pre_adv), bool(use_feats)
         if self.dens_feats or self.pres_feats or self.dens_norm or self.use_pre_adv or self.use_feats:
             fused = False
+        if voxel_size is None and any(s != 1 for s in strides):
+            fused = False  # farthest-point multi-scale sampling (utils/tools/losses.py:274-282): layer-by-layer path
         self.kernel_size = list(kernel_size)
         self.channel = channels
         self.strides = list(strides)
@@ -692,7 +694,12 @@ class HRNet(PBFNet):
         return out
 
     def _dense_used(self, i, j, k, l):
-        return k > 0 or j == l  # voxel mode: only the diagonal Dense layers ever run (models/hrnet.py:94-99)
+        # voxel mode: only the diagonal Dense layers ever run (models/hrnet.py:94-99); with farthest-point sampling the
+        # cross-scale ones act on gathered / scattered rows (:100-113)
+        return k > 0 or j == l or self._fps_scales()
+
+    def _fps_scales(self):
+        return self.voxel_size is None and any(s != 1 for s in self.strides)
 
     def _scale_channels(self):
         """Channel count of ans_convs[layer][scale] for every layer (index 0 = the preprocess output)."""
@@ -767,6 +774,17 @@ class HRNet(PBFNet):
                             a = a + self.denses[layer][scale][0][inp_scale](f)
                             if a.shape[-1] == ans_convs[-1][scale].shape[-1]:
                                 a = a + ans_convs[-1][scale]
+                        elif self.voxel_size is None:  # models/hrnet.py:100-113: nested farthest-point subsets
+                            dense = self.denses[layer][scale][0][inp_scale]
+                            if scale > inp_scale:  # the coarse points' own rows of the finer features
+                                for i in range(inp_scale, scale):
+                                    f = f[idx[i + 1][0].long()]
+                                a = a + dense(f)
+                            else:  # coarse features added onto the fine points they were sampled from
+                                ind = idx[scale + 1][0].long()
+                                for i in range(scale + 1, inp_scale):
+                                    ind = ind[idx[i + 1][0].long()]
+                                a = a.index_add(0, ind, dense(f))
                         inp.append(a)
                     if self.add_merge:
                         s = inp[0]

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DMCF_B200_VERSION 102
+#define DMCF_B200_VERSION 103
 
 enum dmcf_status {
     DMCF_OK = 0,
@@ -201,6 +201,35 @@ int dmcf_grid_pos_mark(const float* pos, int64_t n, const float* voxel_host3, co
                        const int32_t* lo_host3, const int32_t* dims_host3, int32_t* flags, void* stream);
 int dmcf_grid_pos_emit(const int32_t* flags, const int32_t* offsets, const float* voxel_host3, const float* center_host3,
                        const int32_t* lo_host3, const int32_t* dims_host3, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Point-set ops of the reference's in-repo CUDA extensions.
+ *
+ * dmcf_farthest_point_sample  replaces op FarthestPointSample (utils/tools/sampling.cpp:49-61,115-148, kernel
+ *   utils/tools/sampling.cu:125-190; called at utils/tools/losses.py:241, 277-279).  points [b,n,3] -> idx_out [b,m]
+ *   int32, first index 0, then repeatedly the point farthest from the chosen set; float32 distance
+ *   fma(dz,dz, fma(dx,dx, dy*dy)) and the reference kernel's tie order (smaller k mod 512, then smaller k).
+ *   temp [b,n] floats of scratch.  cluster_size: CTAs per batch item (thread-block cluster), 0 = choose, else 1/2/4/8.
+ * dmcf_approx_match  replaces op ApproxMatch (utils/tools/tf_approxmatch.cpp:33-38, kernels tf_approxmatch.cu:27-160,
+ *   CPU twin tf_approxmatch.cpp:51-112; called at utils/tools/losses.py:406, 413) for ONE batch item with n points in
+ *   xyz1 and m in xyz2 (the reference's per-item counts n[i], m[i]: pass those counts and the row stride of the padded
+ *   matrix).  match [m][match_ld] (match[l*match_ld + k], like the reference's [b, m, n] layout) may be NULL;
+ *   cost_out (one float, may be NULL) receives sum_kl |x1_k - x2_l| match[l][k] (= op MatchCost) accumulated on the
+ *   fly, so the EMD metric never needs the n x m matrix.  first_level: the annealing starts at exp(-4^first_level d^2):
+ *   7 = the reference's CUDA kernel (tf_approxmatch.cu:47), 8 = its CPU kernel (tf_approxmatch.cpp:59).
+ * dmcf_match_cost  replaces op MatchCost (tf_approxmatch.cpp:39-43,177-196; losses.py:407) for one batch item.
+ * dmcf_nn_distance replaces one direction of op NnDistance (utils/tools/nn_distance.cpp:29-35,47-70): for every point of
+ *   xyz1 the squared distance to / index of its nearest point in xyz2 ((x*x + y*y) + z*z uncontracted, first minimum).
+ * ------------------------------------------------------------------------------------------------- */
+int dmcf_farthest_point_sample(const float* points, int32_t b, int32_t n, int32_t m, float* temp, int32_t* idx_out,
+                               int32_t cluster_size, void* stream);
+size_t dmcf_approx_match_workspace_bytes(int32_t n, int32_t m);
+int dmcf_approx_match(const float* xyz1, int32_t n, const float* xyz2, int32_t m, int32_t first_level, float* match,
+                      int64_t match_ld, float* cost_out, void* workspace, size_t workspace_bytes, void* stream);
+size_t dmcf_match_cost_workspace_bytes(int32_t n, int32_t m);
+int dmcf_match_cost(const float* xyz1, int32_t n, const float* xyz2, int32_t m, const float* match, int64_t match_ld,
+                    float* cost_out, void* workspace, size_t workspace_bytes, void* stream);
+int dmcf_nn_distance(const float* xyz1, int32_t n, const float* xyz2, int32_t m, float* dist, int32_t* idx, void* stream);
 
 #ifdef __cplusplus
 }

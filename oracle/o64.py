@@ -376,17 +376,22 @@ def grid_pos(pos, voxel_size, centralize=False, pad=0, hyst=0.1):
     return (gpos.astype(F32) * v + v / F32(2)).astype(F32)
 
 
-def get_dilated_pos(pos, strides, voxel_size=None, centralize=False, pad=0, hyst=0.1):
-    """utils/tools/losses.py:249-284, voxel mode only (FPS mode needs the in-repo CUDA op)."""
-    out = []
+def get_dilated_pos(pos, strides, voxel_size=None, centralize=False, pad=0, hyst=0.1, return_idx=False):
+    """utils/tools/losses.py:249-284: voxel lattices, or (voxel_size None) nested farthest-point subsets of
+    N // stride points taken from the previous scale (:274-282); idx[s] = indices of scale s inside scale s-1."""
+    out, idx = [], []
     for s in strides:
         if s == 1:
             out.append(np.asarray(pos, F32))
+            idx.append(None)
+        elif voxel_size is None:
+            from . import pointset
+            cnt = max(len(pos) // int(s), 1)
+            idx.append(pointset.farthest_point_sample(cnt, out[-1]))
+            out.append(out[-1][idx[-1]])
         else:
-            if voxel_size is None:
-                raise NotImplementedError("FPS sub-sampling (voxel_size: null) is out of scope")
             out.append(grid_pos(pos, np.asarray(voxel_size, F32) * F32(s), centralize, pad, hyst))
-    return out
+    return (out, idx) if return_idx else out
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -517,8 +522,8 @@ class ModelO64:
             feats = np.concatenate([ans_conv, ans_obs, ans_adv, ans_dense, ans_dens_adv], axis=1)
         else:
             feats = np.concatenate([ans_conv, ans_obs, ans_dense], axis=1)
-        dil = get_dilated_pos(all_pos if c["use_bnds"] else pos2_32, c["strides"], c["voxel_size"],
-                              c["centralize"], c["sample_pad"], c["sample_hyst"])  # :413-419
+        dil, self.fps_idx = get_dilated_pos(all_pos if c["use_bnds"] else pos2_32, c["strides"], c["voxel_size"],
+                                            c["centralize"], c["sample_pad"], c["sample_hyst"], return_idx=True)  # :413-419
         self.dilated_pos = dil
         self.dens = None
         if c["dens_norm"]:  # :421-435 (the radius is passed as the sampling extent)
@@ -553,7 +558,7 @@ class ModelO64:
             pos_new = pos_new - np.asarray(tr["translate"])
         return pos_new, vel_new
 
-    # -- models/hrnet.py:69-133 (voxel mode, k == 0 convs only, no dens_norm) --------------------------------
+    # -- models/hrnet.py:69-133 (k == 0 convs only) --------------------------------
     def _forward_hrnet(self, pos, feats, ext, n_f):
         c = self.c
         lc = c["layer_channels"]
@@ -583,6 +588,18 @@ class ModelO64:
                         a = a + self._dense("denses/%d/%d/0/%d" % (i - 1, j, l), fe)
                         if a.shape[1] == ans_convs[-1][j].shape[1]:
                             a = a + ans_convs[-1][j]
+                    elif c["voxel_size"] is None:  # models/hrnet.py:100-113: nested farthest-point subsets
+                        key_d = "denses/%d/%d/0/%d" % (i - 1, j, l)
+                        if j > l:
+                            for t in range(l, j):
+                                fe = fe[self.fps_idx[t + 1]]
+                            a = a + self._dense(key_d, fe)
+                        else:
+                            ind = self.fps_idx[j + 1]
+                            for t in range(j + 1, l):
+                                ind = ind[self.fps_idx[t + 1]]
+                            a = a.copy()
+                            np.add.at(a, ind, self._dense(key_d, fe))
                     inp.append(a)
                 ans.append(sum(inp) if c["add_merge"] else np.concatenate(inp, axis=1))
             ans_convs.append(ans)

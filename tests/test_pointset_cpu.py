@@ -1,0 +1,141 @@
+"""CPU suite for the point-set ops: the NumPy restatements in oracle/pointset.py against the
+reference's OWN CPU functions compiled from the reference checkout (oracle/_ref/libdmcf_refops.so: approxmatch_cpu,
+approxmatch_cpu_dyn, matchcost_cpu of utils/tools/tf_approxmatch.cpp and nnsearch of utils/tools/nn_distance.cpp), and
+the farthest-point restatement against a literal emulation of the reference kernel's thread structure."""
+import numpy as np
+import pytest
+
+from oracle import pointset as ps
+
+needs_ref = pytest.mark.skipif(not ps.ref_available(), reason="oracle/_ref not built (needs the reference checkout)")
+
+
+def _sets(n, m, scale, seed, dim=3):
+    rng = np.random.default_rng(seed)
+    a = (rng.random((n, 3)) * scale).astype(np.float32)
+    b = (rng.random((m, 3)) * scale).astype(np.float32)
+    if dim == 2:
+        a[:, 2] = 0
+        b[:, 2] = 0
+    return a, b
+
+
+@needs_ref
+@pytest.mark.parametrize("n,m,scale,dim", [(200, 200, 1.0, 3), (300, 150, 0.3, 3), (100, 250, 0.05, 3), (64, 64, 0.02, 2),
+                                           (1, 7, 0.1, 3), (5, 1, 0.1, 3)])
+def test_approx_match_restatement_matches_reference_cpu_code(n, m, scale, dim):
+    a, b = _sets(n, m, scale, 1, dim)
+    ref = ps.ref_approx_match(a[None], b[None])[0]
+    got = ps.approx_match(a, b, first_level=8)  # the CPU kernel's schedule (tf_approxmatch.cpp:59)
+    # same scheme, 1e-9 guards placed differently (tf_approxmatch.cu:84,118 vs tf_approxmatch.cpp:73-79)
+    assert np.abs(got - ref).max() <= 5e-3
+    c_ref = float(ps.ref_match_cost(a[None], b[None], ref[None])[0])
+    assert abs(ps.match_cost(a, b, got) - c_ref) <= 1e-4 * c_ref + 1e-7
+    assert abs(ps.match_cost(a, b, ref) - c_ref) <= 1e-5 * c_ref + 1e-7  # match_cost restatement on the same matrix
+    # capacities: a point of the smaller set may be matched max/min (integer division) times, one of the larger once;
+    # the total matched mass is the smaller of the two total capacities
+    fl, fr = max(n, m) // n, max(n, m) // m
+    assert ref.sum(0).max() <= fl + 1e-4 and ref.sum(1).max() <= fr + 1e-4
+    assert abs(ref.sum() - min(n * fl, m * fr)) <= 1e-3 * max(n, m)
+
+
+@needs_ref
+def test_approx_match_dyn_counts_reference():
+    a, b = _sets(40, 60, 0.2, 2)
+    cn, cm = 33, 47
+    ref = ps.ref_approx_match_dyn(a[None], b[None], [cn], [cm])[0]
+    assert np.all(ref[cm:] == 0) and np.all(ref[:, cn:] == 0)
+    got = ps.approx_match(a[:cn], b[:cm], first_level=8)
+    assert np.abs(got - ref[:cm, :cn]).max() <= 5e-3
+
+
+def test_reference_cpu_and_cuda_schedules_differ_on_small_scenes():
+    """The reference's CPU op anneals from exp(-4^8 d^2), its CUDA op from exp(-4^7 d^2): on scenes with particle
+    spacings below ~0.01 (WBC-SPH: 0.005) the two give different matches.  dmcf_b200 follows the CUDA op by default."""
+    a, b = _sets(64, 64, 0.02, 3)
+    assert np.abs(ps.approx_match(a, b, 8) - ps.approx_match(a, b, 7)).max() > 0.05
+    a, b = _sets(64, 64, 2.0, 3)
+    assert np.abs(ps.approx_match(a, b, 8) - ps.approx_match(a, b, 7)).max() < 1e-3
+
+
+@needs_ref
+@pytest.mark.parametrize("n,m", [(300, 200), (1, 5), (50, 1)])
+def test_nn_search_bit_exact_vs_reference(n, m):
+    a, b = _sets(n, m, 1.0, 4)
+    b[m // 2] = b[0]  # an exact tie: the first minimum wins
+    d_ref, i_ref = ps.ref_nn_search(a[None], b[None])
+    d, i = ps.nn_search(a, b)
+    assert np.array_equal(i, i_ref[0]) and np.array_equal(d, d_ref[0])
+
+
+def _fps_literal(points, m, threads=512):
+    """utils/tools/sampling.cu:125-190 thread by thread (strided scan per thread, then the pairwise tree)."""
+    pts = np.asarray(points, np.float32)
+    n = len(pts)
+    temp = np.full(n, 1e38, np.float32)
+    out = [0]
+    old = 0
+    for _ in range(1, m):
+        d2 = np.minimum(ps.fps_dist2(pts, pts[old]), temp)
+        temp = d2
+        best = np.full(threads, -1.0, np.float32)
+        besti = np.zeros(threads, np.int64)
+        for t in range(min(threads, n)):
+            ks = np.arange(t, n, threads)
+            j = int(np.argmax(d2[ks]))  # first maximum = the strict '>' of the scan
+            best[t], besti[t] = d2[ks][j], ks[j]
+        u = 0
+        while (1 << u) < threads:
+            for t in range(threads >> (u + 1)):
+                i1, i2 = (t * 2) << u, (t * 2 + 1) << u
+                if best[i1] < best[i2]:
+                    best[i1], besti[i1] = best[i2], besti[i2]
+            u += 1
+        old = int(besti[0])
+        out.append(old)
+    return np.asarray(out, np.int32)
+
+
+def test_fps_restatement_definition_and_tie_order():
+    rng = np.random.default_rng(5)
+    pts = rng.random((700, 3)).astype(np.float32)
+    idx = ps.farthest_point_sample(60, pts)
+    assert idx[0] == 0 and len(set(idx.tolist())) == 60
+    chosen = [0]
+    for j in range(1, 60):  # each new point maximises the distance to the chosen set
+        d = np.min(np.stack([ps.fps_dist2(pts, pts[c]) for c in chosen]), axis=0)
+        assert d[idx[j]] == d.max()
+        chosen.append(int(idx[j]))
+    assert np.array_equal(idx, _fps_literal(pts, 60))
+    # an exact lattice is full of ties: the order must be the kernel's (k mod 512, then k)
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(11), np.arange(10), indexing="ij"), -1).reshape(-1, 3)
+    lat = (g * 0.25).astype(np.float32)
+    assert np.array_equal(ps.farthest_point_sample(40, lat), _fps_literal(lat, 40))
+
+
+def fps_cfg():
+    return dict(name="SymNet", layer_channels=[[[4]], [[8], [4], [4]], [[8]], [[3]]], kernel_size=[4, 4, 4],
+                sym_kernel_size=[6, 6, 6], coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear",
+                window="poly6", window_sym="peak", strides=[1, 2, 4], particle_radii=[0.1, 0.2, 0.4], timestep=0.02,
+                grav=-9.81, out_scale=[0.0078125] * 3, voxel_size=None, sym_axis=1, add_merge=True, use_acc=False)
+
+
+def test_o64_model_with_farthest_point_scales():
+    """voxel_size: null -> nested farthest-point subsets (utils/tools/losses.py:274-282) and the cross-scale Dense
+    gather / scatter (models/hrnet.py:100-113) in the float64 oracle model."""
+    from oracle import o64
+    from dmcf_b200 import config, scenes
+    from test_models_gpu import oracle_weights
+    model = config.build_model(fps_cfg())
+    assert model.fused is False  # farthest-point scales run on the layer-by-layer path
+    model.init_weights(seed=0, device="cpu", scale=0.1)
+    w = oracle_weights(model)
+    assert "denses/0/1/0/0/kernel" in w and "denses/1/0/0/2/kernel" in w  # the cross-scale Dense layers exist in this mode
+    scene = scenes.lattice_scene((5, 5, 4), dx=0.05, seed=2, open_top=True)
+    m = o64.ModelO64(fps_cfg(), w)
+    pos, vel = m(scene["pos"], scene["vel"], None, scene["box"], scene["box_normals"])
+    n_all = scene["pos"].shape[0] + scene["box"].shape[0]
+    assert np.isfinite(pos).all()
+    assert [d.shape[0] for d in m.dilated_pos] == [n_all, n_all // 2, n_all // 4]
+    assert np.array_equal(m.dilated_pos[2], m.dilated_pos[1][m.fps_idx[2]])  # nested subsets
+    assert np.abs(m.net_out.sum(0)).max() <= 1e-9 * np.abs(m.net_out).sum() + 1e-12  # momentum is still conserved

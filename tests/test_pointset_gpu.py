@@ -1,0 +1,215 @@
+"""GPU parity of the point-set ops through the C ABI: farthest-point sampling (bit-exact indices
+against the restated reference kernel), approx-match / match-cost / EMD (against the reference's own CPU code in
+oracle/_ref and the float64 restatement), nn-distance (bit-exact against the reference's nnsearch), and a model step
+with farthest-point multi-scale sampling against the float64 oracle model."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import o64
+from oracle import pointset as ps
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def _sets(n, m, scale, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.random((n, 3)) * scale).astype(np.float32), (rng.random((m, 3)) * scale).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# farthest-point sampling
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cluster", [0, 1, 2, 4, 8])
+def test_fps_indices_bit_exact(cuda, cluster):
+    from dmcf_b200 import pointops
+    rng = np.random.default_rng(7)
+    pts = rng.random((3, 5000, 3)).astype(np.float32)
+    pts[1] *= 0.01  # WBC-SPH sized coordinates
+    pts[2, :, 2] = 0.0  # 2-D data padded to 3-D
+    got = pointops.farthest_point_sample(300, _t(pts, cuda), cluster_size=cluster).cpu().numpy()
+    assert got.dtype == np.int32 and got.shape == (3, 300)
+    for b in range(3):
+        assert np.array_equal(got[b], ps.farthest_point_sample(300, pts[b])), f"batch item {b}"
+
+
+def test_fps_tie_order_on_exact_lattice(cuda):
+    from dmcf_b200 import pointops
+    g = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(16), indexing="ij"), -1).reshape(-1, 3)
+    lat = (g * 0.25).astype(np.float32)
+    want = ps.farthest_point_sample(64, lat)
+    for cluster in (1, 8):
+        got = pointops.farthest_point_sample(64, _t(lat[None], cuda), cluster_size=cluster).cpu().numpy()[0]
+        assert np.array_equal(got, want)
+
+
+def test_fps_edge_cases_and_large_slices(cuda):
+    from dmcf_b200 import pointops
+    rng = np.random.default_rng(8)
+    one = _t(rng.random((1, 1, 3)).astype(np.float32), cuda)
+    assert pointops.farthest_point_sample(1, one).cpu().tolist() == [[0]]
+    assert pointops.farthest_point_sample(0, one).shape == (1, 0)
+    pts = rng.random((1, 37, 3)).astype(np.float32)
+    full = pointops.farthest_point_sample(37, _t(pts, cuda), cluster_size=8).cpu().numpy()[0]  # m == n, CTAs without points
+    assert sorted(full.tolist()) == list(range(37)) and np.array_equal(full, ps.farthest_point_sample(37, pts[0]))
+    # one CTA, slice larger than its shared-memory cache (12 800 points): the global-memory tail
+    big = rng.random((1, 20000, 3)).astype(np.float32)
+    got = pointops.farthest_point_sample(40, _t(big, cuda), cluster_size=1).cpu().numpy()[0]
+    assert np.array_equal(got, ps.farthest_point_sample(40, big[0]))
+    with pytest.raises(ValueError):
+        pointops.farthest_point_sample(38, _t(pts, cuda))
+    with pytest.raises(Exception):
+        pointops.farthest_point_sample(3, torch.from_numpy(pts))  # CPU tensor: no fallback
+
+
+def test_fps_coverage_property_at_scale(cuda):
+    """200 k points, 2 000 samples: the covering radius of the sample equals the last selection distance, and every
+    sample is at least that far from every other one (the defining property of farthest-point sampling)."""
+    from dmcf_b200 import pointops
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    pts = torch.rand((1, 200000, 3), generator=gen).to(cuda)
+    idx = pointops.farthest_point_sample(2000, pts).long()[0]
+    assert idx[0] == 0 and torch.unique(idx).numel() == 2000
+    sel = pts[0][idx]
+    d_all = torch.cdist(pts[0], sel).min(dim=1).values  # distance of every point to the sample
+    d_sel = torch.cdist(sel, sel) + torch.eye(2000, device=cuda) * 10
+    assert d_sel.min() >= d_all.max() * (1 - 1e-5)
+
+
+def test_gather_point(cuda):
+    from dmcf_b200 import pointops
+    rng = np.random.default_rng(9)
+    inp = rng.random((2, 50, 3)).astype(np.float32)
+    idx = rng.integers(0, 50, (2, 17)).astype(np.int32)
+    got = pointops.gather_point(_t(inp, cuda), _t(idx, cuda)).cpu().numpy()
+    assert np.array_equal(got, np.stack([inp[b][idx[b]] for b in range(2)]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# approx-match / match-cost / EMD
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m,scale", [(200, 200, 1.0), (300, 150, 0.3), (100, 250, 0.05), (1500, 1100, 0.5), (1, 9, 0.1)])
+def test_approx_match_vs_restatement_and_reference_cpu(cuda, n, m, scale):
+    from dmcf_b200 import pointops
+    a, b = _sets(n, m, scale, 11)
+    ta, tb = _t(a[None], cuda), _t(b[None], cuda)
+    # the reference's CUDA schedule (levels 7..-2) against the float64 restatement of that kernel
+    got7 = pointops.approx_match(ta, tb).cpu().numpy()[0]
+    assert got7.shape == (m, n)
+    want7 = ps.approx_match(a, b, first_level=7)
+    assert np.abs(got7 - want7).max() <= 5e-4, np.abs(got7 - want7).max()  # float32 sums + ex2.approx vs float64
+    # the reference's CPU schedule (levels 8..-2) against the reference's own approxmatch_cpu
+    got8 = pointops.approx_match(ta, tb, first_level=8).cpu().numpy()[0]
+    if ps.ref_available():
+        ref = ps.ref_approx_match(a[None], b[None])[0]
+        assert np.abs(got8 - ref).max() <= 5e-3  # guard placement differs between the reference's two kernels
+        c_ref = float(ps.ref_match_cost(a[None], b[None], ref[None])[0])
+        c_got = float(pointops.match_cost(ta, tb, _t(got8[None], cuda))[0])
+        assert abs(c_got - c_ref) <= 2e-4 * c_ref + 1e-7
+        # match_cost on the SAME matrix: only summation order differs
+        c_same = float(pointops.match_cost(ta, tb, _t(ref[None], cuda))[0])
+        assert abs(c_same - c_ref) <= 2e-6 * c_ref + 1e-8
+    # fused EMD == match_cost(approx_match)
+    c_two = float(pointops.match_cost(ta, tb, _t(got7[None], cuda))[0])
+    c_fused = float(pointops.emd_cost(ta, tb)[0])
+    assert abs(c_fused - c_two) <= 2e-5 * c_two + 1e-8
+    assert abs(c_two - ps.match_cost(a, b, want7)) <= 2e-4 * c_two + 1e-7
+    e = float(pointops.emd_loss(ta, tb)[0])
+    assert abs(e - c_fused / max(n, m)) <= 1e-6 * abs(e) + 1e-12
+    e2 = float(pointops.emd_loss(ta, tb, fused=False)[0])
+    assert abs(e - e2) <= 2e-5 * abs(e) + 1e-12
+
+
+def test_approx_match_batch_and_dyn_counts(cuda):
+    from dmcf_b200 import pointops
+    rng = np.random.default_rng(12)
+    a = (rng.random((2, 40, 3)) * 0.2).astype(np.float32)
+    b = (rng.random((2, 60, 3)) * 0.2).astype(np.float32)
+    cn, cm = [33, 40], [47, 12]
+    got = pointops.approx_match(_t(a, cuda), _t(b, cuda), torch.tensor(cn), torch.tensor(cm), first_level=8).cpu().numpy()
+    assert got.shape == (2, 60, 40)
+    for i in range(2):
+        assert np.all(got[i, cm[i]:] == 0) and np.all(got[i, :, cn[i]:] == 0)
+        want = ps.approx_match(a[i, :cn[i]], b[i, :cm[i]], first_level=8)
+        assert np.abs(got[i, :cm[i], :cn[i]] - want).max() <= 5e-4
+    if ps.ref_available():
+        ref = ps.ref_approx_match_dyn(a, b, cn, cm)
+        assert np.abs(got - ref).max() <= 5e-3
+    e = pointops.emd_loss(_t(a, cuda), _t(b, cuda), cn, cm).cpu().numpy()
+    for i in range(2):
+        want = ps.emd_loss(a[i, :cn[i]], b[i, :cm[i]])
+        assert abs(e[i] - want) <= 2e-4 * want + 1e-9
+
+
+def test_approx_vel(cuda):
+    from dmcf_b200 import pointops
+    a, b = _sets(120, 120, 0.3, 13)
+    got = pointops.approx_vel(_t(a[None], cuda), _t(b[None], cuda)).cpu().numpy()[0]
+    mt = ps.approx_match(a, b, 7)  # [m, n]
+    want = (mt[:, :, None] * (b[:, None, :].astype(np.float64) - a[None, :, :])).sum(0)
+    assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max() + 1e-6
+
+
+def test_emd_properties_at_scale(cuda):
+    """10 000 x 10 000 (a WBC-SPH sized frame, mean spacing 0.005): capacities are respected, the soft assignment of
+    identical sets costs about one particle spacing (it never collapses to the identity), a rigid shift by s >> spacing
+    costs about s per point, and the fused cost agrees with the two-op form."""
+    from dmcf_b200 import pointops
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    a = (torch.rand((1, 10000, 3), generator=gen) * torch.tensor([0.5, 0.5, 0.0])).to(cuda)
+    match = pointops.approx_match(a, a)
+    assert float((match.sum(1) - 1).abs().max()) <= 1e-3 and float((match.sum(2) - 1).abs().max()) <= 1e-3
+    same = float(pointops.emd_loss(a, a)[0])
+    assert 0.002 <= same <= 0.012  # float64 restatement on a 2 000-point sample of the same density: 0.0065
+    shift = 0.05
+    b = a + torch.tensor([shift, 0.0, 0.0], device=cuda)
+    moved = float(pointops.emd_loss(a, b)[0])
+    assert shift * 0.9 <= moved <= shift * 1.4  # restatement at 2 000 points: 0.058
+    two = float(pointops.emd_loss(a, b, fused=False)[0])
+    assert abs(two - moved) <= 1e-4 * moved
+
+
+def test_nn_distance_bit_exact(cuda):
+    from dmcf_b200 import pointops
+    a, b = _sets(3000, 2100, 1.0, 14)
+    b[1000] = b[3]  # exact tie: first minimum
+    d1, i1, d2, i2 = (x.cpu().numpy() for x in pointops.nn_distance(_t(a[None], cuda), _t(b[None], cuda)))
+    if ps.ref_available():
+        rd1, ri1 = ps.ref_nn_search(a[None], b[None])
+        rd2, ri2 = ps.ref_nn_search(b[None], a[None])
+    else:
+        rd1, ri1 = (x[None] for x in ps.nn_search(a, b))
+        rd2, ri2 = (x[None] for x in ps.nn_search(b, a))
+    assert np.array_equal(i1, ri1) and np.array_equal(d1, rd1)
+    assert np.array_equal(i2, ri2) and np.array_equal(d2, rd2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# model step with farthest-point multi-scale sampling (voxel_size: null)
+# ---------------------------------------------------------------------------------------------------------
+def test_model_step_with_farthest_point_scales(cuda):
+    from dmcf_b200 import config, scenes
+    from test_models_gpu import oracle_weights
+    from test_pointset_cpu import fps_cfg
+    cfg = fps_cfg()
+    scene = scenes.lattice_scene((9, 8, 7), dx=0.05, seed=5, open_top=True)
+    model = config.build_model(cfg)
+    assert model.fused is False
+    model.init_weights(seed=1, device=cuda, scale=0.1)
+    t = lambda a: _t(np.asarray(a, np.float32), cuda)
+    data = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
+    pos_u, vel_u = model(data)
+    ref = o64.ModelO64(cfg, oracle_weights(model))
+    pos_r, vel_r = ref(scene["pos"], scene["vel"], None, scene["box"], scene["box_normals"])
+    for s in (1, 2):  # the sampled subsets are the oracle's, index for index
+        assert np.array_equal(model.dilated_pos[s].cpu().numpy(), ref.dilated_pos[s])
+    n_f = scene["pos"].shape[0]
+    net = model.net_out.cpu().numpy()
+    scale = np.abs(ref.net_out).max()
+    tol = (2e-5 * scale + 1e-6) * 8
+    assert np.abs(net[:n_f] - ref.net_out[:n_f]).max() <= tol
+    assert np.abs(pos_u.cpu().numpy() - pos_r).max() <= tol * 0.0078125 + 4e-7 * max(np.abs(pos_r).max(), 1.0)
