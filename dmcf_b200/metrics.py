@@ -1,8 +1,8 @@
 """Validation metrics of the reference's ``run_valid`` / ``run_test`` (pipelines/simulator.py:216-263), SURVEY 8f rank 2:
 ``distance`` / ``chamfer_distance`` / ``compute_stats`` / ``compare_dist`` / ``merge_dicts`` (utils/evaluation_helper.py:14-90,
 host-side NumPy/SciPy exactly like the reference) and ``density_loss`` (utils/tools/losses.py:380-398, on the GPU through
-``compute_density`` = fixed-radius search + window).  The EMD metric needs the approx-match CUDA op and is
-not provided."""
+``compute_density`` = fixed-radius search + window) and the EMD metric (``emd_loss``, utils/tools/losses.py:401-408, on the
+GPU through the approx-match kernels of dmcf_b200/pointops.py)."""
 from __future__ import annotations
 
 import numpy as np
@@ -75,7 +75,7 @@ def density_loss(gt, pred, gt_in=None, pred_in=None, radius=0.005, eps=0.01, win
     return torch.relu(pred_dens - rest_dens - eps).mean()
 
 
-def rollout_metrics(pos, vel, target_pos, target_vel, box, model=None, split="valid"):
+def rollout_metrics(pos, vel, target_pos, target_vel, box, model=None, split="valid", emd=True):
     """The per-frame metric dict of run_valid (pipelines/simulator.py:216-250) for one predicted frame."""
     dev = pos.device if isinstance(pos, torch.Tensor) else "cuda"
     t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
@@ -92,6 +92,9 @@ def rollout_metrics(pos, vel, target_pos, target_vel, box, model=None, split="va
                                                       torch.cat([target_pos, box], 0), radius=model.particle_radii[0],
                                                       win=get_window_func(model.window_dens), use_max=True))
         loss["chamfer_val_2"] = float(np.mean(chamfer_distance(pos, target_pos).astype(np.float32)))
+        if emd and pos.shape[0] > 0 and target_pos.shape[0] > 0:  # pipelines/simulator.py:247-249
+            from .pointops import emd_loss
+            loss["emd"] = float(emd_loss(target_pos.unsqueeze(0), pos.unsqueeze(0)).mean())
         loss["vel_diff_val"] = float(compare_dist(target_vel, vel))
         loss["vel_diff_val_2"] = float(compare_dist(vel, target_vel))
     return loss

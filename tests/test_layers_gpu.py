@@ -243,4 +243,8 @@ def test_density_loss_and_rollout_metrics(cuda):
     assert abs(got_max - abs(d1.max() - d2.max()) / d2.max()) <= 1e-5
     vel = rng.standard_normal(gt.shape).astype(np.float32)
     m = metrics.rollout_metrics(t(pred), t(vel), t(gt), t(vel * 1.1), t(box), split="valid")
-    assert set(m) >= {"mse_val", "chamfer_val", "dens_val", "chamfer_val_2", "vel_diff_val"} and all(np.isfinite(v) for v in m.values())
+    assert set(m) >= {"mse_val", "chamfer_val", "dens_val", "chamfer_val_2", "vel_diff_val", "emd"} and all(np.isfinite(v) for v in m.values())
+    from oracle import pointset
+    clipped = np.clip(pred, box.min(0), box.max(0))  # run_valid clamps the prediction into the box (pipelines/simulator.py:218-219)
+    want = pointset.emd_loss(gt, clipped)
+    assert abs(m["emd"] - want) <= 5e-4 * want
