@@ -166,6 +166,37 @@ def conv_algorithmic_bytes(rec):
     return b
 
 
+def hbm_op_breakdown(recs, step_ms_total, peak):
+    """The HBM-bound ops around the convs (cell list, neighbour search, pair geometry): live CUDA-event time per launch in
+    the timed region against their algorithmic bytes (B_frs = 12 (N_in + N_out) + 4 P + 8 (N_out + 1); cell list
+    12 N read + 20 N written + 4 per cell; pair geometry 4 P + 12 (N_in + N_out) + 8 (N_out + 1) read, 36 P written)."""
+    def nbytes(r):
+        if r["kind"] == "cell_list":
+            return 32 * r["n_points"] + 4 * r["n_cells"]
+        if r["kind"] == "frs_count":
+            return 12 * (r["n_points"] + r["n_queries"]) + 4 * r["n_queries"] + 8 * (r["n_queries"] + 1)
+        if r["kind"] == "frs_fill":
+            return 12 * (r["n_points"] + r["n_queries"]) + (8 if r["distances"] else 4) * r["pairs"] + 8 * (r["n_queries"] + 1)
+        if r["kind"] == "pair_records":
+            return 40 * r["pairs"] + 12 * (r["n_inp"] + r["n_out"]) + 8 * (r["n_out"] + 1)
+        return 0
+    names = {"cell_list": "dmcf_grid_build (k_cell_hist/scan/scatter/sort/gather_pos)", "frs_count": "k_frs<count> + row_splits scan",
+             "frs_fill": "k_frs<fill>", "pair_records": "k_cconv_prepare"}
+    groups = {}
+    for r in recs:
+        g = groups.setdefault(r["kind"], {"ms": 0.0, "n": 0, "bytes": 0})
+        g["ms"] += r["start"].elapsed_time(r["end"])
+        g["n"] += 1
+        g["bytes"] += nbytes(r)
+    out = []
+    for kind, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+        gbps = g["bytes"] / 1e9 / (g["ms"] * 1e-3) if g["ms"] > 0 else 0.0
+        out.append({"kernel": names.get(kind, kind), "launches": g["n"], "avg_ms": round(g["ms"] / g["n"], 4),
+                    "share_of_step": round(g["ms"] / step_ms_total, 4), "algorithmic_GB_per_launch": round(g["bytes"] / g["n"] / 1e9, 4),
+                    "GBps": round(gbps, 1), "frac_of_hbm_peak": round(gbps / peak, 4)})
+    return out
+
+
 def conv_flops(rec):
     """P(F_map + 16 Cin) + 2 N_out K Cin Cout."""
     return rec["pairs"] * (60 + 16 * rec["cin"]) + 2 * rec["n_out"] * rec["rows"] * rec["cout"]
@@ -257,6 +288,8 @@ def main():
 
     # ---- roofline of the dominant kernel (live CUDA events around each conv launch in the timed region) -------
     groups = {}
+    hbm_ops = [rec for rec in prof if "kind" in rec]
+    prof = [rec for rec in prof if "kind" not in rec]
     for rec in prof:
         k = (rec["kernel_size"], rec["cin"], rec["cout"], rec["ascc"])
         g = groups.setdefault(k, {"ms": 0.0, "n": 0, "rec": rec})
@@ -279,6 +312,8 @@ def main():
                     "fp32_tflops": top["fp32_TFLOPs"], "fp32_simt_peak_tflops": 74.0,
                     "note": "wide CConv layers are fp32-FLOP bound (SURVEY 8d): HBM fraction reported as BASELINE asks, "
                             "fp32 TFLOP/s beside it"}
+
+    hbm_kernels = hbm_op_breakdown(hbm_ops, ms, peak)
 
     # ---- end-to-end arm: host buffers in, host buffers out, copies inside the timed region ----------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory()
@@ -331,6 +366,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": copy_bytes, "d2h_bytes_per_step": copy_bytes,
                     "steps": e2e_steps, "api": "Simulator.step on pinned host pos/vel, results copied back to pinned host"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": breakdown,
+            "hbm_kernels": hbm_kernels,
             "cpu_baseline": cpu, "finite": ok,
         }
         sys.stdout.flush()

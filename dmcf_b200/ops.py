@@ -31,6 +31,21 @@ MAX_CELLS = 1 << 24
 PROFILE = None
 
 
+def _prof_begin(kind, **meta):
+    """bench.py's per-op timing hook for the HBM-bound ops around the convs (record has a ``kind`` key; conv records do not)."""
+    if PROFILE is None:
+        return None
+    rec = dict(kind=kind, start=torch.cuda.Event(enable_timing=True), end=torch.cuda.Event(enable_timing=True), **meta)
+    rec["start"].record()
+    return rec
+
+
+def _prof_end(rec):
+    if rec is not None:
+        rec["end"].record()
+        PROFILE.append(rec)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -112,7 +127,9 @@ class CellList:
         self.grid = g
         ws_bytes = lib.dmcf_grid_workspace_bytes(n, self.n_cells)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rec = _prof_begin("cell_list", n_points=n, n_cells=self.n_cells)
         check(lib.dmcf_grid_build(_p(points), C.byref(g), _p(ws), ws_bytes, _stream()))
+        _prof_end(rec)
 
 
 def exclusive_scan(counts, out_dtype=torch.int64):
@@ -150,16 +167,22 @@ def fixed_radius_search(points, queries, radius, ignore_query_point=False, retur
     points = _pos(points, "points")
     queries = _pos(queries, "queries")
     radius = float(radius)
+    if cell_list is None:  # built (and profiled) on its own
+        cell_list = CellList(points, max(radius, 1e-30))
+    rec = _prof_begin("frs_count", n_points=points.shape[0], n_queries=queries.shape[0])
     counts, cell_list = neighbor_counts(points, queries, radius, ignore_query_point, cell_list)
     row_splits = exclusive_scan(counts, torch.int64)
+    _prof_end(rec)
     nq = queries.shape[0]
     total = int(row_splits[-1].item())  # data-dependent output size: the one host sync of the op
     index = torch.empty(total, dtype=torch.int32, device=queries.device)
     dist = torch.empty(total if return_distances else 0, dtype=torch.float32, device=queries.device)
     if total > 0:
+        rec = _prof_begin("frs_fill", n_points=points.shape[0], n_queries=nq, pairs=total, distances=bool(return_distances))
         check(lib.dmcf_frs_fill(C.byref(cell_list.grid), _p(queries), nq, radius, int(bool(ignore_query_point)),
                                 _p(row_splits), total, _p(index), _p(dist) if return_distances else None, None,
                                 _stream()))
+        _prof_end(rec)
     return NeighborSearchResult(index, row_splits, dist)
 
 
@@ -366,9 +389,11 @@ def prepare_pair_records(kernel_size, out_positions, extents, offset, inp_positi
     d.nbr_lo, d.nbr_hi = (0, 0) if nbr_range is None else (int(nbr_range[0]), int(nbr_range[1]))
     n_pairs = int(neighbors_index.shape[0])
     records = torch.empty((9, n_pairs), dtype=torch.float32, device=out_positions.device)
+    rec = _prof_begin("pair_records", n_inp=inp_positions.shape[0], n_out=out_positions.shape[0], pairs=n_pairs)
     check(lib.dmcf_cconv_prepare(C.byref(d), _p(out_positions), out_positions.shape[0], _p(inp_positions),
                                  inp_positions.shape[0], _p(inp_importance), _p(neighbors_index), _p(neighbors_row_splits),
                                  _p(neighbors_importance), n_pairs, _p(records), _stream()))
+    _prof_end(rec)
     return records
 
 

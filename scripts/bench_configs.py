@@ -1,6 +1,8 @@
 """Per-step timing of the BASELINE configs 2 and 3 (WBC-SPH 2-D ~10k particles, Liquid3d 3-D ~100k particles) with the
 shipped checkpoints (tests/golden/ckpt_*.npz): ms/step and the time per conv kernel group.
-  python scripts/bench_configs.py [liquid3d|wbc] [steps]"""
+`c5shard` is one GPU's share of BASELINE config 5 (4 M particles on 8 GPUs, full multi-scale Liquid3d net): 80^3 = 512 000
+fluid particles in an open box.
+  python scripts/bench_configs.py [liquid3d|wbc|c5shard] [steps]"""
 import os, sys
 sys.path.insert(0, '.')
 sys.path.insert(0, 'tests')
@@ -11,7 +13,10 @@ import test_models_gpu as T
 which = sys.argv[1] if len(sys.argv) > 1 else 'liquid3d'
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dev = torch.device('cuda')
-if which == 'liquid3d':
+if which == 'c5shard':
+    cfg, scene, wname = T.liquid3d_cfg(), scenes.lattice_scene((80, 80, 80), dx=0.05, seed=2, open_top=True), 'ckpt_Liquid3d.npz'
+    acc = None
+elif which == 'liquid3d':
     cfg, scene, wname = T.liquid3d_cfg(), scenes.lattice_scene((46, 46, 46), dx=0.05, seed=2, open_top=True), 'ckpt_Liquid3d.npz'
     acc = None
 else:
@@ -31,6 +36,7 @@ e0.record()
 for _ in range(steps): out = sim.step(sample)
 e1.record(); torch.cuda.synchronize()
 prof, ops.PROFILE = ops.PROFILE, None
+prof = [r for r in prof if 'kind' not in r]  # conv launches only
 ms = e0.elapsed_time(e1) / steps
 print('ms/step %.2f  particles*steps/s %.3e' % (ms, scene['pos'].shape[0] / ms * 1e3))
 g = {}
@@ -43,3 +49,4 @@ for k, v in sorted(g.items(), key=lambda kv: -sum(kv[1])):
     tot += per
     print('%-15s %s %3d->%-3d n_in %7d n_out %7d pairs %9d : %6.3f ms/step (%d launches/step)' % (k[0], k[1], k[2], k[3], k[4], k[5], k[6], per, len(v) // steps))
 print('conv kernels total %.2f ms/step' % tot)
+print('peak memory %.2f GB' % (torch.cuda.max_memory_allocated() / 2 ** 30))

@@ -19,6 +19,7 @@ def run(opt, label):
     for _ in range(3): sim.step(sample)
     e1.record(); torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
+    prof = [r for r in prof if 'kind' not in r]
     g = {}
     for r in prof:
         k = (r['kernel_size'], r['cin'], r['cout'])
