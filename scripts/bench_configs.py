@@ -36,6 +36,7 @@ e0.record()
 for _ in range(steps): out = sim.step(sample)
 e1.record(); torch.cuda.synchronize()
 prof, ops.PROFILE = ops.PROFILE, None
+hbm = [r for r in prof if 'kind' in r]
 prof = [r for r in prof if 'kind' not in r]  # conv launches only
 ms = e0.elapsed_time(e1) / steps
 print('ms/step %.2f  particles*steps/s %.3e' % (ms, scene['pos'].shape[0] / ms * 1e3))
@@ -49,4 +50,10 @@ for k, v in sorted(g.items(), key=lambda kv: -sum(kv[1])):
     tot += per
     print('%-15s %s %3d->%-3d n_in %7d n_out %7d pairs %9d : %6.3f ms/step (%d launches/step)' % (k[0], k[1], k[2], k[3], k[4], k[5], k[6], per, len(v) // steps))
 print('conv kernels total %.2f ms/step' % tot)
+h = {}
+for r in hbm:
+    a = h.setdefault(r['kind'], [0.0, 0, 0])
+    a[0] += r['start'].elapsed_time(r['end']); a[1] += 1; a[2] += r.get('pairs', 0)
+for k, a in sorted(h.items(), key=lambda kv: -kv[1][0]):
+    print('%-13s %7.3f ms/step (%d launches/step, %d pairs/step)' % (k, a[0] / steps, a[1] // steps, a[2] // steps))
 print('peak memory %.2f GB' % (torch.cuda.max_memory_allocated() / 2 ** 30))
