@@ -65,6 +65,7 @@ SIGNATURES = {
     "dmcf_approx_match": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "dmcf_match_cost_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "dmcf_match_cost": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "dmcf_match_cost_grad": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dmcf_nn_distance": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
 }
 

@@ -293,6 +293,55 @@ __global__ void __launch_bounds__(256) k_match_cost(const float* __restrict__ xy
     if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
 }
 
+// gradient of the match cost w.r.t. both point sets (tf_approxmatch.cpp:198-232, the match is a constant):
+//   g = match[l][k] (x2_l - x1_k) / max(|x2_l - x1_k|, 1e-20);  grad1[k] = -sum_l g;  grad2[l] = sum_k g
+// grad1: one thread per k (match reads coalesced over k); grad2: one warp per l, lanes over k, shuffle reduction.
+__global__ void __launch_bounds__(256) k_match_cost_grad1(const float* __restrict__ xyz1, int n, const float* __restrict__ xyz2, int m,
+                                                            const float* __restrict__ match, int64_t match_ld, float* __restrict__ grad1) {
+    __shared__ float buf[3 * kAmTile];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    float x1 = 0.f, y1 = 0.f, z1 = 0.f;
+    if (k < n) { x1 = xyz1[3 * k]; y1 = xyz1[3 * k + 1]; z1 = xyz1[3 * k + 2]; }
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int l0 = 0; l0 < m; l0 += kAmTile) {
+        const int lend = min(m, l0 + kAmTile) - l0;
+        for (int t = threadIdx.x; t < 3 * lend; t += blockDim.x) buf[t] = xyz2[(size_t)3 * l0 + t];
+        __syncthreads();
+        if (k < n) {
+            for (int l = 0; l < lend; ++l) {
+                const float dx = buf[3 * l] - x1, dy = buf[3 * l + 1] - y1, dz = buf[3 * l + 2] - z1;
+                const float d = fmaxf(sqrtf(fps_dist2(dx, dy, dz)), 1e-20f);
+                const float w = match[(int64_t)(l0 + l) * match_ld + k];
+                gx -= w * (dx / d); gy -= w * (dy / d); gz -= w * (dz / d);
+            }
+        }
+        __syncthreads();
+    }
+    if (k < n) { grad1[3 * k] = gx; grad1[3 * k + 1] = gy; grad1[3 * k + 2] = gz; }
+}
+
+__global__ void __launch_bounds__(256) k_match_cost_grad2(const float* __restrict__ xyz1, int n, const float* __restrict__ xyz2, int m,
+                                                            const float* __restrict__ match, int64_t match_ld, float* __restrict__ grad2) {
+    const int lane = threadIdx.x & 31;
+    const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (l >= m) return;
+    const float x2 = xyz2[3 * l], y2 = xyz2[3 * l + 1], z2 = xyz2[3 * l + 2];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int k = lane; k < n; k += 32) {
+        const float dx = x2 - xyz1[3 * k], dy = y2 - xyz1[3 * k + 1], dz = z2 - xyz1[3 * k + 2];
+        const float d = fmaxf(sqrtf(fps_dist2(dx, dy, dz)), 1e-20f);
+        const float w = match[(int64_t)l * match_ld + k];
+        sx += w * (dx / d); sy += w * (dy / d); sz += w * (dz / d);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, off);
+        sy += __shfl_xor_sync(0xffffffffu, sy, off);
+        sz += __shfl_xor_sync(0xffffffffu, sz, off);
+    }
+    if (lane == 0) { grad2[3 * l] = sx; grad2[3 * l + 1] = sy; grad2[3 * l + 2] = sz; }
+}
+
 // nearest neighbour in set 2 of every point of set 1 (utils/tools/nn_distance.cpp:47-70): squared distance
 // (x*x + y*y) + z*z without contraction, first minimum wins
 __global__ void __launch_bounds__(256) k_nn_distance(const float* __restrict__ xyz1, int n, const float* __restrict__ xyz2, int m,
@@ -407,6 +456,19 @@ extern "C" int dmcf_match_cost(const float* xyz1, int32_t n, const float* xyz2, 
     DMCF_LAUNCH_CHECK("k_match_cost");
     k_sum_f32<<<1, 1024, 0, st>>>(nullptr, 0, (const double*)workspace, (int64_t)grid.x * grid.y, cost_out);
     DMCF_LAUNCH_CHECK("k_sum_f32");
+    return DMCF_OK;
+}
+
+extern "C" int dmcf_match_cost_grad(const float* xyz1, int32_t n, const float* xyz2, int32_t m, const float* match, int64_t match_ld,
+                                    float* grad1, float* grad2, void* stream) {
+    DMCF_REQUIRE(n >= 1 && m >= 1, "match_cost_grad: empty point set (n=%d m=%d)", n, m);
+    DMCF_REQUIRE(xyz1 && xyz2 && match && grad1 && grad2, "match_cost_grad: NULL buffer");
+    DMCF_REQUIRE(match_ld >= n, "match_cost_grad: match row stride smaller than n");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_match_cost_grad1<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(xyz1, n, xyz2, m, match, match_ld, grad1);
+    DMCF_LAUNCH_CHECK("k_match_cost_grad1");
+    k_match_cost_grad2<<<(unsigned)ceil_div(m, 8), 256, 0, st>>>(xyz1, n, xyz2, m, match, match_ld, grad2);
+    DMCF_LAUNCH_CHECK("k_match_cost_grad2");
     return DMCF_OK;
 }
 

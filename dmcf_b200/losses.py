@@ -107,7 +107,7 @@ def compute_density(out_pos, in_pos=None, radius=0.005, win=None):
 
 def get_loss(typ, fac=1.0, **kwargs):
     """Training losses of utils/tools/losses.py:47-134 that need nothing but the predicted / target positions:
-    'mse', 'weighted_mse', 'vel', and 'dense' (density_loss)."""
+    'mse', 'weighted_mse', 'vel', 'dense' (density_loss) and 'emd' (approx-match cost with the reference's gradient)."""
     gamma = kwargs.get("gamma", 0.5)
 
     def pre_factor(kw):
@@ -130,4 +130,10 @@ def get_loss(typ, fac=1.0, **kwargs):
         from .metrics import density_loss
         kw2 = dict(kwargs)
         return partial(density_loss, win=get_window_func(kw2.pop("win", None)), **kw2)
+    if typ == "emd":  # :105-106 -> emd_loss(y_true, y_pred) on [n, 3] frames
+        from .pointops import emd_loss
+
+        def f(target, pred, **kw):
+            return fac * emd_loss(target.unsqueeze(0).contiguous(), pred.unsqueeze(0).contiguous()).mean()
+        return f
     raise NotImplementedError(f"loss {typ!r}")

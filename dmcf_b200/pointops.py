@@ -3,6 +3,7 @@
   * ``farthest_point_sample(npoint, inp)``, ``gather_point(inp, idx)``     <- utils/tools/sampling.py:62-112
   * ``approx_match(xyz1, xyz2, n=None, m=None)``, ``match_cost(...)``       <- utils/tools/tf_approxmatch.py:43-75
   * ``nn_distance(xyz1, xyz2)``                                             <- utils/tools/nn_distance.py:41-52
+  * ``match_cost_grad`` (the registered gradient of ``match_cost``)         <- utils/tools/tf_approxmatch.py:78-88
   * ``emd_loss`` / ``approx_vel``                                           <- utils/tools/losses.py:401-413
 
 Batched CUDA float32 tensors in the reference's layouts ([b, n, 3] point sets, match [b, m, n]); every function raises
@@ -97,6 +98,38 @@ def match_cost(xyz1, xyz2, match):
     return cost
 
 
+def match_cost_grad(xyz1, xyz2, match):
+    """op MatchCostGrad (utils/tools/tf_approxmatch.py:78-88 registers it as the gradient of match_cost): d cost / d xyz1
+    [b, n, 3] and d cost / d xyz2 [b, m, 3] with the match held constant."""
+    lib = _lib.load()
+    xyz1, xyz2 = _points(xyz1, "xyz1"), _points(xyz2, "xyz2")
+    _req(match, "match", dim=3)
+    b, nn, mm = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    if tuple(match.shape) != (b, mm, nn):
+        raise ValueError(f"match must have shape {(b, mm, nn)}, got {tuple(match.shape)}")
+    match = match.contiguous()
+    g1, g2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
+    for i in range(b):
+        check(lib.dmcf_match_cost_grad(_p(xyz1[i]), nn, _p(xyz2[i]), mm, _p(match[i]), nn, _p(g1[i]), _p(g2[i]), _stream()))
+    return g1, g2
+
+
+class _MatchCost(torch.autograd.Function):
+    """match_cost with the reference's registered gradient (the match itself carries none: ops.NoGradient('ApproxMatch'))."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, match):
+        ctx.save_for_backward(xyz1, xyz2, match)
+        return match_cost(xyz1, xyz2, match)
+
+    @staticmethod
+    def backward(ctx, grad_cost):
+        xyz1, xyz2, match = ctx.saved_tensors
+        g1, g2 = match_cost_grad(xyz1.detach(), xyz2.detach(), match)
+        gc = grad_cost.reshape(-1, 1, 1)
+        return g1 * gc, g2 * gc, None
+
+
 def emd_cost(xyz1, xyz2, n=None, m=None, first_level=7):
     """``match_cost(xyz1, xyz2, approx_match(xyz1, xyz2, n, m))`` without the [m, n] match matrix: the cost is accumulated
     while the assignment is annealed (O(n + m) memory; the metric of run_valid on scenes whose match matrix would not fit)."""
@@ -119,7 +152,11 @@ def emd_loss(y_true, y_pred, n=None, m=None, fused=True, first_level=7):
     """utils/tools/losses.py:401-408: match cost / max(n, m), [b]."""
     b = y_true.shape[0]
     cn, cm = _counts(n, b, y_true.shape[1], "n"), _counts(m, b, y_pred.shape[1], "m")
-    if fused:
+    if y_true.requires_grad or y_pred.requires_grad:  # training loss (utils/tools/losses.py:105-106)
+        with torch.no_grad():
+            match = approx_match(y_true, y_pred, n, m, first_level)
+        cost = _MatchCost.apply(y_true, y_pred, match)
+    elif fused:
         cost = emd_cost(y_true, y_pred, n, m, first_level)
     else:
         cost = match_cost(y_true, y_pred, approx_match(y_true, y_pred, n, m, first_level))

@@ -229,6 +229,10 @@ int dmcf_approx_match(const float* xyz1, int32_t n, const float* xyz2, int32_t m
 size_t dmcf_match_cost_workspace_bytes(int32_t n, int32_t m);
 int dmcf_match_cost(const float* xyz1, int32_t n, const float* xyz2, int32_t m, const float* match, int64_t match_ld,
                     float* cost_out, void* workspace, size_t workspace_bytes, void* stream);
+/* op MatchCostGrad (tf_approxmatch.cpp:44-50,198-232): gradients of the match cost w.r.t. both point sets, match held constant;
+ * grad1 [n,3], grad2 [m,3]. */
+int dmcf_match_cost_grad(const float* xyz1, int32_t n, const float* xyz2, int32_t m, const float* match, int64_t match_ld,
+                         float* grad1, float* grad2, void* stream);
 int dmcf_nn_distance(const float* xyz1, int32_t n, const float* xyz2, int32_t m, float* dist, int32_t* idx, void* stream);
 
 #ifdef __cplusplus

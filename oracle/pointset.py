@@ -81,6 +81,16 @@ def ref_match_cost(xyz1, xyz2, match):
     return cost
 
 
+def ref_match_cost_grad(xyz1, xyz2, match):
+    """matchcostgrad_cpu (:198-232) -> (grad1 [b,n,3], grad2 [b,m,3]).  (The reference zeroes only component 0 of grad1
+    before accumulating; the buffers handed over here are zero-filled.)"""
+    xyz1, xyz2, match = (np.ascontiguousarray(a, F32) for a in (xyz1, xyz2, match))
+    b, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    g1, g2 = np.zeros((b, n, 3), F32), np.zeros((b, m, 3), F32)
+    ref_lib().ref_matchcostgrad(b, n, m, _p(xyz1), _p(xyz2), _p(match), _p(g1), _p(g2))
+    return g1, g2
+
+
 def ref_nn_search(xyz1, xyz2):
     """nnsearch (nn_distance.cpp:47-70): xyz1 [b,n,3], xyz2 [b,m,3] -> (squared distance [b,n], index [b,n])."""
     xyz1, xyz2 = np.ascontiguousarray(xyz1, F32), np.ascontiguousarray(xyz2, F32)
@@ -158,6 +168,15 @@ def match_cost(xyz1, xyz2, match):
     x1, x2 = np.asarray(xyz1, np.float64), np.asarray(xyz2, np.float64)
     d = np.sqrt(((x2[:, None, :] - x1[None, :, :]) ** 2).sum(-1))
     return float((d * np.asarray(match, np.float64)).sum())
+
+
+def match_cost_grad(xyz1, xyz2, match):
+    """tf_approxmatch.cpp:198-232 for one batch item in float64: (grad1 [n,3], grad2 [m,3])."""
+    x1, x2, mt = np.asarray(xyz1, np.float64), np.asarray(xyz2, np.float64), np.asarray(match, np.float64)
+    diff = x2[:, None, :] - x1[None, :, :]  # [m, n, 3]
+    d = np.maximum(np.sqrt((diff ** 2).sum(-1)), 1e-20)
+    g = mt[:, :, None] * diff / d[:, :, None]
+    return -g.sum(0), g.sum(1)
 
 
 def emd_loss(y_true, y_pred, first_level=7):

@@ -143,8 +143,12 @@ def test_grid_pos_matches_oracle_as_sets(cuda, dim, centralize):
     dil, pcnt, idx = losses.get_dilated_pos(t, [1, 2, 4], voxel_size=[0.025 if v > 0 else 0.0 for v in vox], centralize=centralize)
     ref = o64.get_dilated_pos(pts, [1, 2, 4], voxel_size=[0.025 if v > 0 else 0.0 for v in vox], centralize=centralize)
     assert dil[0] is t and [d.shape[0] for d in dil] == [r.shape[0] for r in ref] == pcnt
-    with pytest.raises(NotImplementedError):
-        losses.get_dilated_pos(t, [1, 2], voxel_size=None)
+    # voxel_size None: nested farthest-point subsets of N // stride points (utils/tools/losses.py:274-282)
+    dil, pcnt, idx = losses.get_dilated_pos(t, [1, 2, 8], voxel_size=None)
+    ref, ridx = o64.get_dilated_pos(pts, [1, 2, 8], voxel_size=None, return_idx=True)
+    assert pcnt == [3000, 1500, 375] and idx[0] is None and tuple(idx[1].shape) == (1, 1500)
+    for s in (1, 2):
+        assert np.array_equal(idx[s][0].cpu().numpy(), ridx[s]) and np.array_equal(dil[s].cpu().numpy(), ref[s])
 
 
 def test_compute_density_and_empty_inputs(cuda, cloud):

@@ -139,3 +139,18 @@ def test_o64_model_with_farthest_point_scales():
     assert [d.shape[0] for d in m.dilated_pos] == [n_all, n_all // 2, n_all // 4]
     assert np.array_equal(m.dilated_pos[2], m.dilated_pos[1][m.fps_idx[2]])  # nested subsets
     assert np.abs(m.net_out.sum(0)).max() <= 1e-9 * np.abs(m.net_out).sum() + 1e-12  # momentum is still conserved
+
+
+@needs_ref
+def test_match_cost_grad_restatement_vs_reference():
+    a, b = _sets(70, 50, 0.4, 6)
+    mt = ps.approx_match(a, b, 8).astype(np.float32)
+    g1r, g2r = ps.ref_match_cost_grad(a[None], b[None], mt[None])
+    g1, g2 = ps.match_cost_grad(a, b, mt)
+    assert np.abs(g1 - g1r[0]).max() <= 1e-5 and np.abs(g2 - g2r[0]).max() <= 1e-5
+    # and it IS the derivative of match_cost with the match held constant
+    eps = 1e-6
+    a2 = a.astype(np.float64).copy()
+    a2[3, 1] += eps
+    num = (ps.match_cost(a2, b, mt) - ps.match_cost(a, b, mt)) / eps
+    assert abs(num - g1[3, 1]) <= 1e-4 * max(1.0, abs(num))

@@ -215,3 +215,25 @@ def test_model_step_with_farthest_point_scales(cuda):
     tol = (2e-5 * scale + 1e-6) * 8
     assert np.abs(net[:n_f] - ref.net_out[:n_f]).max() <= tol
     assert np.abs(pos_u.cpu().numpy() - pos_r).max() <= tol * 0.0078125 + 4e-7 * max(np.abs(pos_r).max(), 1.0)
+
+
+def test_match_cost_grad_and_emd_training_loss(cuda):
+    """op MatchCostGrad against the reference's matchcostgrad_cpu, and autograd through emd_loss (the 'emd' training loss)."""
+    from dmcf_b200 import pointops
+    from dmcf_b200.losses import get_loss
+    a, b = _sets(300, 260, 0.4, 15)
+    mt = ps.approx_match(a, b, 7).astype(np.float32)
+    g1, g2 = pointops.match_cost_grad(_t(a[None], cuda), _t(b[None], cuda), _t(mt[None], cuda))
+    if ps.ref_available():
+        w1, w2 = ps.ref_match_cost_grad(a[None], b[None], mt[None])
+    else:
+        w1, w2 = (x[None] for x in ps.match_cost_grad(a, b, mt))
+    assert np.abs(g1.cpu().numpy() - w1).max() <= 2e-5 and np.abs(g2.cpu().numpy() - w2).max() <= 2e-5
+    pred = _t(b, cuda).clone().requires_grad_(True)
+    loss = get_loss("emd", fac=2.0)(_t(a, cuda), pred)
+    loss.backward()
+    mt_gpu = pointops.approx_match(_t(a[None], cuda), _t(b[None], cuda))
+    _, want2 = ps.match_cost_grad(a, b, mt_gpu.cpu().numpy()[0])
+    want = 2.0 * want2 / max(len(a), len(b))
+    assert np.abs(pred.grad.cpu().numpy() - want).max() <= 2e-5 * max(1.0, np.abs(want).max()) + 1e-7
+    assert abs(float(loss) - 2.0 * float(pointops.emd_loss(_t(a[None], cuda), _t(b[None], cuda))[0])) <= 1e-5 * float(loss)
