@@ -236,4 +236,4 @@ def test_match_cost_grad_and_emd_training_loss(cuda):
     _, want2 = ps.match_cost_grad(a, b, mt_gpu.cpu().numpy()[0])
     want = 2.0 * want2 / max(len(a), len(b))
     assert np.abs(pred.grad.cpu().numpy() - want).max() <= 2e-5 * max(1.0, np.abs(want).max()) + 1e-7
-    assert abs(float(loss) - 2.0 * float(pointops.emd_loss(_t(a[None], cuda), _t(b[None], cuda))[0])) <= 1e-5 * float(loss)
+    assert abs(float(loss.detach()) - 2.0 * float(pointops.emd_loss(_t(a[None], cuda), _t(b[None], cuda))[0])) <= 1e-5 * float(loss.detach())
