@@ -16,6 +16,7 @@ struct ConvParams {
     int debug_wrap_w;         // timing experiment switches (dmcf_set_kernel_options bits 8+), never set in production
     int filter_antisym;       // desc flag: filters[rev(cell)] == -filters[cell]
     int use_zsplit;           // option bit 2: run 4x4x4 wide layers as two z-half launches (2 CTAs/SM)
+    int no_multipair;         // option bit 5: k_cconv_lean keeps the one-pair-per-step walk for narrow inputs (A/B switch)
     int cip, cp;              // pow2 lane groupings for input / output channels
     const float* filters;
     const float* out_pos;

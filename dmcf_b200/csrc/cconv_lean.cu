@@ -34,7 +34,9 @@
 namespace dmcf {
 
 
-template <int KZ, int KY, int KX, int MT, int NW, bool RELU, bool FX>
+// SL = 1: the register-patch walk above.  SL = 2 / 4 / 8 (cin <= 16 / 8 / 4): the multi-pair phase 1 of cconv_walk.cuh
+// (lean::point_patch_mp; relu / scale are run-time flags there, so those instances use RELU = FX = false).
+template <int KZ, int KY, int KX, int MT, int NW, bool RELU, bool FX, int SL>
 __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     using G = FilterGrid<KZ, KY, KX>;
     constexpr int K = G::K;
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     const size_t tile_words = (size_t)(p.kc_pad / 4) * MTP * 4, red_words = (size_t)NW * MT * 32;
     float* recs = patch + (tile_words > red_words ? tile_words : red_words);
     float* norm = recs + (size_t)NW * lean::kRecWords;  // [MT]
+    float* accs = norm + MT;                             // SL > 1: [NW][K][32] per-warp slot patches
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile_base = (int64_t)blockIdx.x * MT;
@@ -66,6 +69,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         ox = __ldg(p.out_pos + 3 * o); oy = __ldg(p.out_pos + 3 * o + 1); oz = __ldg(p.out_pos + 3 * o + 2);
     }
     PairRec cur = pair_record(p, rs + lane, rs + lane < re, ox, oy, oz);
+    if constexpr (SL > 1) {
+        float* a = accs + (size_t)warp * K * 32 + lane;
+#pragma unroll 8
+        for (int c = 0; c < K; ++c) a[c * 32] = 0.0f;
+        __syncwarp();
+    }
 
 #pragma unroll 1
     for (int i = 0; i < PPW; ++i) {
@@ -81,21 +90,31 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         }
         // first chunk of the next point: in flight during this whole point (a short last chunk would not cover it)
         const PairRec first_n = pair_record(p, rs_n + lane, n_ok && rs_n + lane < re_n, ox_n, oy_n, oz_n);
-        float acc[K];
-#pragma unroll
-        for (int c = 0; c < K; ++c) acc[c] = 0.0f;
-        float fc = 0.0f;  // centre feature of the antisymmetric layer (out point o == input row o)
-        if (p.ascc && o_ok && lane_ci) {
-            fc = __ldg(p.inp_feat + o * p.inp_stride + lane);
-            if (RELU) fc = fmaxf(fc, 0.0f);
-            fc *= p.feat_scale;
-        }
-        float norm_acc = lean::point_patch<lean::FullPatch<KZ, KY, KX>, RELU, FX>(p, cx, cur, rs, re, ox, oy, oz, fc, acc);
-        // ---- patch row -> shared memory (lane = channel: conflict free), Dense columns, padding ----
-        if (!o_ok) {
-            for (int k = lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
+        float norm_acc;
+        if constexpr (SL > 1) {
+            // lanes = SL pair slots x 32/SL channels; the patch row is written by point_patch_mp
+            const int ch = lane % (32 / SL);
+            float fc = 0.0f;
+            if (p.ascc && o_ok && ch < p.cin) {
+                fc = __ldg(p.inp_feat + o * p.inp_stride + ch);
+                if (p.relu_input) fc = fmaxf(fc, 0.0f);
+                fc *= p.feat_scale;
+            }
+            norm_acc = lean::point_patch_mp<G, SL, MT>(p, lane, cur, rs, re, ox, oy, oz, fc, p.ascc || p.feat_scale != 1.0f,
+                                                        accs + (size_t)warp * K * 32, patch, m);
         } else {
-            if (lane_ci) {
+            float acc[K];
+#pragma unroll
+            for (int c = 0; c < K; ++c) acc[c] = 0.0f;
+            float fc = 0.0f;  // centre feature of the antisymmetric layer (out point o == input row o)
+            if (p.ascc && o_ok && lane_ci) {
+                fc = __ldg(p.inp_feat + o * p.inp_stride + lane);
+                if (RELU) fc = fmaxf(fc, 0.0f);
+                fc *= p.feat_scale;
+            }
+            norm_acc = lean::point_patch<lean::FullPatch<KZ, KY, KX>, RELU, FX>(p, cx, cur, rs, re, ox, oy, oz, fc, acc);
+            // ---- patch row -> shared memory (lane = channel: conflict free) ----
+            if (o_ok && lane_ci) {
                 if ((p.cin & 3) == 0) {  // k = c*cin + lane: the k-quad advances by cin/4 per cell -> one running pointer
                     float* pp = patch + patchq_index<MT>(m, lane);
                     const int step = p.cin * MTP;
@@ -106,6 +125,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
                     for (int c = 0; c < K; ++c) patch[patchq_index<MT>(m, c * p.cin + lane)] = acc[c];
                 }
             }
+        }
+        // ---- Dense columns, padding ----
+        if (!o_ok) {
+            for (int k = lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
+        } else {
             if (p.dense_cin > 0) {
                 const float* drow = p.dense_inp + o * p.dense_stride;
                 for (int ci = lane; ci < p.dense_cin; ci += 32) {
@@ -293,9 +317,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     }
 }
 
-static size_t lean_smem_bytes(int mt, int nw, int kc_pad) {
+static size_t lean_smem_bytes(int mt, int nw, int kc_pad, int slot_patch_cells = 0) {
     const size_t tile = (size_t)(kc_pad / 4) * (mt + 1) * 4, red = (size_t)nw * mt * 32;
-    return ((tile > red ? tile : red) + (size_t)nw * lean::kScratchWords + mt) * sizeof(float);
+    return ((tile > red ? tile : red) + (size_t)nw * lean::kScratchWords + mt + (size_t)nw * slot_patch_cells * 32) * sizeof(float);
 }
 
 template <int KZ, int KY, int KX>
@@ -306,17 +330,31 @@ static int launch_lean_grid(const ConvParams& p, cudaStream_t st, bool* handled)
     static bool attr_set = false;
     // [relu on the input][feature scale and/or the antisymmetric centre term]
     void (*kerns[2][2])(const ConvParams) = {
-        {k_cconv_lean<KZ, KY, KX, MT, NW, false, false>, k_cconv_lean<KZ, KY, KX, MT, NW, false, true>},
-        {k_cconv_lean<KZ, KY, KX, MT, NW, true, false>, k_cconv_lean<KZ, KY, KX, MT, NW, true, true>}};
+        {k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 1>, k_cconv_lean<KZ, KY, KX, MT, NW, false, true, 1>},
+        {k_cconv_lean<KZ, KY, KX, MT, NW, true, false, 1>, k_cconv_lean<KZ, KY, KX, MT, NW, true, true, 1>}};
+    // multi-pair phase 1 for narrow inputs: [0] cin <= 16 (2 pair slots), [1] cin <= 8 (4), [2] cin <= 4 (8)
+    void (*kerns_mp[3])(const ConvParams) = {k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 2>,
+                                             k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 4>,
+                                             k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 8>};
     if (!attr_set) {
         for (int i = 0; i < 4; ++i) {
             cudaError_t e = cudaFuncSetAttribute(kerns[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_lean)");
         }
+        for (int i = 0; i < 3; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kerns_mp[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_lean, multi-pair)");
+        }
         attr_set = true;
     }
     *handled = true;
     const int64_t tiles = ceil_div(p.n_out, MT);
+    constexpr int K = KZ * KY * KX;
+    if (!p.no_multipair && p.cin <= 16 && lean_smem_bytes(MT, NW, p.kc_pad, K) <= 227 * 1024) {
+        kerns_mp[p.cin <= 4 ? 2 : (p.cin <= 8 ? 1 : 0)]<<<(unsigned)tiles, NW * 32, lean_smem_bytes(MT, NW, p.kc_pad, K), st>>>(p);
+        DMCF_LAUNCH_CHECK("k_cconv_lean (multi-pair)");
+        return DMCF_OK;
+    }
     const bool fx = p.ascc || p.feat_scale != 1.0f;
     kerns[p.relu_input ? 1 : 0][fx ? 1 : 0]<<<(unsigned)tiles, NW * 32, lean_smem_bytes(MT, NW, p.kc_pad), st>>>(p);
     DMCF_LAUNCH_CHECK("k_cconv_lean");

@@ -278,6 +278,145 @@ __device__ __forceinline__ float point_patch(const ConvParams& p, WarpCtx& cx, P
     return norm_acc;
 }
 
+// ---- multi-pair phase 1 for narrow inputs (cin <= 16) ---------------------------------------------------------------
+// With few input channels the lane = channel layout of point_patch leaves most lanes idle and still pays the ~28-instruction
+// walk for every pair (measured: the 4 -> 32 and the 24 -> 32 cross-scale convs of Liquid3d cost the same 2 ms).  Here the 32
+// lanes are SL pair slots x CP = 32 / SL channels: one step scatters SL pairs at once, every lane into ITS OWN column of a
+// per-warp shared-memory patch accs[cell][lane] (bank = lane: conflict free, no atomics; no sort, no indirect branch, no
+// per-pair control flow).  A chunk's features are fetched with NT = 32 / SL independent loads per lane, one chunk ahead.  When
+// the point is complete the SL slot columns of every cell are summed in a fixed order (deterministic) into the CTA's patch
+// tile and zeroed for the warp's next point.
+template <class G, int SL, int MT>
+__device__ __forceinline__ float point_patch_mp(const ConvParams& p, int lane, PairRec cur, int64_t rs, int64_t re, float ox,
+                                                float oy, float oz, float fc, bool fx, float* accs, float* patch, int m) {
+    static_assert(SL == 2 || SL == 4 || SL == 8, "pair slots per step");
+    static_assert(G::K % SL == 0, "the slot reduction walks SL cells at a time");
+    constexpr int CP = 32 / SL, NT = 32 / SL;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int slot = lane / CP, ch = lane % CP;
+    const bool ch_ok = ch < p.cin;
+    const char* fbase = reinterpret_cast<const char*>(p.inp_feat) + 4 * (ch_ok ? ch : 0);
+    const int stride_b = (int)p.inp_stride * 4;
+    const bool relu = p.relu_input != 0;
+    const float scale = p.feat_scale;
+    float norm_acc = 0.0f;
+
+    // base form of this lane's pair: cell of corner 0, byte offset of the feature row (-1 = dropped), 8 corner weights
+    auto to_base = [&](const PairRec& r, int& c000, int& off, float4& wa, float4& wb) {
+        c000 = 0; off = -1;
+        wa = make_float4(0.f, 0.f, 0.f, 0.f); wb = wa;
+        if (r.row >= 0) {
+            int bx, by, bz;
+            float xl, xh, yl, yh, zl, zh;
+            base_axis(G::KX_, r.g.i0 & 0xff, r.g.wx0, r.g.wx1, bx, xl, xh);
+            base_axis(G::KY_, (r.g.i0 >> 8) & 0xff, r.g.wy0, r.g.wy1, by, yl, yh);
+            base_axis(G::KZ_, (r.g.i0 >> 16) & 0xff, r.g.wz0, r.g.wz1, bz, zl, zh);
+            c000 = (bz * G::KY_ + by) * G::KX_ + bx;
+            wa = make_float4(xl * yl * zl, xh * yl * zl, xl * yh * zl, xh * yh * zl);
+            wb = make_float4(xl * yl * zh, xh * yl * zh, xl * yh * zh, xh * yh * zh);
+            off = r.row * stride_b;
+        }
+    };
+    // features of a chunk: step t serves pairs t*SL .. t*SL + SL - 1, this lane the pair of its slot
+    auto load_feats = [&](int off, int nsteps, float (&f)[NT]) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int o = __shfl_sync(FULL, off, t * SL + slot);
+            f[t] = (t < nsteps && ch_ok && o >= 0) ? __ldg(reinterpret_cast<const float*>(fbase + (unsigned)o)) : 0.0f;
+        }
+    };
+    auto steps = [&](int c000, const float4& wa, const float4& wb, const float (&f)[NT], int nsteps) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (t < nsteps) {  // warp uniform
+                const int q = t * SL + slot;
+                const int c0 = __shfl_sync(FULL, c000, q);
+                const float w0 = __shfl_sync(FULL, wa.x, q), w1 = __shfl_sync(FULL, wa.y, q);
+                const float w2 = __shfl_sync(FULL, wa.z, q), w3 = __shfl_sync(FULL, wa.w, q);
+                const float w4 = __shfl_sync(FULL, wb.x, q), w5 = __shfl_sync(FULL, wb.y, q);
+                const float w6 = __shfl_sync(FULL, wb.z, q), w7 = __shfl_sync(FULL, wb.w, q);
+                float v = f[t];
+                if (relu) v = fmaxf(v, 0.0f);
+                if (fx) v = fmaf(v, scale, fc);
+                float* a = accs + c0 * 32 + lane;
+                constexpr int sx = 32, sy = 32 * G::KX_, sz = 32 * G::KY_ * G::KX_;
+                a[0] = fmaf(w0, v, a[0]);
+                if constexpr (G::KX_ > 1) a[sx] = fmaf(w1, v, a[sx]);
+                if constexpr (G::KY_ > 1) a[sy] = fmaf(w2, v, a[sy]);
+                if constexpr (G::KX_ > 1 && G::KY_ > 1) a[sx + sy] = fmaf(w3, v, a[sx + sy]);
+                if constexpr (G::KZ_ > 1) {
+                    a[sz] = fmaf(w4, v, a[sz]);
+                    if constexpr (G::KX_ > 1) a[sz + sx] = fmaf(w5, v, a[sz + sx]);
+                    if constexpr (G::KY_ > 1) a[sz + sy] = fmaf(w6, v, a[sz + sy]);
+                    if constexpr (G::KX_ > 1 && G::KY_ > 1) a[sz + sx + sy] = fmaf(w7, v, a[sz + sx + sy]);
+                }
+            }
+        }
+    };
+    auto empty_rec = [] {
+        PairRec r;
+        r.row = -1; r.norm = 0.0f; r.g.i0 = r.g.i1 = 0;
+        r.g.wx0 = r.g.wx1 = r.g.wy0 = r.g.wy1 = r.g.wz0 = r.g.wz1 = 0.0f;
+        return r;
+    };
+
+    int c000, off;
+    float4 wa, wb;
+    to_base(cur, c000, off, wa, wb);
+    norm_acc += cur.norm;
+    int64_t c0 = rs;
+    int nrange = (int)(re - c0 < 32 ? re - c0 : 32);
+    if (nrange < 0) nrange = 0;
+    bool last = c0 + 32 >= re;
+    PairRec nxt = empty_rec();
+    if (!last) nxt = pair_record(p, c0 + 32 + lane, c0 + 32 + lane < re, ox, oy, oz);
+    float fcur[NT];
+    load_feats(off, (nrange + SL - 1) / SL, fcur);
+#pragma unroll 1
+    for (;;) {
+        const int nsteps = (nrange + SL - 1) / SL;
+        // the next chunk: base form, its features, and the raw records of the chunk after it -- all in flight during the steps
+        int c000n = 0, offn = -1, nrange_n = 0;
+        float4 wan = make_float4(0.f, 0.f, 0.f, 0.f), wbn = wan;
+        float fnx[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) fnx[t] = 0.0f;
+        PairRec nxt2 = empty_rec();
+        if (!last) {  // warp uniform
+            to_base(nxt, c000n, offn, wan, wbn);
+            norm_acc += nxt.norm;
+            nrange_n = (int)(re - (c0 + 32) < 32 ? re - (c0 + 32) : 32);
+            if (c0 + 64 < re) nxt2 = pair_record(p, c0 + 64 + lane, c0 + 64 + lane < re, ox, oy, oz);
+            load_feats(offn, (nrange_n + SL - 1) / SL, fnx);
+        }
+        steps(c000, wa, wb, fcur, nsteps);
+        if (last) break;
+        c000 = c000n; off = offn; wa = wan; wb = wbn; nrange = nrange_n; nxt = nxt2;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) fcur[t] = fnx[t];
+        c0 += 32;
+        last = c0 + 32 >= re;
+    }
+    // ---- slot columns -> patch row; cell = cell0 + slot reads the columns in the rotated order slot, slot+1, ... so that the
+    // 32 lanes hit 32 different banks; every word is zeroed by the lane that read it ----
+    __syncwarp();
+#pragma unroll 2
+    for (int cell0 = 0; cell0 < G::K; cell0 += SL) {
+        const int cell = cell0 + slot;
+        float* row = accs + cell * 32 + ch;
+        float v = 0.0f;
+#pragma unroll
+        for (int i = 0; i < SL; ++i) {
+            const int s = (i + slot) & (SL - 1);
+            v += row[s * CP];
+            row[s * CP] = 0.0f;
+        }
+        if (ch_ok) patch[patchq_index<MT>(m, cell * p.cin + ch)] = v;
+    }
+    __syncwarp();
+    return norm_acc;
+}
+
 }  // namespace lean
 
 }  // namespace dmcf

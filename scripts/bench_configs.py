@@ -2,7 +2,7 @@
 shipped checkpoints (tests/golden/ckpt_*.npz): ms/step and the time per conv kernel group.
 `c5shard` is one GPU's share of BASELINE config 5 (4 M particles on 8 GPUs, full multi-scale Liquid3d net): 80^3 = 512 000
 fluid particles in an open box.
-  python scripts/bench_configs.py [liquid3d|wbc|c5shard] [steps]"""
+  python scripts/bench_configs.py [liquid3d|wbc|c5shard|c4] [steps] [kernel options]"""
 import os, sys
 sys.path.insert(0, '.')
 sys.path.insert(0, 'tests')
@@ -12,8 +12,13 @@ from dmcf_b200.simulator import Simulator
 import test_models_gpu as T
 which = sys.argv[1] if len(sys.argv) > 1 else 'liquid3d'
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+if len(sys.argv) > 3:
+    ops.set_kernel_options(int(sys.argv[3]))  # e.g. 35 = single-pair walk for narrow inputs (A/B against the default 3)
 dev = torch.device('cuda')
-if which == 'c5shard':
+if which == 'c4':
+    cfg, scene, wname = scenes.c4_model_cfg(), scenes.lattice_scene((100, 100, 100), dx=0.05, seed=0), None
+    acc = None
+elif which == 'c5shard':
     cfg, scene, wname = T.liquid3d_cfg(), scenes.lattice_scene((80, 80, 80), dx=0.05, seed=2, open_top=True), 'ckpt_Liquid3d.npz'
     acc = None
 elif which == 'liquid3d':
@@ -23,7 +28,10 @@ else:
     cfg, scene, wname = T.wbc_cfg(), scenes.lattice_scene((100, 100, 1), dx=0.005, seed=3, vel_sigma=0.05), 'ckpt_WBC-SPH.npz'
     acc = np.tile(np.array([[0.0, -9.81, 0.0]], np.float32), (scene['pos'].shape[0], 1))
 model = config.build_model(cfg)
-model.load_weights(T.load_npz_weights(wname), device=dev)
+if wname is None:
+    model.init_weights(seed=0, device=dev, scale=0.1)
+else:
+    model.load_weights(T.load_npz_weights(wname), device=dev)
 sim = Simulator(model, device='cuda')
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
 sample = [t(scene['pos']), t(scene['vel']), None if acc is None else t(acc), None, t(scene['box']), t(scene['box_normals'])]

@@ -141,7 +141,8 @@ CONV_CASES = [
 ]
 
 
-@pytest.fixture(params=[3, 27, 31, 0], ids=["fast-kernels", "legacy-wide-direct", "legacy-wide-zsplit-direct", "generic-kernel"])
+@pytest.fixture(params=[3, 35, 27, 31, 0], ids=["fast-kernels", "fast-kernels-single-pair-walk", "legacy-wide-direct",
+                                               "legacy-wide-zsplit-direct", "generic-kernel"])
 def kernel_options(request):
     from dmcf_b200 import ops
     prev = ops.set_kernel_options(request.param)
@@ -200,12 +201,14 @@ def test_continuous_conv_matches_oracle(cuda, case, fused_window, kernel_options
         feat_close(got2.cpu().numpy(), got.cpu().numpy(), 0.5)
 
 
-def test_continuous_conv_fused_extras(cuda, kernel_options):
+@pytest.mark.parametrize("cin", [24, 16, 11, 8, 3])
+def test_continuous_conv_fused_extras(cuda, kernel_options, cin):
     """relu on the input, feature scale, neighbour sub-range, skip-self on a self-containing CSR, fused Dense,
-    bias, residual, accumulate, strided in/out rows."""
+    bias, residual, accumulate, strided in/out rows.  cin <= 16 runs the multi-pair phase 1 of k_cconv_lean (2 / 4 / 8 pair
+    slots per step) unless the kernel options ask for the single-pair walk."""
     from dmcf_b200 import ops
     rng = np.random.default_rng(11)
-    n, cin, cout, ks = 800, 24, 32, (4, 4, 4)
+    n, cout, ks = 800, 32, (4, 4, 4)
     pts = rng.random((n, 3)).astype(np.float32)
     feats_wide = rng.standard_normal((n, cin + 5)).astype(np.float32)
     feats = feats_wide[:, 2:2 + cin]
@@ -349,3 +352,93 @@ def test_no_cpu_fallback(cuda):
     from dmcf_b200._lib import DmcfError
     with pytest.raises(DmcfError):
         ops.fixed_radius_search(torch.zeros((4, 3)), torch.zeros((4, 3)), 0.1)
+
+
+@pytest.mark.parametrize("ks,cin,cout,extent", [((4, 4, 4), 4, 16, 0.45), ((4, 4, 4), 8, 32, 0.45), ((4, 4, 4), 16, 8, 0.45),
+                                                ((1, 8, 8), 5, 12, 0.3), ((1, 8, 1), 2, 4, 0.2), ((4, 4, 4), 1, 4, 0.4)])
+def test_multipair_phase1_cross_sets_long_rows(cuda, ks, cin, cout, extent):
+    """Multi-pair phase 1 (cin <= 16) on the shape of the cross-scale convs: distinct in / out sets, rows of 100+ pairs
+    (several chunks, the chunk pipeline), rows without any neighbour, an out-point count that is not a multiple of the
+    24-point tile, with and without pair records, the antisymmetric centre term on a 4-channel output; against the oracle
+    and against the single-pair walk."""
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(cin * 100 + cout)
+    n_in, n_out = 2600, 1013
+    pts = rng.random((n_in, 3)).astype(np.float32)
+    outp = (rng.random((n_out, 3)) * 1.3 - 0.15).astype(np.float32)  # some out points have no neighbour at all
+    if ks[0] == 1:
+        pts[:, 2] = 0; outp[:, 2] = 0
+    if ks[2] == 1:
+        pts[:, 0] = 0; outp[:, 0] = 0
+    outp[:3] = np.where(np.array(ks[::-1]) > 1, 5.0, 0.0).astype(np.float32)  # far away: rows without neighbours
+    feats = rng.standard_normal((n_in, cin)).astype(np.float32)
+    filt = rng.uniform(-0.5, 0.5, ks + (cin, cout)).astype(np.float32)
+    ext = np.float32(extent)
+    radius = np.float32(0.5) * ext
+    idx, splits, d2 = o64.fixed_radius_search(pts, outp, radius)
+    counts = np.diff(splits)
+    assert counts.max() > 64 and counts.min() == 0
+    imp = o64.window("poly6", d2.astype(np.float64) / (np.float64(radius) ** 2))
+    ref = o64.continuous_conv(filt, outp, ext, (0, 0, 0), pts, np.maximum(feats, 0) * 0.7, None, idx, imp, splits,
+                              align_corners=True, coordinate_mapping="ball_to_cube_volume_preserving", normalize=False,
+                              interpolation="linear")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    kw = dict(align_corners=True, coordinate_mapping="ball_to_cube_volume_preserving", normalize=False, interpolation="linear",
+              window="poly6", relu_input=True, feat_scale=0.7)
+    recs = ops.prepare_pair_records(ks, t(outp), float(ext), None, t(pts), None, t(idx), None, t(splits), align_corners=True,
+                                    coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear", window="poly6")
+    outs = {}
+    for opt in (3, 35):
+        prev = ops.set_kernel_options(opt)
+        try:
+            for rec in (None, recs):
+                got = ops.continuous_conv(t(filt), t(outp), float(ext), None, t(pts), t(feats), None, t(idx), None, t(splits),
+                                          pair_records=rec, **kw).cpu().numpy()
+                feat_close(got, ref)
+                outs[(opt, rec is None)] = got
+        finally:
+            ops.set_kernel_options(prev)
+    feat_close(outs[(3, True)], outs[(35, True)], 0.5)
+    feat_close(outs[(3, False)], outs[(35, False)], 0.5)
+    assert np.all(outs[(3, True)][counts == 0] == 0)
+    # normaliser (sum of the window values) through the multi-pair path
+    refn = o64.continuous_conv(filt, outp, ext, (0, 0, 0), pts, feats, None, idx, imp, splits, align_corners=True,
+                               coordinate_mapping="ball_to_cube_volume_preserving", normalize=True, interpolation="linear")
+    gotn = ops.continuous_conv(t(filt), t(outp), float(ext), None, t(pts), t(feats), None, t(idx), None, t(splits),
+                               align_corners=True, coordinate_mapping="ball_to_cube_volume_preserving", normalize=True,
+                               interpolation="linear", window="poly6").cpu().numpy()
+    feat_close(gotn, refn)
+
+
+@pytest.mark.parametrize("cin", [4, 8, 16])
+def test_multipair_phase1_antisymmetric_centre_term(cuda, cin):
+    """ascc on a 4-channel output that takes the k_cconv_lean path (apatch / direct switched off): out_i = sum_j W(r_ij)
+    (f_j + f_i) with the centre term added per pair slot; against the single-pair walk and momentum conservation."""
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(40 + cin)
+    n, cout = 1100, 4
+    pts = rng.random((n, 3)).astype(np.float32) * 0.6
+    feats = rng.standard_normal((n, cin)).astype(np.float32)
+    half = rng.uniform(-0.5, 0.5, (4, 2, 4, cin, cout)).astype(np.float32)
+    full = o64.symmetric_kernel(half, 1).astype(np.float32)
+    extent = np.float32(0.25)
+    ref = o64.cconv_layer(np.maximum(feats, 0), pts, pts, extent, half, None, align_corners=True,
+                          coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear", normalize=False,
+                          ignore_query_points=True, window_name="peak", symmetric=True, sym_axis=1)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    nns = ops.fixed_radius_search(t(pts), t(pts), float(np.float32(0.5) * extent), ignore_query_point=True)
+    outs = []
+    for opt in (1, 1 | 32):  # bit 1 off: no direct / apatch kernel, the lean kernel takes cout = 4
+        prev = ops.set_kernel_options(opt)
+        try:
+            got = ops.continuous_conv(t(full), t(pts), float(extent), None, t(pts), t(feats), None, nns.neighbors_index, None,
+                                      nns.neighbors_row_splits, align_corners=True,
+                                      coordinate_mapping="ball_to_cube_volume_preserving", normalize=False,
+                                      interpolation="linear", window="peak", relu_input=True, ascc=True).cpu().numpy()
+        finally:
+            ops.set_kernel_options(prev)
+        feat_close(got, ref)
+        total = np.abs(got).sum(axis=0)
+        assert np.all(np.abs(got.astype(np.float64).sum(axis=0)) <= 1e-5 * total + 1e-5)
+        outs.append(got)
+    feat_close(outs[0], outs[1], 0.5)
