@@ -34,7 +34,7 @@
 namespace dmcf {
 
 
-// SL = 1: the register-patch walk above.  SL = 2 / 4 / 8 (cin <= 16 / 8 / 4): the multi-pair phase 1 of cconv_walk.cuh
+// SL = 1: the register-patch walk above.  SL = 4 / 8 (cin <= 8 / 4): the multi-pair phase 1 of cconv_walk.cuh
 // (lean::point_patch_mp; relu / scale are run-time flags there, so those instances use RELU = FX = false).
 template <int KZ, int KY, int KX, int MT, int NW, bool RELU, bool FX, int SL>
 __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
@@ -332,16 +332,17 @@ static int launch_lean_grid(const ConvParams& p, cudaStream_t st, bool* handled)
     void (*kerns[2][2])(const ConvParams) = {
         {k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 1>, k_cconv_lean<KZ, KY, KX, MT, NW, false, true, 1>},
         {k_cconv_lean<KZ, KY, KX, MT, NW, true, false, 1>, k_cconv_lean<KZ, KY, KX, MT, NW, true, true, 1>}};
-    // multi-pair phase 1 for narrow inputs: [0] cin <= 16 (2 pair slots), [1] cin <= 8 (4), [2] cin <= 4 (8)
-    void (*kerns_mp[3])(const ConvParams) = {k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 2>,
-                                             k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 4>,
+    // multi-pair phase 1 for narrow inputs: [0] cin <= 8 (4 pair slots), [1] cin <= 4 (8 pair slots).  Measured on the
+    // Liquid3d cross-scale convs (26 M pairs): cin = 4: 1.95 -> 1.02 ms, cin = 8: 2.07 -> 1.59 ms; two slots (cin <= 16) were
+    // slower than the single-pair walk (2.15 -> 2.60 ms: a step costs about two walk iterations) and are not instantiated.
+    void (*kerns_mp[2])(const ConvParams) = {k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 4>,
                                              k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 8>};
     if (!attr_set) {
         for (int i = 0; i < 4; ++i) {
             cudaError_t e = cudaFuncSetAttribute(kerns[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_lean)");
         }
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 2; ++i) {
             cudaError_t e = cudaFuncSetAttribute(kerns_mp[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_lean, multi-pair)");
         }
@@ -350,8 +351,8 @@ static int launch_lean_grid(const ConvParams& p, cudaStream_t st, bool* handled)
     *handled = true;
     const int64_t tiles = ceil_div(p.n_out, MT);
     constexpr int K = KZ * KY * KX;
-    if (!p.no_multipair && p.cin <= 16 && lean_smem_bytes(MT, NW, p.kc_pad, K) <= 227 * 1024) {
-        kerns_mp[p.cin <= 4 ? 2 : (p.cin <= 8 ? 1 : 0)]<<<(unsigned)tiles, NW * 32, lean_smem_bytes(MT, NW, p.kc_pad, K), st>>>(p);
+    if (!p.no_multipair && p.cin <= 8 && lean_smem_bytes(MT, NW, p.kc_pad, K) <= 227 * 1024) {
+        kerns_mp[p.cin <= 4 ? 1 : 0]<<<(unsigned)tiles, NW * 32, lean_smem_bytes(MT, NW, p.kc_pad, K), st>>>(p);
         DMCF_LAUNCH_CHECK("k_cconv_lean (multi-pair)");
         return DMCF_OK;
     }

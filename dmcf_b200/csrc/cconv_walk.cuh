@@ -2,6 +2,7 @@
 // k_cconv_apatch (cconv_apatch.cu): one warp per out point, lane = input channel, the trilinear patch of the point in
 // registers.  See cconv_lean.cu for the reasoning behind each piece.
 #pragma once
+#include <type_traits>
 #include "cconv_scatter.cuh"
 
 namespace dmcf {
@@ -278,22 +279,23 @@ __device__ __forceinline__ float point_patch(const ConvParams& p, WarpCtx& cx, P
     return norm_acc;
 }
 
-// ---- multi-pair phase 1 for narrow inputs (cin <= 16) ---------------------------------------------------------------
+// ---- multi-pair phase 1 for narrow inputs (cin <= 8) ----------------------------------------------------------------
 // With few input channels the lane = channel layout of point_patch leaves most lanes idle and still pays the ~28-instruction
 // walk for every pair (measured: the 4 -> 32 and the 24 -> 32 cross-scale convs of Liquid3d cost the same 2 ms).  Here the 32
 // lanes are SL pair slots x CP = 32 / SL channels: one step scatters SL pairs at once, every lane into ITS OWN column of a
-// per-warp shared-memory patch accs[cell][lane] (bank = lane: conflict free, no atomics; no sort, no indirect branch, no
-// per-pair control flow).  A chunk's features are fetched with NT = 32 / SL independent loads per lane, one chunk ahead.  When
-// the point is complete the SL slot columns of every cell are summed in a fixed order (deterministic) into the CTA's patch
-// tile and zeroed for the warp's next point.
+// per-warp shared-memory patch accs[cell][ch * SL + slot] (bank = a permutation of the lane id: conflict free, no atomics; no
+// sort, no indirect branch, no per-pair control flow).  The chunks of a point alternate between two register sets (static
+// indices, no register moves behind loads in flight): while the steps of chunk k run, the features of chunk k+1 and the raw
+// records of chunk k+2 are in flight.  When the point is complete the SL slot words of every (cell, channel) -- contiguous, one
+// LDS.128 -- are summed in a fixed order (deterministic) into the CTA's patch tile and zeroed for the warp's next point.
 template <class G, int SL, int MT>
-__device__ __forceinline__ float point_patch_mp(const ConvParams& p, int lane, PairRec cur, int64_t rs, int64_t re, float ox,
-                                                float oy, float oz, float fc, bool fx, float* accs, float* patch, int m) {
-    static_assert(SL == 2 || SL == 4 || SL == 8, "pair slots per step");
-    static_assert(G::K % SL == 0, "the slot reduction walks SL cells at a time");
+__device__ __forceinline__ float point_patch_mp(const ConvParams& p, int lane, const PairRec& first, int64_t rs, int64_t re,
+                                                float ox, float oy, float oz, float fc, bool fx, float* accs, float* patch, int m) {
+    static_assert(SL == 4 || SL == 8, "pair slots per step");
     constexpr int CP = 32 / SL, NT = 32 / SL;
     constexpr unsigned FULL = 0xffffffffu;
     const int slot = lane / CP, ch = lane % CP;
+    const int col = ch * SL + slot;  // this lane's column of the slot patch
     const bool ch_ok = ch < p.cin;
     const char* fbase = reinterpret_cast<const char*>(p.inp_feat) + 4 * (ch_ok ? ch : 0);
     const int stride_b = (int)p.inp_stride * 4;
@@ -301,44 +303,50 @@ __device__ __forceinline__ float point_patch_mp(const ConvParams& p, int lane, P
     const float scale = p.feat_scale;
     float norm_acc = 0.0f;
 
-    // base form of this lane's pair: cell of corner 0, byte offset of the feature row (-1 = dropped), 8 corner weights
-    auto to_base = [&](const PairRec& r, int& c000, int& off, float4& wa, float4& wb) {
-        c000 = 0; off = -1;
-        wa = make_float4(0.f, 0.f, 0.f, 0.f); wb = wa;
+    // two chunk states (even / odd chunks of the point): raw records, base form (cell of corner 0, byte offset of the feature
+    // row or -1, 8 corner weights) of this lane's pair, and the features of this lane's slot for the NT steps
+    PairRec raw[2];
+    int c000[2], off[2], nrange[2];
+    float4 wa[2], wb[2];
+    float f[2][NT];
+
+    auto to_base = [&](const PairRec& r, int& c0, int& o, float4& a, float4& b) {
+        c0 = 0; o = -1;
+        a = make_float4(0.f, 0.f, 0.f, 0.f); b = a;
         if (r.row >= 0) {
             int bx, by, bz;
             float xl, xh, yl, yh, zl, zh;
             base_axis(G::KX_, r.g.i0 & 0xff, r.g.wx0, r.g.wx1, bx, xl, xh);
             base_axis(G::KY_, (r.g.i0 >> 8) & 0xff, r.g.wy0, r.g.wy1, by, yl, yh);
             base_axis(G::KZ_, (r.g.i0 >> 16) & 0xff, r.g.wz0, r.g.wz1, bz, zl, zh);
-            c000 = (bz * G::KY_ + by) * G::KX_ + bx;
-            wa = make_float4(xl * yl * zl, xh * yl * zl, xl * yh * zl, xh * yh * zl);
-            wb = make_float4(xl * yl * zh, xh * yl * zh, xl * yh * zh, xh * yh * zh);
-            off = r.row * stride_b;
+            c0 = (bz * G::KY_ + by) * G::KX_ + bx;
+            a = make_float4(xl * yl * zl, xh * yl * zl, xl * yh * zl, xh * yh * zl);
+            b = make_float4(xl * yl * zh, xh * yl * zh, xl * yh * zh, xh * yh * zh);
+            o = r.row * stride_b;
         }
     };
     // features of a chunk: step t serves pairs t*SL .. t*SL + SL - 1, this lane the pair of its slot
-    auto load_feats = [&](int off, int nsteps, float (&f)[NT]) {
+    auto load_feats = [&](int o_lane, int nsteps, float (&ff)[NT]) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            const int o = __shfl_sync(FULL, off, t * SL + slot);
-            f[t] = (t < nsteps && ch_ok && o >= 0) ? __ldg(reinterpret_cast<const float*>(fbase + (unsigned)o)) : 0.0f;
+            const int o = __shfl_sync(FULL, o_lane, t * SL + slot);
+            ff[t] = (t < nsteps && ch_ok && o >= 0) ? __ldg(reinterpret_cast<const float*>(fbase + (unsigned)o)) : 0.0f;
         }
     };
-    auto steps = [&](int c000, const float4& wa, const float4& wb, const float (&f)[NT], int nsteps) {
+    auto steps = [&](int c0_lane, const float4& a4, const float4& b4, const float (&ff)[NT], int nsteps) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             if (t < nsteps) {  // warp uniform
                 const int q = t * SL + slot;
-                const int c0 = __shfl_sync(FULL, c000, q);
-                const float w0 = __shfl_sync(FULL, wa.x, q), w1 = __shfl_sync(FULL, wa.y, q);
-                const float w2 = __shfl_sync(FULL, wa.z, q), w3 = __shfl_sync(FULL, wa.w, q);
-                const float w4 = __shfl_sync(FULL, wb.x, q), w5 = __shfl_sync(FULL, wb.y, q);
-                const float w6 = __shfl_sync(FULL, wb.z, q), w7 = __shfl_sync(FULL, wb.w, q);
-                float v = f[t];
+                const int c0 = __shfl_sync(FULL, c0_lane, q);
+                const float w0 = __shfl_sync(FULL, a4.x, q), w1 = __shfl_sync(FULL, a4.y, q);
+                const float w2 = __shfl_sync(FULL, a4.z, q), w3 = __shfl_sync(FULL, a4.w, q);
+                const float w4 = __shfl_sync(FULL, b4.x, q), w5 = __shfl_sync(FULL, b4.y, q);
+                const float w6 = __shfl_sync(FULL, b4.z, q), w7 = __shfl_sync(FULL, b4.w, q);
+                float v = ff[t];
                 if (relu) v = fmaxf(v, 0.0f);
                 if (fx) v = fmaf(v, scale, fc);
-                float* a = accs + c0 * 32 + lane;
+                float* a = accs + c0 * 32 + col;
                 constexpr int sx = 32, sy = 32 * G::KX_, sz = 32 * G::KY_ * G::KX_;
                 a[0] = fmaf(w0, v, a[0]);
                 if constexpr (G::KX_ > 1) a[sx] = fmaf(w1, v, a[sx]);
@@ -353,65 +361,55 @@ __device__ __forceinline__ float point_patch_mp(const ConvParams& p, int lane, P
             }
         }
     };
-    auto empty_rec = [] {
-        PairRec r;
-        r.row = -1; r.norm = 0.0f; r.g.i0 = r.g.i1 = 0;
-        r.g.wx0 = r.g.wx1 = r.g.wy0 = r.g.wy1 = r.g.wz0 = r.g.wz1 = 0.0f;
-        return r;
+    auto chunk_len = [&](int64_t c0) {
+        const int64_t n = re - c0;
+        return (int)(n < 0 ? 0 : (n < 32 ? n : 32));
+    };
+    // chunk c0 lives in state P; prepares chunk c0 + 32 in state 1 - P (needs its raw records, issued one chunk earlier), issues
+    // the raw records of chunk c0 + 64 into raw[P] (chunk c0's are dead: it is in base form), then runs the steps of chunk c0.
+    // Returns true when chunk c0 was the last one.
+    auto half = [&](auto P_, int64_t c0) {
+        constexpr int P = decltype(P_)::value, Q = 1 - P;
+        const bool last = c0 + 32 >= re;  // warp uniform
+        if (!last) {
+            to_base(raw[Q], c000[Q], off[Q], wa[Q], wb[Q]);
+            norm_acc += raw[Q].norm;
+            nrange[Q] = chunk_len(c0 + 32);
+            if (c0 + 64 < re) raw[P] = pair_record(p, c0 + 64 + lane, c0 + 64 + lane < re, ox, oy, oz);
+            load_feats(off[Q], (nrange[Q] + SL - 1) / SL, f[Q]);
+        }
+        steps(c000[P], wa[P], wb[P], f[P], (nrange[P] + SL - 1) / SL);
+        return last;
     };
 
-    int c000, off;
-    float4 wa, wb;
-    to_base(cur, c000, off, wa, wb);
-    norm_acc += cur.norm;
-    int64_t c0 = rs;
-    int nrange = (int)(re - c0 < 32 ? re - c0 : 32);
-    if (nrange < 0) nrange = 0;
-    bool last = c0 + 32 >= re;
-    PairRec nxt = empty_rec();
-    if (!last) nxt = pair_record(p, c0 + 32 + lane, c0 + 32 + lane < re, ox, oy, oz);
-    float fcur[NT];
-    load_feats(off, (nrange + SL - 1) / SL, fcur);
+    raw[0] = first;
+    raw[1] = first;  // placeholder, overwritten before use
+    to_base(raw[0], c000[0], off[0], wa[0], wb[0]);
+    norm_acc += raw[0].norm;
+    nrange[0] = chunk_len(rs);
+    if (rs + 32 < re) raw[1] = pair_record(p, rs + 32 + lane, rs + 32 + lane < re, ox, oy, oz);
+    load_feats(off[0], (nrange[0] + SL - 1) / SL, f[0]);
 #pragma unroll 1
-    for (;;) {
-        const int nsteps = (nrange + SL - 1) / SL;
-        // the next chunk: base form, its features, and the raw records of the chunk after it -- all in flight during the steps
-        int c000n = 0, offn = -1, nrange_n = 0;
-        float4 wan = make_float4(0.f, 0.f, 0.f, 0.f), wbn = wan;
-        float fnx[NT];
-#pragma unroll
-        for (int t = 0; t < NT; ++t) fnx[t] = 0.0f;
-        PairRec nxt2 = empty_rec();
-        if (!last) {  // warp uniform
-            to_base(nxt, c000n, offn, wan, wbn);
-            norm_acc += nxt.norm;
-            nrange_n = (int)(re - (c0 + 32) < 32 ? re - (c0 + 32) : 32);
-            if (c0 + 64 < re) nxt2 = pair_record(p, c0 + 64 + lane, c0 + 64 + lane < re, ox, oy, oz);
-            load_feats(offn, (nrange_n + SL - 1) / SL, fnx);
-        }
-        steps(c000, wa, wb, fcur, nsteps);
-        if (last) break;
-        c000 = c000n; off = offn; wa = wan; wb = wbn; nrange = nrange_n; nxt = nxt2;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) fcur[t] = fnx[t];
-        c0 += 32;
-        last = c0 + 32 >= re;
+    for (int64_t c0 = rs;; c0 += 64) {
+        if (half(std::integral_constant<int, 0>{}, c0)) break;
+        if (half(std::integral_constant<int, 1>{}, c0 + 32)) break;
     }
-    // ---- slot columns -> patch row; cell = cell0 + slot reads the columns in the rotated order slot, slot+1, ... so that the
-    // 32 lanes hit 32 different banks; every word is zeroed by the lane that read it ----
+    // ---- slot words -> patch row: lane handles (cell, channel) = idx / CP, idx % CP; its SL slot words are contiguous ----
     __syncwarp();
 #pragma unroll 2
-    for (int cell0 = 0; cell0 < G::K; cell0 += SL) {
-        const int cell = cell0 + slot;
-        float* row = accs + cell * 32 + ch;
-        float v = 0.0f;
-#pragma unroll
-        for (int i = 0; i < SL; ++i) {
-            const int s = (i + slot) & (SL - 1);
-            v += row[s * CP];
-            row[s * CP] = 0.0f;
+    for (int idx = lane; idx < G::K * CP; idx += 32) {
+        const int cell = idx / CP, c = idx % CP;
+        float4* w4 = reinterpret_cast<float4*>(accs + cell * 32 + c * SL);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 a = w4[0];
+        w4[0] = z4;
+        float v = (a.x + a.y) + (a.z + a.w);
+        if constexpr (SL == 8) {
+            const float4 b = w4[1];
+            w4[1] = z4;
+            v += (b.x + b.y) + (b.z + b.w);
         }
-        if (ch_ok) patch[patchq_index<MT>(m, cell * p.cin + ch)] = v;
+        if (c < p.cin) patch[patchq_index<MT>(m, cell * p.cin + c)] = v;
     }
     __syncwarp();
     return norm_acc;
