@@ -166,7 +166,8 @@ int dmcf_cconv_patches(const dmcf_conv_desc* desc, const float* out_positions, i
  * k_cconv_wide where the lean kernel is not eligible), bit 1 = resident-filter direct kernel for cout <= 4
  * (k_cconv_direct) and the folded half-patch kernel for antisymmetric filters (k_cconv_apatch), bit 2 = run 4x4x4 layers of
  * the legacy k_cconv_wide as two z-half launches, bit 3 = use the legacy k_cconv_wide instead of k_cconv_lean, bit 4 = do
- * not use k_cconv_apatch (bits 3 and 4 are kept for A/B measurements); 0 forces the generic kernel.  Returns the previous
+ * not use k_cconv_apatch, bit 5 = k_cconv_lean keeps the one-pair-per-step walk for inputs with <= 8 channels instead of the
+ * multi-pair phase 1 (bits 3, 4 and 5 are kept for A/B measurements); 0 forces the generic kernel.  Returns the previous
  * mask.  Results agree to float32 rounding. */
 int dmcf_set_kernel_options(int options);
 
