@@ -5,6 +5,10 @@
   column_seed44.npz     1-D SPH column from the reference's own generator datasets/column_gen.py (imported, not copied),
                         with the generator's brute-force neighbour counter SPH1D.cnt_nn (:36-43) as the known answer
   canyon_crop.npz       frame 0 of datasets/canyon_data/canyon.msgpack.zst cropped around the inflow block
+  pointset_ref.npz      outputs of the reference's own CPU functions for the in-repo point-set ops (approxmatch_cpu,
+                        approxmatch_cpu_dyn, matchcost_cpu, matchcostgrad_cpu of utils/tools/tf_approxmatch.cpp, nnsearch of
+                        utils/tools/nn_distance.cpp), run through oracle/_ref/libdmcf_refops.so (built by oracle/Makefile from
+                        the reference sources where they lie) on seeded point clouds
 """
 import os
 import sys
@@ -74,8 +78,36 @@ def canyon():
     print("canyon", pos.shape, int(m.sum()), "boundary points kept of", len(m))
 
 
+def pointset():
+    from oracle import pointset as ps
+    assert ps.ref_available(), "build oracle/_ref first: make -C oracle"
+    out = {}
+    cases = [("a", 96, 96, 1.0, 3), ("b", 150, 75, 0.3, 3), ("c", 60, 140, 0.05, 3), ("d", 64, 64, 0.02, 2)]
+    for name, n, m, scale, dim in cases:
+        rng = np.random.default_rng(sum(map(ord, name)) + n)
+        x1 = (rng.random((n, 3)) * scale).astype(np.float32)
+        x2 = (rng.random((m, 3)) * scale).astype(np.float32)
+        if dim == 2:
+            x1[:, 2] = 0
+            x2[:, 2] = 0
+        match = ps.ref_approx_match(x1[None], x2[None])
+        out[f"{name}_xyz1"], out[f"{name}_xyz2"], out[f"{name}_match"] = x1, x2, match[0]
+        out[f"{name}_cost"] = ps.ref_match_cost(x1[None], x2[None], match)[0]
+        g1, g2 = ps.ref_match_cost_grad(x1[None], x2[None], match)
+        out[f"{name}_grad1"], out[f"{name}_grad2"] = g1[0], g2[0]
+        d, i = ps.ref_nn_search(x1[None], x2[None])
+        out[f"{name}_nn_dist"], out[f"{name}_nn_idx"] = d[0], i[0]
+    # per-item counts (the *_dyn kernel)
+    x1, x2 = out["b_xyz1"], out["b_xyz2"]
+    out["b_dyn_counts"] = np.asarray([101, 60], np.int32)
+    out["b_dyn_match"] = ps.ref_approx_match_dyn(x1[None], x2[None], [101], [60])[0]
+    np.savez_compressed(os.path.join(OUT, "pointset_ref.npz"), **out)
+    print("pointset", len(out), "arrays", sum(v.nbytes for v in out.values()), "bytes")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     checkpoints()
     column()
     canyon()
+    pointset()

@@ -154,3 +154,47 @@ def test_match_cost_grad_restatement_vs_reference():
     a2[3, 1] += eps
     num = (ps.match_cost(a2, b, mt) - ps.match_cost(a, b, mt)) / eps
     assert abs(num - g1[3, 1]) <= 1e-4 * max(1.0, abs(num))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# committed golden vectors: outputs of the reference's own CPU functions (tests/golden/pointset_ref.npz, made by
+# scripts/make_golden.py::pointset from oracle/_ref) -- these pin the restatement wherever oracle/_ref is not built
+# ---------------------------------------------------------------------------------------------------------
+def golden_pointset():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "pointset_ref.npz"))
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+def test_restatement_against_golden_reference_outputs(case):
+    z = golden_pointset()
+    x1, x2, ref = z[f"{case}_xyz1"], z[f"{case}_xyz2"], z[f"{case}_match"]
+    got = ps.approx_match(x1, x2, first_level=8)
+    # the restatement follows the CUDA kernel's formulation, the fixture the CPU kernel's: same scheme, the 1e-9 guards sit in
+    # different places (tf_approxmatch.cu:84,118 vs tf_approxmatch.cpp:73-79) -> up to 6e-3 on single entries, 1e-4 on the cost
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-2
+    c_ref = float(z[f"{case}_cost"])
+    assert abs(ps.match_cost(x1, x2, ref) - c_ref) <= 1e-5 * c_ref + 1e-7
+    assert abs(ps.match_cost(x1, x2, got) - c_ref) <= 1e-4 * c_ref + 1e-7
+    g1, g2 = ps.match_cost_grad(x1, x2, ref)
+    assert np.abs(g1 - z[f"{case}_grad1"]).max() <= 2e-5 and np.abs(g2 - z[f"{case}_grad2"]).max() <= 2e-5
+    d, i = ps.nn_search(x1, x2)
+    assert np.array_equal(i, z[f"{case}_nn_idx"]) and np.array_equal(d, z[f"{case}_nn_dist"])
+
+
+def test_restatement_dyn_counts_against_golden():
+    z = golden_pointset()
+    cn, cm = (int(v) for v in z["b_dyn_counts"])
+    ref = z["b_dyn_match"]
+    assert np.all(ref[cm:] == 0) and np.all(ref[:, cn:] == 0)
+    got = ps.approx_match(z["b_xyz1"][:cn], z["b_xyz2"][:cm], first_level=8)
+    assert np.abs(got - ref[:cm, :cn]).max() <= 5e-3
+
+
+@needs_ref
+def test_golden_vectors_are_what_the_reference_code_produces():
+    """The fixture is reproducible from oracle/_ref (guards against a stale file)."""
+    z = golden_pointset()
+    for case in ("a", "d"):
+        m = ps.ref_approx_match(z[f"{case}_xyz1"][None], z[f"{case}_xyz2"][None])[0]
+        assert np.array_equal(m, z[f"{case}_match"])

@@ -237,3 +237,27 @@ def test_match_cost_grad_and_emd_training_loss(cuda):
     want = 2.0 * want2 / max(len(a), len(b))
     assert np.abs(pred.grad.cpu().numpy() - want).max() <= 2e-5 * max(1.0, np.abs(want).max()) + 1e-7
     assert abs(float(loss.detach()) - 2.0 * float(pointops.emd_loss(_t(a[None], cuda), _t(b[None], cuda))[0])) <= 1e-5 * float(loss.detach())
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+def test_kernels_against_golden_reference_outputs(cuda, case):
+    """The CUDA kernels against the committed outputs of the reference's own CPU functions (tests/golden/pointset_ref.npz,
+    scripts/make_golden.py::pointset) -- the pin that does not need oracle/_ref on the box."""
+    from dmcf_b200 import pointops
+    from test_pointset_cpu import golden_pointset
+    z = golden_pointset()
+    x1, x2, ref = z[f"{case}_xyz1"], z[f"{case}_xyz2"], z[f"{case}_match"]
+    t1, t2 = _t(x1[None], cuda), _t(x2[None], cuda)
+    got = pointops.approx_match(t1, t2, first_level=8).cpu().numpy()[0]
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1.2e-2  # CUDA-kernel formulation vs CPU-kernel formulation of the reference (guards)
+    c_ref = float(z[f"{case}_cost"])
+    c_same = float(pointops.match_cost(t1, t2, _t(ref[None], cuda))[0])
+    assert abs(c_same - c_ref) <= 2e-6 * c_ref + 1e-8
+    c_got = float(pointops.match_cost(t1, t2, _t(got[None], cuda))[0])
+    assert abs(c_got - c_ref) <= 5e-4 * c_ref + 1e-7
+    g1, g2 = pointops.match_cost_grad(t1, t2, _t(ref[None], cuda))
+    assert np.abs(g1.cpu().numpy()[0] - z[f"{case}_grad1"]).max() <= 2e-5
+    assert np.abs(g2.cpu().numpy()[0] - z[f"{case}_grad2"]).max() <= 2e-5
+    d1, i1, _, _ = pointops.nn_distance(t1, t2)
+    assert np.array_equal(i1.cpu().numpy()[0], z[f"{case}_nn_idx"]) and np.array_equal(d1.cpu().numpy()[0], z[f"{case}_nn_dist"])
