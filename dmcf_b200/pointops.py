@@ -13,8 +13,6 @@ on non-CUDA input -- there is no CPU path.  ``approx_match`` follows the referen
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from . import _lib
