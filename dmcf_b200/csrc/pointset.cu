@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(kFpsThreads, 1) k_fps(const float* __restrict_
     }
     int old = 0;
     if (rank == 0 && tid == 0 && m > 0) idx_out[0] = 0;
-    __syncthreads();
+    // every CTA of the cluster must be running before a sibling writes into its shared memory (first write: round j = 1)
+    if constexpr (CL > 1) cg::this_cluster().sync(); else __syncthreads();
     for (int j = 1; j < m; ++j) {
         const float x1 = __ldg(points + 3 * old), y1 = __ldg(points + 3 * old + 1), z1 = __ldg(points + 3 * old + 2);
         unsigned long long best = 0ull;
