@@ -4,7 +4,8 @@
   ckpt_<name>.npz       trained weights of the shipped checkpoints, read with dmcf_b200.checkpoint (TF-free)
   column_seed44.npz     1-D SPH column from the reference's own generator datasets/column_gen.py (imported, not copied),
                         with the generator's brute-force neighbour counter SPH1D.cnt_nn (:36-43) as the known answer
-  canyon_crop.npz       frame 0 of datasets/canyon_data/canyon.msgpack.zst cropped around the inflow block
+  canyon_crop.npz       frame 0 of datasets/canyon_data/canyon.msgpack.zst cropped around the inflow block, plus the particle
+                        positions of all 13 shipped ground-truth frames (the block falls and hits the canyon floor)
   pointset_ref.npz      outputs of the reference's own CPU functions for the in-repo point-set ops (approxmatch_cpu,
                         approxmatch_cpu_dyn, matchcost_cpu, matchcostgrad_cpu of utils/tools/tf_approxmatch.cpp, nnsearch of
                         utils/tools/nn_distance.cpp), run through oracle/_ref/libdmcf_refops.so (built by oracle/Makefile from
@@ -74,7 +75,8 @@ def canyon():
     m = np.all((f0["box"] >= lo) & (f0["box"] <= hi), axis=1)
     np.savez_compressed(os.path.join(OUT, "canyon_crop.npz"), pos=pos.astype(np.float32), vel=vel.astype(np.float32),
                         box=f0["box"][m].astype(np.float32), box_normals=f0["box_normals"][m].astype(np.float32),
-                        gt_pos_1=frames[1]["pos"].astype(np.float32))
+                        gt_pos_1=frames[1]["pos"].astype(np.float32),
+                        gt_pos=np.stack([f["pos"] for f in frames]).astype(np.float32))  # the 13 SPH ground-truth frames
     print("canyon", pos.shape, int(m.sum()), "boundary points kept of", len(m))
 
 

@@ -202,6 +202,26 @@ def test_rollout_pipeline(cuda):
     assert p.min() > -0.2 and p[:, :, [0, 2]].max() < 0.6
 
 
+def test_canyon_rollout_tracks_the_shipped_ground_truth(cuda):
+    """The CUDA path on the reference's own data: the shipped Liquid3d checkpoint rolled out over the 12 ground-truth steps
+    of datasets/canyon_data/canyon.msgpack.zst (the block falls and hits the canyon floor).  Shape error (centroid offset
+    removed) after 12 steps; the oracle gets 0.0206 with the restated conventions, 0.039 without the network, 0.049 / 0.21 with
+    transposed / mirrored filter axes (tests/test_oracle_cpu.py)."""
+    from dmcf_b200 import config
+    from dmcf_b200.simulator import Simulator
+    z = np.load(os.path.join(GOLDEN, "canyon_crop.npz"))
+    model = config.build_model(liquid3d_cfg())
+    sim = Simulator(model, device="cuda")
+    model.load_weights(load_npz_weights("ckpt_Liquid3d.npz"), device=cuda)
+    data = [dict(pos=z["pos"][None], vel=z["vel"][None], grav=[None], box=z["box"][None], box_normals=z["box_normals"][None])]
+    res = sim.run_rollout(data, timesteps=13)
+    assert len(res[0]) == 13
+    pos = res[0][12][0].cpu().numpy().astype(np.float64)
+    d = pos - z["gt_pos"][12]
+    err = float(np.linalg.norm(d - d.mean(0), axis=1).mean())
+    assert np.isfinite(pos).all() and err < 0.027, err
+
+
 @pytest.mark.parametrize("flags", [dict(dens_feats=True, pres_feats=True), dict(use_pre_adv=True), dict(dens_norm=True),
                                    dict(dens_feats=True, pres_feats=True, use_pre_adv=True, dens_norm=True, add_merge=False)],
                          ids=["dens+pres feats", "pre_adv", "dens_norm", "all, concat merge"])
