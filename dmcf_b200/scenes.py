@@ -44,6 +44,18 @@ def lattice_scene(shape, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0, origin=(0.0
     return dict(pos=pos.astype(np.float32), vel=vel.astype(np.float32), box=box, box_normals=normals)
 
 
+def hydrostatic_scene_2d(n=30, dx=0.005, layers=3, jitter=0.1, seed=3):
+    """A resting n x n block of fluid filling a 2-D box whose walls are `layers` rings of wall particles at pitch dx with
+    inward normals (the wall sampling of the WBC-SPH data).  Returns dict(pos, vel, acc, box, box_normals)."""
+    sc = lattice_scene((n, n, 1), dx=dx, jitter=jitter, vel_sigma=0.0, seed=seed)
+    lo, hi = np.zeros(3), np.array([n * dx, n * dx, 0.0])
+    rings = [_walls(lo - k * dx, hi + k * dx, dx, [0, 1]) for k in range(layers)]
+    sc["box"] = np.concatenate([r[0] for r in rings]).astype(np.float32)
+    sc["box_normals"] = np.concatenate([r[1] for r in rings]).astype(np.float32)
+    sc["acc"] = np.tile(np.array([[0.0, -9.81, 0.0]], np.float32), (sc["pos"].shape[0], 1))
+    return sc
+
+
 def c4_model_cfg():
     """BASELINE.json config 4: single-scale ASCC+CConv stack (SymNet with strides [1]) on a 3-D box, Liquid3d physics."""
     return dict(name="SymNet", layer_channels=[[[8]], [[32]], [[32]], [[32]], [[3]]], kernel_size=[4, 4, 4],

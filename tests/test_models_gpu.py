@@ -131,6 +131,29 @@ def test_c2_wbc_sph_2d_checkpoint(cuda):
     run_case(cuda, wbc_cfg(), scene, weights=load_npz_weights("ckpt_WBC-SPH.npz"), acc=acc)
 
 
+def test_wbc_sph_checkpoint_holds_a_hydrostatic_block(cuda):
+    """The CUDA path of the behavioural pin in tests/test_oracle_cpu.py: the shipped WBC-SPH checkpoint keeps a resting block at
+    rest in a box with the data's wall sampling (oracle: mean drift 0.0006 = 12 % of the spacing after 60 steps, lowest particle
+    at y = 0.0021, spacing 0.00483; without the network 0.112 / -0.110; mirrored or transposed filter axes explode)."""
+    from scipy.spatial import cKDTree
+    from dmcf_b200 import config, scenes
+    from dmcf_b200.simulator import Simulator
+    sc = scenes.hydrostatic_scene_2d()
+    model = config.build_model(wbc_cfg())
+    sim = Simulator(model, device="cuda")
+    model.load_weights(load_npz_weights("ckpt_WBC-SPH.npz"), device=cuda)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(cuda)
+    sample = [t(sc["pos"]), t(sc["vel"]), t(sc["acc"]), None, t(sc["box"]), t(sc["box_normals"])]
+    with torch.no_grad():
+        for _ in range(60):
+            sample = sim.step(sample)
+    pos = sample[0].cpu().numpy()
+    assert np.isfinite(pos).all()
+    drift = float(np.linalg.norm(pos - sc["pos"], axis=1).mean())
+    d, _ = cKDTree(pos[:, :2]).query(pos[:, :2], k=2)
+    assert drift < 0.002 and pos[:, 1].min() > -0.001 and abs(float(d[:, 1].mean()) - 0.00488) < 0.0003, (drift, pos[:, 1].min())
+
+
 def test_c2_gravity_alignment_rotated(cuda):
     """grav_eqvar: a rotated scene with rotated gravity gives the rotated result (models/pbf_model.py:269-301)."""
     from dmcf_b200 import scenes

@@ -336,3 +336,40 @@ def test_trained_checkpoint_tracks_the_shipped_ground_truth_only_with_the_restat
     assert err < 0.7 * err_none, (err, err_none)
     assert err < 0.6 * err_swap, (err, err_swap)
     assert err < 0.25 * err_flip, (err, err_flip)
+
+
+def _hydrostatic_drift(cfg, weights, sc, steps=60):
+    """Mean particle displacement, lowest particle and mean nearest-neighbour distance after `steps` steps of a resting block."""
+    from scipy.spatial import cKDTree
+    m = o32.ModelO32(cfg, weights)
+    pos, vel = sc["pos"].copy(), sc["vel"].copy()
+    for _ in range(steps):
+        p, v = m(pos, vel, sc["acc"], sc["box"], sc["box_normals"])
+        pos, vel = np.asarray(p, np.float32), np.asarray(v, np.float32)
+        if not np.isfinite(pos).all():
+            return float("inf"), float("-inf"), float("inf")
+    d, _ = cKDTree(pos[:, :2]).query(pos[:, :2], k=2)
+    return float(np.linalg.norm(pos - sc["pos"], axis=1).mean()), float(pos[:, 1].min()), float(d[:, 1].mean())
+
+
+def test_wbc_sph_checkpoint_holds_a_hydrostatic_block_only_with_the_restated_conventions():
+    """Second behavioural pin, 2-D path (1x8x8 filters, four scales, gravity alignment): the shipped WBC-SPH checkpoint keeps a
+    resting block of fluid at rest in a box with the data's wall sampling (three rings of wall particles) -- mean drift 0.0006
+    = 12 % of the particle spacing after 60 steps, nothing leaks, the spacing is kept.  Without the network the block falls
+    through the floor; with the filters mirrored along y or with x / y transposed it explodes."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_models_gpu import wbc_cfg
+    from dmcf_b200 import scenes
+    sc = scenes.hydrostatic_scene_2d()
+    assert sc["pos"].shape == (900, 3) and sc["box"].shape == (408, 3)
+    w = _weights("ckpt_WBC-SPH.npz")
+    cfg = wbc_cfg()
+    spatial = lambda fn: {k: (np.ascontiguousarray(fn(v)) if v.ndim == 5 else v) for k, v in w.items()}
+    drift, ymin, nn = _hydrostatic_drift(cfg, w, sc)
+    assert drift < 0.002 and ymin > -0.001 and abs(nn - 0.00488) < 0.0003, (drift, ymin, nn)  # measured 0.0006 / 0.0021 / 0.00483
+    drift_none, ymin_none, _ = _hydrostatic_drift(cfg, {k: (np.zeros_like(v) if k.startswith("sym") else v) for k, v in w.items()}, sc)
+    assert drift_none > 0.05 and ymin_none < -0.05, (drift_none, ymin_none)  # measured 0.112 / -0.110
+    drift_flip, _, _ = _hydrostatic_drift(cfg, spatial(lambda v: v[:, ::-1]), sc)
+    drift_swap, _, _ = _hydrostatic_drift(cfg, spatial(lambda v: v.transpose(0, 2, 1, 3, 4)), sc)
+    assert drift_flip > 0.5 and drift_swap > 0.5, (drift_flip, drift_swap)  # measured 2.05 / 1.44
