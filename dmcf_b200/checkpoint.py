@@ -99,31 +99,53 @@ def read_index(prefix):
                 continue  # BundleHeaderProto
             msg = _parse_proto(value)
             entries[key.decode()] = (msg.get(1, [0])[0], _shape(msg[2][0]) if 2 in msg else (), msg.get(4, [0])[0],
-                                     msg.get(5, [0])[0])
+                                     msg.get(5, [0])[0], msg.get(3, [0])[0])
     return entries
 
 
-def load_checkpoint(path):
+def resolve_prefix(path):
+    """Bundle prefix for ``path``: the prefix itself, or for a directory the bundle named by the CheckpointManager state file
+    ``checkpoint`` (``model_checkpoint_path: "ckpt-12"``, what ``manager.latest_checkpoint`` restores,
+    pipelines/base_pipeline.py:155-187), else the ``*.index`` with the largest trailing integer (ckpt-10 after ckpt-9)."""
+    import re
+    if not os.path.isdir(path):
+        return path
+    state = os.path.join(path, "checkpoint")
+    if os.path.exists(state):
+        with open(state) as fh:
+            m = re.search(r'^model_checkpoint_path:\s*"([^"]+)"', fh.read(), re.M)
+        if m:
+            cand = m.group(1) if os.path.isabs(m.group(1)) else os.path.join(path, m.group(1))
+            if os.path.exists(cand + ".index"):
+                return cand
+    cands = [f[:-6] for f in os.listdir(path) if f.endswith(".index")]
+    if not cands:
+        raise FileNotFoundError(f"no *.index in {path}")
+
+    def order(name):
+        nums = re.findall(r"\d+", name)
+        return (int(nums[-1]) if nums else -1, name)
+    return os.path.join(path, max(cands, key=order))
+
+
+def load_checkpoint(path, return_prefix=False):
     """Returns {variable path without '/.ATTRIBUTES/VARIABLE_VALUE': ndarray}; optimizer slots are dropped.
     ``path`` may be the bundle prefix ('.../ckpt') or the directory holding 'ckpt.index' (run_sample.py:184-197)."""
-    prefix = path
-    if os.path.isdir(path):
-        cands = sorted(f[:-6] for f in os.listdir(path) if f.endswith(".index"))
-        if not cands:
-            raise FileNotFoundError(f"no *.index in {path}")
-        prefix = os.path.join(path, cands[-1])
+    prefix = resolve_prefix(path)
     entries = read_index(prefix)
     with open(prefix + ".data-00000-of-00001", "rb") as fh:
         blob = fh.read()
     out = {}
     suffix = "/.ATTRIBUTES/VARIABLE_VALUE"
-    for key, (dt, shape, off, size) in entries.items():
+    for key, (dt, shape, off, size, _shard) in entries.items():
         if not key.endswith(suffix) or ".OPTIMIZER_SLOT" in key or dt not in _DTYPES:
             continue
+        if entries[key][4] != 0:
+            raise NotImplementedError(f"{key}: tensor lives in data shard {entries[key][4]}; only single-shard bundles are read")
         arr = np.frombuffer(blob, dtype=np.dtype(_DTYPES[dt]).newbyteorder("<"), count=int(np.prod(shape, dtype=np.int64)),
                             offset=off).reshape(shape)
         out[key[:-len(suffix)]] = arr.copy()
-    return out
+    return (out, prefix) if return_prefix else out
 
 
 def model_weights(ckpt):

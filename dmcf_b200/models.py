@@ -193,6 +193,11 @@ class PBFNet(BaseModel):
                 raise NotImplementedError("slab decomposition needs voxel-grid multi-scale sampling")
             if not self.use_bnds:
                 raise NotImplementedError("slab decomposition with use_bnds=False")
+            if self.transformation:
+                # the slab faces live in the un-transformed frame (migration compares them with inv_transformed positions)
+                # while halos / ownership inside the step would see translated / scaled / rotated positions
+                raise NotImplementedError("slab decomposition with a non-empty `transformation` (translate / scale / "
+                                          "grav_eqvar): ownership and halos would be evaluated in two different frames")
             self.fused = True
         self.slab = slab
 
@@ -213,6 +218,12 @@ class PBFNet(BaseModel):
 
     # -- physics: models/pbf_model.py:234-250 -----------------------------------------------------------------
     def integrate_pos_vel(self, pos1, vel1, acc1=None):
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (pos1, vel1, acc1)):
+            # training path (unrolled steps, pipelines/simulator.py:316-421): the same arithmetic in torch ops so that the loss of
+            # step t+1 reaches the correction of step t through pos / vel (d pos2 / d pos = I, d pos2 / d vel = dt)
+            a = acc1 if acc1 is not None else torch.tensor([0.0, self.grav, 0.0], dtype=pos1.dtype, device=pos1.device)
+            vel2 = vel1 + self.timestep * a
+            return pos1 + self.timestep * vel2, vel2
         return ops.integrate(pos1, vel1, acc1, (0.0, self.grav, 0.0), self.timestep)
 
     def compute_new_pos_vel(self, pos1, vel1, pos2, vel2, pos_correction):
@@ -234,6 +245,8 @@ class PBFNet(BaseModel):
                 acc = acc * s
         if "grav_eqvar" in tr:
             g = torch.tensor(tr["grav_eqvar"], dtype=torch.float32, device=dev)
+            if acc is None or acc.shape[0] == 0:
+                raise ValueError("grav_eqvar needs the per-particle acceleration of at least one particle (data[2])")
             self.R = align_vector(g, acc[0])
             pos, vel, acc, box, bfeats = pos @ self.R, vel @ self.R, acc @ self.R, box @ self.R, bfeats @ self.R
         return [pos, vel, acc, feats, box, bfeats]
@@ -545,7 +558,7 @@ class PBFNet(BaseModel):
         bounds, values = list(cfg["lr_boundaries"]), list(cfg["lr_values"])
         opt = torch.optim.Adam([p for p in self.parameters() if p.requires_grad], lr=values[0], eps=1e-6)
         import bisect
-        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: values[bisect.bisect_right(bounds, it)] / values[0])
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: values[bisect.bisect_left(bounds, it)] / values[0])
         return opt, sched
 
     @property
@@ -698,6 +711,13 @@ class HRNet(PBFNet):
         # cross-scale ones act on gathered / scattered rows (:100-113)
         return k > 0 or j == l or self._fps_scales()
 
+    def _set_key(self, inp_scale, out_scale):
+        """Step-cache key of the (input set, output set) pair of a conv: scale 0 is [fluid | boundary] with use_bnds and the
+        fluid rows alone without (preprocess stores the all->all list under (0, 0): the two must not collide)."""
+        if self.use_bnds:
+            return (inp_scale, out_scale)
+        return (("f", inp_scale), ("f", out_scale))
+
     def _fps_scales(self):
         return self.voxel_size is None and any(s != 1 for s in self.strides)
 
@@ -758,7 +778,7 @@ class HRNet(PBFNet):
                         o = buf if self.add_merge else buf[:, inp_scale * cw:(inp_scale + 1) * cw]
                         self.conv_block(self.convs[layer][scale][0][inp_scale],
                                         self.denses[layer][scale][0][inp_scale] if same else None, x, pos[inp_scale],
-                                        pos[scale], ext, (inp_scale, scale), relu=True, scale=importance,
+                                        pos[scale], ext, self._set_key(inp_scale, scale), relu=True, scale=importance,
                                         same_set=same, residual=res, out=o,
                                         accumulate=self.add_merge and inp_scale > 0, inp_scale=inp_scale)
                     ans.append(buf)
@@ -800,7 +820,7 @@ class HRNet(PBFNet):
                         res = ans_convs[-1][scale]
                     if self.fused:
                         ans[-1] = self.conv_block(self.convs[layer][scale][i][0], self.denses[layer][scale][i][0], x,
-                                                  pos[scale], pos[scale], ext, (scale, scale), relu=False,
+                                                  pos[scale], pos[scale], ext, self._set_key(scale, scale), relu=False,
                                                   scale=importance, same_set=True, residual=res, inp_scale=scale)
                     else:
                         a = self.convs[layer][scale][i][0](x * importance, pos[scale], pos[scale], ext, None)

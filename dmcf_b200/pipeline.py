@@ -37,17 +37,23 @@ def _generator_args(pipeline_cfg, split):
     for other in ("train", "valid", "test"):
         gen.pop(other, None)
     gen.update(per_split)
+    # options the reference forwards to PhysicsSimDataFlow that CHANGE the sequences (sub-sampled particles, dropped leading
+    # frames, rotated gravity): not implemented here -- refuse instead of silently rolling out different data
+    for k, neutral in (("sample_cnt", (None, 0)), ("pre_frames", (None, 0)), ("grav_eqvar", (None, False))):
+        if gen.get(k) not in neutral:
+            raise NotImplementedError(f"data_generator option {k}={gen[k]!r} is not supported by get_rollout")
     for k in ("repeat", "shuffle_buffer", "is2d", "num_workers", "sample_cnt", "augment", "eval_stride", "batch_size", "window",
-              "pre_frames"):
+              "pre_frames", "grav_eqvar"):
         gen.pop(k, None)  # data-flow options of the training loader, not of get_rollout
     if isinstance(gen.get("scale"), (list, tuple)):
         gen["scale"] = np.asarray(gen["scale"], np.float32)
     return gen, per_split
 
 
-def run_test(sim, dataset, pipeline_cfg, out_dir, epoch=0, compute_metric=None):
+def run_test(sim, dataset, pipeline_cfg, out_dir, epoch=0, compute_metric=None, valid_dataset=None):
     """pipelines/simulator.py:110-158.  Returns the list of written files (and the validation dict when
-    ``test_compute_metric`` is set, :157-158)."""
+    ``test_compute_metric`` is set, :157-158).  The reference's run_valid always rolls out ``dataset.valid``: pass that split
+    as ``valid_dataset``; without it the metrics are computed on the test split (logged as a deviation)."""
     gen, _ = _generator_args(pipeline_cfg, "test")
     test_data = datasets.get_rollout(dataset, **gen)
     if not test_data:
@@ -68,7 +74,10 @@ def run_test(sim, dataset, pipeline_cfg, out_dir, epoch=0, compute_metric=None):
                 os.remove(f)
     valid = None
     if compute_metric if compute_metric is not None else pipeline_cfg.get("test_compute_metric", False):
-        valid = run_valid(sim, dataset, pipeline_cfg, epoch, split="test")
+        if valid_dataset is None:
+            log.warning("test_compute_metric: no validation split given, computing the metrics on the test split")
+        valid = run_valid(sim, valid_dataset if valid_dataset is not None else dataset, pipeline_cfg, epoch,
+                          split="valid" if valid_dataset is not None else "test")
     return written, valid
 
 

@@ -83,10 +83,11 @@ class Simulator:
         if ckpt_path is None:
             log.info("Initializing from scratch.")
             return 0
-        weights = model_weights(load_checkpoint(ckpt_path))
+        ckpt, prefix = load_checkpoint(ckpt_path, return_prefix=True)
+        weights = model_weights(ckpt)
         missing = self.model.load_weights(weights, device=self.device)
         if missing:
             log.warning("layers without checkpoint weights: %s", missing)
         log.info("Restored from {}".format(ckpt_path))
-        nums = re.findall(r"\d+", str(ckpt_path).split("/")[-1])
+        nums = re.findall(r"\d+", str(prefix).split("/")[-1])  # epoch from the bundle that was restored ("ckpt-12")
         return int(nums[-1]) if nums else 0

@@ -15,14 +15,74 @@ are a few MB per face per layer, i.e. latency bound, so they are batched into on
 """
 from __future__ import annotations
 
+import queue
+import threading
+
 import torch
 import torch.distributed as dist
 
 
-class SlabContext:
-    def __init__(self, faces, axis=0, group=None, rank=None, world_size=None):
-        """``faces``: world_size+1 increasing coordinates (use -inf / +inf for the outer ones)."""
+class DistTransport:
+    """The production transport: torch.distributed point-to-point / all-reduce (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
         self.group = group
+
+    def all_reduce(self, rank, t, op):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def sendrecv(self, rank, sends, recvs):
+        """``sends`` / ``recvs``: {peer rank: tensor}; receives are filled in place.  One batched isend/irecv group."""
+        ops = []
+        for peer, t in sends.items():
+            if t.numel():
+                ops.append(dist.P2POp(dist.isend, t, peer, self.group))
+        for peer, t in recvs.items():
+            if t.numel():
+                ops.append(dist.P2POp(dist.irecv, t, peer, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+
+class LocalTransport:
+    """In-process stand-in for torch.distributed: ``world`` SlabContexts, each driven by its own Python thread on ONE device
+    (the default stream orders the work of all threads, and a tensor is handed over only after its producer kernels were
+    enqueued).  Lets the 2-slab == 1-slab parity test run on a single GPU (tests/test_slab_gpu.py) and the halo / migration
+    logic on CPU tensors."""
+
+    def __init__(self, world):
+        self.world = world
+        self._barrier = threading.Barrier(world)
+        self._slots = [None] * world
+        self._q = {(a, b): queue.Queue() for a in range(world) for b in range(world) if a != b}
+
+    def all_reduce(self, rank, t, op):
+        self._slots[rank] = t.clone()
+        self._barrier.wait()
+        parts = torch.stack(list(self._slots))
+        res = parts.amax(dim=0) if op == "max" else parts.sum(dim=0)
+        self._barrier.wait()  # every rank has read the slots before anyone overwrites them
+        t.copy_(res)
+        return t
+
+    def sendrecv(self, rank, sends, recvs):
+        for peer, t in sends.items():
+            self._q[(rank, peer)].put(t.clone())
+        for peer, t in recvs.items():
+            src = self._q[(peer, rank)].get(timeout=120)
+            if src.shape != t.shape:
+                raise RuntimeError(f"LocalTransport: rank {rank} expected {tuple(t.shape)} from {peer}, got {tuple(src.shape)}")
+            t.copy_(src)
+
+
+class SlabContext:
+    def __init__(self, faces, axis=0, group=None, rank=None, world_size=None, transport=None):
+        """``faces``: world_size+1 increasing coordinates (use -inf / +inf for the outer ones).  ``transport``: a
+        LocalTransport shared by the ranks of a single-process run (then ``rank`` / ``world_size`` are required)."""
+        self.group = group
+        self.transport = transport if transport is not None else DistTransport(group)
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world_size is None else world_size
         if len(faces) != self.world + 1:
@@ -57,12 +117,12 @@ class SlabContext:
         if self.world == 1:
             return lo, hi
         buf = torch.cat([-lo, hi]).contiguous()
-        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=self.group)
+        self.transport.all_reduce(self.rank, buf, "max")
         return -buf[:3], buf[3:]
 
     def all_reduce_sum(self, t):
         if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            self.transport.all_reduce(self.rank, t, "sum")
         return t
 
     def _exchange(self, to_left, to_right, n_from_left=None, n_from_right=None):
@@ -74,34 +134,22 @@ class SlabContext:
             cnt_out = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=dev)
             cnt_l = torch.zeros(1, dtype=torch.int64, device=dev)
             cnt_r = torch.zeros(1, dtype=torch.int64, device=dev)
-            ops = []
+            sends, recvs = {}, {}
             if self.left is not None:
-                ops += [dist.P2POp(dist.isend, cnt_out[0:1], self.left, self.group),
-                        dist.P2POp(dist.irecv, cnt_l, self.left, self.group)]
+                sends[self.left], recvs[self.left] = cnt_out[0:1], cnt_l
             if self.right is not None:
-                ops += [dist.P2POp(dist.isend, cnt_out[1:2], self.right, self.group),
-                        dist.P2POp(dist.irecv, cnt_r, self.right, self.group)]
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
+                sends[self.right], recvs[self.right] = cnt_out[1:2], cnt_r
+            self.transport.sendrecv(self.rank, sends, recvs)
             n_from_left, n_from_right = int(cnt_l.item()), int(cnt_r.item())
         from_left = torch.empty((n_from_left, *cols), dtype=dt, device=dev)
         from_right = torch.empty((n_from_right, *cols), dtype=dt, device=dev)
-        ops = []
         to_left, to_right = to_left.contiguous(), to_right.contiguous()
+        sends, recvs = {}, {}
         if self.left is not None:
-            if to_left.numel():
-                ops.append(dist.P2POp(dist.isend, to_left, self.left, self.group))
-            if from_left.numel():
-                ops.append(dist.P2POp(dist.irecv, from_left, self.left, self.group))
+            sends[self.left], recvs[self.left] = to_left, from_left
         if self.right is not None:
-            if to_right.numel():
-                ops.append(dist.P2POp(dist.isend, to_right, self.right, self.group))
-            if from_right.numel():
-                ops.append(dist.P2POp(dist.irecv, from_right, self.right, self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            sends[self.right], recvs[self.right] = to_right, from_right
+        self.transport.sendrecv(self.rank, sends, recvs)
         self.bytes_exchanged += (to_left.numel() + to_right.numel()) * to_left.element_size()
         return from_left, from_right, n_from_left, n_from_right
 

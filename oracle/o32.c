@@ -286,6 +286,67 @@ void o32_continuous_conv(const float* filters, int kz, int ky, int kx, int cin, 
                 norm[m] = nrm;
             }
             /* out[nb x cout] = B[nb x KC] * filters[KC x cout] */
+#ifdef O32_TIMED
+            /* timed build (libo32_timed.so, bench.py's CPU arm only): the same product as a register-blocked micro-kernel,
+             * 4 out points x 16 channels of accumulators, FMA contraction allowed (-ffp-contract=fast) -- Open3D hands this
+             * product to a BLAS-class GEMM, so the baseline is not handicapped by a scalar read-modify-write loop.  Results
+             * differ from the parity build by float32 rounding only (tests/test_oracle_cpu.py). */
+            for (int m0 = 0; m0 < nb; m0 += 4) {
+                const int mr = nb - m0 < 4 ? nb - m0 : 4;
+                const float* Br[4];
+                for (int r = 0; r < 4; ++r) Br[r] = B + (size_t)(m0 + (r < mr ? r : 0)) * KC;
+                for (int cb = 0; cb < cout; cb += 16) {
+                    const int cw = cout - cb < 16 ? cout - cb : 16;
+                    float acc[4][16];
+                    if (cw == 16) {
+                        /* GCC vector extension: 8 accumulators of 8 floats stay in ymm registers */
+                        typedef float v8f __attribute__((vector_size(32), aligned(4)));
+                        v8f a00 = {0}, a01 = {0}, a10 = {0}, a11 = {0}, a20 = {0}, a21 = {0}, a30 = {0}, a31 = {0};
+                        const float* restrict wp = filters + cb;
+                        for (int64_t k = 0; k < KC; ++k, wp += cout) {
+                            const v8f w0 = *(const v8f*)wp, w1 = *(const v8f*)(wp + 8);
+                            const float s0 = Br[0][k], s1 = Br[1][k], s2 = Br[2][k], s3 = Br[3][k];
+                            const v8f v0 = {s0, s0, s0, s0, s0, s0, s0, s0}, v1 = {s1, s1, s1, s1, s1, s1, s1, s1};
+                            const v8f v2 = {s2, s2, s2, s2, s2, s2, s2, s2}, v3 = {s3, s3, s3, s3, s3, s3, s3, s3};
+                            a00 += v0 * w0; a01 += v0 * w1; a10 += v1 * w0; a11 += v1 * w1;
+                            a20 += v2 * w0; a21 += v2 * w1; a30 += v3 * w0; a31 += v3 * w1;
+                        }
+                        *(v8f*)&acc[0][0] = a00; *(v8f*)&acc[0][8] = a01; *(v8f*)&acc[1][0] = a10; *(v8f*)&acc[1][8] = a11;
+                        *(v8f*)&acc[2][0] = a20; *(v8f*)&acc[2][8] = a21; *(v8f*)&acc[3][0] = a30; *(v8f*)&acc[3][8] = a31;
+                    } else if (cw == 8) {
+                        typedef float v8f __attribute__((vector_size(32), aligned(4)));
+                        v8f a0 = {0}, a1 = {0}, a2 = {0}, a3 = {0};
+                        const float* restrict wp = filters + cb;
+                        for (int64_t k = 0; k < KC; ++k, wp += cout) {
+                            const v8f w0 = *(const v8f*)wp;
+                            const float s0 = Br[0][k], s1 = Br[1][k], s2 = Br[2][k], s3 = Br[3][k];
+                            a0 += (v8f){s0, s0, s0, s0, s0, s0, s0, s0} * w0; a1 += (v8f){s1, s1, s1, s1, s1, s1, s1, s1} * w0;
+                            a2 += (v8f){s2, s2, s2, s2, s2, s2, s2, s2} * w0; a3 += (v8f){s3, s3, s3, s3, s3, s3, s3, s3} * w0;
+                        }
+                        *(v8f*)&acc[0][0] = a0; *(v8f*)&acc[1][0] = a1; *(v8f*)&acc[2][0] = a2; *(v8f*)&acc[3][0] = a3;
+                    } else {
+                        for (int r = 0; r < 4; ++r)
+                            for (int c = 0; c < 16; ++c) acc[r][c] = 0.0f;
+                        for (int64_t k = 0; k < KC; ++k) {
+                            const float* restrict wrow = filters + k * cout + cb;
+                            for (int r = 0; r < 4; ++r) {
+                                const float v = Br[r][k];
+                                for (int c = 0; c < cw; ++c) acc[r][c] += v * wrow[c];
+                            }
+                        }
+                    }
+                    for (int r = 0; r < mr; ++r)
+                        for (int c = 0; c < cw; ++c) out[(b0 + m0 + r) * cout + cb + c] = acc[r][c];
+                }
+            }
+            if (normalize)
+                for (int m = 0; m < nb; ++m) {
+                    float* dst = out + (b0 + m) * cout;
+                    const float nv = nbr_importance ? norm[m] : (float)(row_splits[b0 + m + 1] - row_splits[b0 + m]);
+                    if (nv != 0.0f)
+                        for (int co = 0; co < cout; ++co) dst[co] /= nv;
+                }
+#else
             for (int m = 0; m < nb; ++m) {
                 float* dst = out + (b0 + m) * cout;
                 for (int co = 0; co < cout; ++co) dst[co] = 0.0f;
@@ -302,6 +363,7 @@ void o32_continuous_conv(const float* filters, int kz, int ky, int kx, int cin, 
                         for (int co = 0; co < cout; ++co) dst[co] /= nv;
                 }
             }
+#endif
         }
         free(B);
     }

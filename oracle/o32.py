@@ -17,7 +17,16 @@ from . import o64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_VARIANT = "libo32.so"
 F32 = np.float32
+
+
+def use_timed_build(flag=True):
+    """bench.py's CPU arm: switch to libo32_timed.so (same source; FMA contraction allowed, register-blocked patch x filter
+    product).  The parity tests keep the default build (-ffp-contract=off)."""
+    global _LIB, _VARIANT
+    _VARIANT = "libo32_timed.so" if flag else "libo32.so"
+    _LIB = None
 
 
 def build():
@@ -28,7 +37,7 @@ def build():
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "libo32.so")
+        path = os.path.join(_HERE, _VARIANT)
         if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "o32.c")):
             build()
         L = C.CDLL(path)

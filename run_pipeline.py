@@ -9,6 +9,7 @@ bnd, the reference's dataset names); ``--split valid`` prints the metric means o
 scope: the training STEP exists (dmcf_b200/training.py), the curriculum around it does not."""
 import argparse
 import json
+import os
 import logging
 import sys
 
@@ -39,7 +40,11 @@ def main(argv=None):
     dataset = pipeline.open_split(cfg["dataset"], args.split)
     out_dir = args.output_dir or cfg["pipeline"].get("output_dir", "./output")
     if args.split == "test":
-        written, valid = pipeline.run_test(sim, dataset, cfg["pipeline"], out_dir, epoch)
+        valid_ds = None
+        if cfg["pipeline"].get("test_compute_metric", False):  # the reference's run_valid rolls out dataset.valid
+            vdir = os.path.join(cfg["dataset"].get("dataset_path") or "", "valid")
+            valid_ds = pipeline.open_split(cfg["dataset"], "valid") if os.path.isdir(vdir) else None
+        written, valid = pipeline.run_test(sim, dataset, cfg["pipeline"], out_dir, epoch, valid_dataset=valid_ds)
         print("\n".join(written))
         if valid is not None:
             print(json.dumps(valid))

@@ -183,3 +183,54 @@ def test_model_gradients_and_train_step(cuda):
     tgt = torch.stack([sample[0], t(target)])
     losses = [training.train_step(model, opt, [sample], [tgt], grad_clip_norm=1.0, scheduler=sched)[0] for _ in range(6)]
     assert losses[-1] < losses[0]
+
+
+def test_two_unrolled_steps_carry_the_gradient_through_pos_and_vel(cuda):
+    """pipelines/simulator.py:316-421 unrolls T steps under one GradientTape: the loss of step 2 reaches the parameters through
+    the step-1 outputs as well (pos2 = pos1 + dt * (vel1 + dt * g) + corr2, vel1 = (pos1 - pos0) / dt: d pos2 / d corr1 = 2 I plus
+    the velocity features).  The integrate / correct kernels have no autograd, so on the training path they must run as torch
+    ops.  Check: gradient of the 2-step loss == direct step-2 gradient + step-1 vector-Jacobian product with the cotangents
+    autograd reports for the step-2 inputs; the position cotangent is exactly d loss / d pos2 (the conv geometry carries no
+    position gradient, like Open3D's op)."""
+    from dmcf_b200 import config, scenes
+    cfg = dict(name="SymNet", layer_channels=[[[4]], [[8]], [[8]], [[3]]], kernel_size=[4, 4, 4], sym_kernel_size=[6, 6, 6],
+               coordinate_mapping=MAP, interpolation="linear", window="poly6", window_sym="peak", strides=[1],
+               particle_radii=[0.1], timestep=0.02, grav=-9.81, out_scale=[0.0078125] * 3, sym_axis=1, add_merge=True,
+               use_acc=False)
+    scene = scenes.lattice_scene((6, 5, 5), dx=0.05, seed=9, open_top=True)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(cuda)
+    model = config.build_model(cfg)
+    model.init_weights(seed=4, device=cuda, scale=0.2)
+    model.set_trainable(True)
+    params = [p for p in model.parameters() if p.requires_grad]
+    sample = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
+    target = t(scene["pos"] + np.array([0, -0.012, 0], np.float32))
+
+    def loss_of(pos):
+        return ((((target - pos) ** 2).sum(-1) + 1e-9) ** 0.5).mean()
+
+    # (a) two unrolled steps, one backward
+    p1, v1 = model(sample, training=True)
+    p2, _ = model([p1, v1] + sample[2:], training=True)
+    g_total = torch.autograd.grad(loss_of(p2), params, allow_unused=True)
+    # (b) step 2 alone on leaf copies of the step-1 outputs
+    p1l, v1l = p1.detach().requires_grad_(True), v1.detach().requires_grad_(True)
+    p2b, _ = model([p1l, v1l] + sample[2:], training=True)
+    p2b.retain_grad()
+    lb = loss_of(p2b)
+    g2 = torch.autograd.grad(lb, params + [p1l, v1l, p2b], allow_unused=True)
+    c_pos, c_vel, dl_dp2 = g2[-3], g2[-2], g2[-1]
+    assert torch.equal(c_pos, dl_dp2)  # identity path only
+    assert float((c_vel - model.timestep * dl_dp2).abs().max()) > 0  # plus the velocity features of step 2
+    # (c) step-1 vector-Jacobian product with those cotangents
+    g1 = torch.autograd.grad([p1, v1], params, grad_outputs=[c_pos, c_vel], allow_unused=True)
+    n_through = 0
+    for gt, ga, gb in zip(g_total, g2[:len(params)], g1):
+        if gt is None:
+            assert ga is None and gb is None
+            continue
+        exp = (ga if ga is not None else 0) + (gb if gb is not None else 0)
+        assert torch.allclose(gt, exp, rtol=1e-4, atol=1e-7 + 1e-5 * float(exp.abs().max()))
+        if gb is not None and float(gb.abs().max()) > 0:
+            n_through += 1
+    assert n_through >= 4  # the step-1 path is really there (it was silently cut when integrate ran as a raw kernel)

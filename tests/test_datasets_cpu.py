@@ -68,3 +68,15 @@ def test_reads_the_reference_encoding_fixture():
                                      [(f["pos"][None], {"name": "pred", "type": "PARTICLE"})])
         r = np.load(out)
         assert r["SymNet/pred"].shape == (1,) + z["pos"].shape and str(r["SymNet/pred@type"]) == "PARTICLE"
+
+
+def test_checkpoint_directory_resolves_like_checkpoint_manager(tmp_path):
+    """pipelines/base_pipeline.py:155-187 restores manager.latest_checkpoint: the bundle named by the `checkpoint` state file,
+    else the highest trailing number (ckpt-10 after ckpt-9, not lexicographic)."""
+    from dmcf_b200.checkpoint import resolve_prefix
+    for n in (2, 9, 10):
+        (tmp_path / f"ckpt-{n}.index").write_bytes(b"")
+    assert resolve_prefix(str(tmp_path)).endswith("ckpt-10")
+    (tmp_path / "checkpoint").write_text('model_checkpoint_path: "ckpt-9"\nall_model_checkpoint_paths: "ckpt-2"\n')
+    assert resolve_prefix(str(tmp_path)).endswith("ckpt-9")
+    assert resolve_prefix(str(tmp_path / "ckpt-2")) == str(tmp_path / "ckpt-2")

@@ -188,6 +188,23 @@ def test_cconv_baseline_model(cuda):
     run_case(cuda, cconv_cfg(), scene, tol_scale=4.0)
 
 
+@pytest.mark.parametrize("name", ["HRNet", "SymNet"])
+def test_multiscale_stack_without_boundary_rows(cuda, name):
+    """use_bnds=False (models/hrnet.py:71-72, models/sym_net.py:60-61): the conv stack runs on the fluid rows only while the input
+    convs (and the antisymmetric layer) still see [fluid | boundary].  The fused step must not reuse the all->all neighbour list
+    of preprocess for the fluid->fluid convs of scale 0 (they share a scale index)."""
+    from dmcf_b200 import scenes
+    scene = scenes.lattice_scene((10, 9, 8), dx=0.05, seed=7)
+    cfg = dict(liquid3d_cfg(), name=name, use_bnds=False)
+    if name == "HRNet":
+        cfg["layer_channels"] = cfg["layer_channels"][:-2] + [[[3]]]
+        for k in ("sym_kernel_size", "sym_axis", "window_sym"):
+            cfg.pop(k)
+    else:  # the antisymmetric layer concatenates the boundary rows of the INPUT features: channel counts must agree (3 * 8)
+        cfg["layer_channels"] = [[[8]], [[16], [8], [4]], [[24]], [[3]]]
+    run_case(cuda, cfg, scene, tol_scale=2.0)
+
+
 def test_free_fall_reduces_to_integration(cuda):
     """No neighbours, zero weights in the last layer -> pure integration (datasets/free_fall_gen.py:19-27 mode 0)."""
     from dmcf_b200 import config, scenes

@@ -108,3 +108,61 @@ def test_two_rank_slab_matches_single_process(tmp_path):
     assert np.all(np.abs(c.sum(0)) <= 1e-9 * np.abs(c).sum(0))
     # migration kept every particle exactly once and on the rank that owns its new position
     assert len(mig) == len(pts)
+
+
+def test_local_transport_three_ranks_in_one_process():
+    """The in-process transport (ranks as threads) that lets the GPU slab parity test run on a 1-GPU box: bbox all-reduce,
+    position / feature halos and migration on CPU tensors against the undivided point set."""
+    import threading
+    from dmcf_b200.slab import LocalTransport, SlabContext
+    pts, feats, *_ = make_problem()
+    world, radius = 3, 0.1
+    tr = LocalTransport(world)
+    faces = SlabContext.uniform_faces(float(pts[:, 0].min()), float(pts[:, 0].max()) + 1e-3, world)
+    out, errs = [None] * world, []
+
+    def body(rank):
+        try:
+            slab = SlabContext(faces, axis=0, rank=rank, world_size=world, transport=tr)
+            P = torch.from_numpy(pts)
+            own = slab.owned_mask(P)
+            p_own, f_own = P[own], torch.from_numpy(feats)[own]
+            lo, hi = slab.all_reduce_minmax(p_own.amin(0), p_own.amax(0))
+            plan = slab.make_halo(p_own, radius)
+            ghost_f = plan.feature_halo(f_own)
+            moved = p_own + torch.tensor([0.11, 0.0, 0.0])
+            mp_, mf_ = slab.migrate(moved, f_own)
+            out[rank] = dict(lo=lo, hi=hi, own=own, ghost_pos=plan.ghost_pos, ghost_f=ghost_f, mig_pos=mp_, mig_f=mf_, slab=slab)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+            tr._barrier.abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=120)
+    assert not errs, errs
+    P, F = torch.from_numpy(pts), torch.from_numpy(feats)
+    n_mig = 0
+    for r, z in enumerate(out):
+        assert torch.equal(z["lo"], P.amin(0)) and torch.equal(z["hi"], P.amax(0))
+        slab = z["slab"]
+        # every ghost is a point of a neighbouring slab within the padded radius of the shared face, with its own features
+        key = {}
+        for i, p in enumerate(P):  # wall particles of different faces coincide on the box edges: a position may have several rows
+            key.setdefault(tuple(p.tolist()), []).append(i)
+        for gp, gf in zip(z["ghost_pos"], z["ghost_f"]):
+            cand = key[tuple(gp.tolist())]
+            assert any((not bool(z["own"][i])) and torch.equal(F[i], gf) for i in cand)
+            assert min(abs(float(gp[0]) - slab.lo), abs(float(gp[0]) - slab.hi)) <= radius * 1.001 + 1e-5
+        # and every such point is among the ghosts
+        x = P[:, 0]
+        near = (~z["own"]) & (((x >= slab.lo - radius) & (x < slab.lo)) | ((x < slab.hi + radius) & (x >= slab.hi)))
+        assert int(near.sum()) <= len(z["ghost_pos"])
+        assert bool(slab.owned_mask(z["mig_pos"]).all())
+        n_mig += len(z["mig_pos"])
+    moved_all = P + torch.tensor([0.11, 0.0, 0.0])
+    assert n_mig == len(P)
+    got = torch.cat([z["mig_pos"] for z in out])
+    assert torch.equal(got[got[:, 0].argsort(stable=True)][:, 0], moved_all[moved_all[:, 0].argsort(stable=True)][:, 0])

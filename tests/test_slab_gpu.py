@@ -23,6 +23,34 @@ def model_cfg(kind):
     return T.liquid3d_cfg(), T.load_npz_weights("ckpt_Liquid3d.npz")
 
 
+def run_rank(rank, dev, slab, kind):
+    """One rank's share of the scene through its own model + Simulator; returns what the comparison needs."""
+    from dmcf_b200 import config
+    from dmcf_b200.simulator import Simulator
+    sc = global_scene()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    pos, box = t(sc["pos"]), t(sc["box"])
+    own_f, own_b = slab.owned_mask(pos), slab.owned_mask(box)
+    ids = torch.nonzero(own_f).flatten()
+    if os.path.join(ROOT, "tests") not in sys.path:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+    cfg, weights = model_cfg(kind)
+    model = config.build_model(cfg)
+    if weights is None:
+        model.init_weights(seed=0, device=dev, scale=0.1)
+    else:
+        model.load_weights(weights, device=dev)
+    model.set_slab(slab)
+    Simulator(model, device=str(dev))
+    sample = [pos[own_f], t(sc["vel"])[own_f], None, None, box[own_b], t(sc["box_normals"])[own_b]]
+    with torch.no_grad():
+        p1, v1 = model(sample)
+    net = model.net_out[: int(own_f.sum())].cpu().numpy()
+    return dict(ids=ids.cpu().numpy(), pos=p1.cpu().numpy(), vel=v1.cpu().numpy(), net=net,
+                net_sum=model.net_out.double().sum(0).cpu().numpy(), net_abs=model.net_out.double().abs().sum(0).cpu().numpy(),
+                bytes=slab.bytes_exchanged)
+
+
 def worker(rank, world, port, out_dir, kind):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -31,35 +59,75 @@ def worker(rank, world, port, out_dir, kind):
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    from dmcf_b200 import config, scenes
-    from dmcf_b200.simulator import Simulator
     from dmcf_b200.slab import SlabContext
-    sc = global_scene()
     faces = SlabContext.uniform_faces(0.0, 28 * 0.05, world)
-    slab = SlabContext(faces, axis=0)
+    res = run_rank(rank, dev, SlabContext(faces, axis=0), kind)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def undivided_reference(kind, dev):
+    from dmcf_b200 import config
+    sc = global_scene()
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
-    pos, box = t(sc["pos"]), t(sc["box"])
-    own_f, own_b = slab.owned_mask(pos), slab.owned_mask(box)
-    ids = torch.nonzero(own_f).flatten()
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     cfg, weights = model_cfg(kind)
     model = config.build_model(cfg)
     if weights is None:
         model.init_weights(seed=0, device=dev, scale=0.1)
     else:
         model.load_weights(weights, device=dev)
-    model.set_slab(slab)
-    sim = Simulator(model, device=f"cuda:{rank}")
-    sample = [pos[own_f], t(sc["vel"])[own_f], None, t(ids.float().cpu().numpy()[:, None]), box[own_b], t(sc["box_normals"])[own_b]]
-    p1, v1 = model(sample[:3] + [None] + sample[4:])
-    net = model.net_out[: int(own_f.sum())].cpu().numpy()
-    n_own = model.net_out.shape[0]
-    full_net_sum = model.net_out.double().sum(0).cpu().numpy()
-    full_net_abs = model.net_out.double().abs().sum(0).cpu().numpy()
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ids=ids.cpu().numpy(), pos=p1.cpu().numpy(), vel=v1.cpu().numpy(), net=net,
-             net_sum=full_net_sum, net_abs=full_net_abs, bytes=slab.bytes_exchanged)
-    dist.barrier()
-    dist.destroy_process_group()
+    with torch.no_grad():
+        p_ref, v_ref = model([t(sc["pos"]), t(sc["vel"]), None, None, t(sc["box"]), t(sc["box_normals"])])
+    return p_ref.cpu().numpy(), v_ref.cpu().numpy()
+
+
+def check_ranks(ranks, p_ref, v_ref, kind):
+    seen = np.zeros(len(p_ref), bool)
+    tot_sum, tot_abs = 0.0, 0.0
+    for r, z in enumerate(ranks):
+        ids = z["ids"]
+        assert not seen[ids].any()
+        seen[ids] = True
+        assert np.abs(z["pos"] - p_ref[ids]).max() <= (2e-6 if kind == "c4" else 1e-5), r
+        assert np.abs(z["vel"] - v_ref[ids]).max() <= (2e-6 if kind == "c4" else 1e-5) / 0.02 * 2, r
+        tot_sum, tot_abs = tot_sum + z["net_sum"], tot_abs + z["net_abs"]
+        assert int(z["bytes"]) > 0
+    assert seen.all()
+    # momentum conservation across the slabs (fluid + boundary rows of all ranks)
+    assert np.all(np.abs(tot_sum) <= 2e-5 * tot_abs + 1e-6)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("kind", ["c4", "liquid3d_multiscale"])
+def test_slabs_on_one_gpu_match_undivided(kind, world):
+    """The same slab code (ownership, halo plans, per-layer feature halos, global bbox / mean reductions) with the ranks as
+    threads of ONE process on ONE GPU and an in-process transport instead of NCCL: runs on a 1-GPU box."""
+    import threading
+    from dmcf_b200.slab import LocalTransport, SlabContext
+    dev = torch.device("cuda:0")
+    tr = LocalTransport(world)
+    faces = SlabContext.uniform_faces(0.0, 28 * 0.05, world)
+    out, errs = [None] * world, []
+
+    def body(rank):
+        try:
+            torch.cuda.set_device(0)
+            out[rank] = run_rank(rank, dev, SlabContext(faces, axis=0, rank=rank, world_size=world, transport=tr), kind)
+        except BaseException as e:  # noqa: BLE001 -- re-raised in the main thread
+            errs.append(e)
+            tr._barrier.abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=500)
+    if errs:
+        raise errs[0]
+    p_ref, v_ref = undivided_reference(kind, dev)
+    check_ranks(out, p_ref, v_ref, kind)
 
 
 @pytest.mark.timeout(600)
@@ -71,27 +139,5 @@ def test_two_gpu_slab_matches_single_gpu(tmp_path, kind):
     from dmcf_b200 import config, scenes
     port = 29700 + os.getpid() % 2000 + (7 if kind == "c4" else 0)
     mp.spawn(worker, args=(2, port, str(tmp_path), kind), nprocs=2, join=True)
-    dev = torch.device("cuda:0")
-    sc = global_scene()
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
-    cfg, weights = model_cfg(kind)
-    model = config.build_model(cfg)
-    if weights is None:
-        model.init_weights(seed=0, device=dev, scale=0.1)
-    else:
-        model.load_weights(weights, device=dev)
-    p_ref, v_ref = model([t(sc["pos"]), t(sc["vel"]), None, None, t(sc["box"]), t(sc["box_normals"])])
-    p_ref, v_ref = p_ref.cpu().numpy(), v_ref.cpu().numpy()
-    seen = np.zeros(len(p_ref), bool)
-    tot_sum, tot_abs = 0.0, 0.0
-    for r in range(2):
-        z = np.load(tmp_path / f"rank{r}.npz")
-        ids = z["ids"]
-        seen[ids] = True
-        assert np.abs(z["pos"] - p_ref[ids]).max() <= (2e-6 if kind == "c4" else 1e-5), r
-        assert np.abs(z["vel"] - v_ref[ids]).max() <= (2e-6 if kind == "c4" else 1e-5) / 0.02 * 2, r
-        tot_sum, tot_abs = tot_sum + z["net_sum"], tot_abs + z["net_abs"]
-        assert int(z["bytes"]) > 0
-    assert seen.all()
-    # momentum conservation across the two slabs (fluid + boundary rows of both ranks)
-    assert np.all(np.abs(tot_sum) <= 2e-5 * tot_abs + 1e-6)
+    p_ref, v_ref = undivided_reference(kind, torch.device("cuda:0"))
+    check_ranks([dict(np.load(tmp_path / f"rank{r}.npz")) for r in range(2)], p_ref, v_ref, kind)
