@@ -4,12 +4,14 @@ Workload (config 4 of BASELINE.json): synthetic 3-D box of jittered-lattice flui
 particles, single-scale SymNet = input convs -> 3x ContinuousConv(4x4x4, ->32) + Dense -> antisymmetric
 ContinuousConv(6x6x6, 32->3), seeded random weights.  One "step" = one full model step (integrate, cull, neighbour
 search, conv stack, correction) on the resident scene; every step starts from the same state so the work per step is
-fixed.  Weak scaling: every rank owns one n_side^3 box (a slab of the global domain).
+fixed.  N > 1 (torchrun, one rank per GPU): STRONG scaling of that one ~1 M-particle scene -- slabs of n_side / N lattice layers
+along x with halo exchange -- is the headline (`"scaling": "strong"`); the weak-scaling run (every rank owns an n_side^3 slab
+of an N times longer box) rides along as the extra key `weak`.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n-side 100] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n-side 100] [--impl ours|reference] [--scaling strong|weak|both]
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference path (oracle O32, all
-host threads) on a bounded sub-volume of the same workload.
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference path (oracle O32 timed build, all
+host threads, thread count set explicitly) on the same full scene; steps are cut to a 150 s budget.
 """
 from __future__ import annotations
 
@@ -108,43 +110,70 @@ def oracle_weights(model):
     return w
 
 
-def cpu_baseline(n_side_sample, steps, warmup, seed=0):
-    """Times the O32 restatement of the reference step (one search per conv, two-pass ASCC) on the host cores."""
-    import torch
+def host_threads():
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, so the CPU arm sets its OpenMP
+    thread count explicitly (and prints it) instead of inheriting that."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(n_side_sample, steps, warmup, seed=0, budget_s=None):
+    """Times the O32 restatement of the reference step (one search per conv, two-pass ASCC, separate Dense / relu / add) on the
+    host cores: the TIMED build of oracle/o32.c (FMA contraction allowed, register-blocked patch x filter product), all host
+    threads.  ``budget_s``: stop adding timed steps once the budget is used (at least one step is always timed)."""
     from dmcf_b200 import config
     from oracle import o32
+    o32.use_timed_build(True)
+    o32.set_num_threads(host_threads())
     scene, cfg = build_workload(n_side_sample, seed)
     model = config.build_model(cfg)
     model.init_weights(seed=0, device="cpu", scale=0.1)
     ref = o32.ModelO32(cfg, oracle_weights(model))
     n = scene["pos"].shape[0]
     times = []
+    t_start = time.time()
     for i in range(warmup + steps):
         t0 = time.time()
         ref(scene["pos"], scene["vel"], None, scene["box"], scene["box_normals"])
         if i >= warmup:
             times.append(time.time() - t0)
+        if budget_s is not None and times and time.time() - t_start + times[-1] > budget_s:
+            break
     sec = float(np.mean(times))
     return {"value": n / sec, "unit": UNIT, "cores": o32.num_threads(), "kind": "port",
             "sample": f"{n_side_sample}^3 = {n} fluid particles + {scene['box'].shape[0]} wall particles, same net/seed, "
-                      f"{steps} step(s) after {warmup} warm-up, {sec:.2f} s/step (oracle O32: C/OpenMP float32 restatement, "
-                      "one neighbour search per conv like the reference)"}, sec
+                      f"{len(times)} step(s) after {warmup} warm-up, {sec:.2f} s/step (oracle O32, timed build: C/OpenMP float32 "
+                      f"restatement with FMA, one neighbour search per conv like the reference; {o32.num_threads()} OpenMP threads "
+                      "set explicitly)"}, sec, len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, sec = cpu_baseline(args.cpu_n_side, max(1, min(args.steps, 3)), 1 if args.warmup > 0 else 0)
-    line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)),
-            "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+    warm = 1 if args.warmup > 0 else 0
+    base, sec, n_timed = cpu_baseline(args.cpu_n_side or args.n_side, max(1, args.steps), warm, budget_s=150.0)
+    full = (args.cpu_n_side or args.n_side) == args.n_side
+    line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n_timed,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"C4 synthetic 3-D box, single-scale SymNet (ASCC+CConv stack); CPU sample {args.cpu_n_side}^3 "
-                                   "particles (bounded sub-volume of the 100^3 workload)"},
+            "config": {"workload": workload_name(args.n_side) if full else
+                       f"C4 synthetic 3-D box, single-scale SymNet (ASCC+CConv stack); CPU sample {args.cpu_n_side}^3 particles "
+                       f"(bounded sub-volume of the {args.n_side}^3 workload)",
+                       "same_config_as_gpu_arm": full,
+                       "steps_note": f"{n_timed} of the requested {args.steps} steps fit the 150 s budget of the CPU arm"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def workload_name(n_side):
+    return (f"C4: ONE synthetic 3-D box of {n_side}^3 = {n_side ** 3} fluid particles (spacing 0.05, jittered lattice) inside wall "
+            "particles, single-scale SymNet (input convs, 3x CConv 4x4x4 ->32 + Dense, ASCC 6x6x6 32->3), r=0.1, seeded random "
+            "weights")
 
 
 def ncu_traffic(top):
@@ -202,14 +231,74 @@ def conv_flops(rec):
     return rec["pairs"] * (60 + 16 * rec["cin"]) + 2 * rec["n_out"] * rec["rows"] * rec["cout"]
 
 
+def timed_steps(sim, sample, steps, warmup, barrier, local_rank, profile=True):
+    """W untimed + exactly K timed steps on the resident sample, bracketed by barrier + synchronize; CUDA events on the launching
+    stream; clocks sampled during the timed region.  Returns (ms of the K steps on this rank, conv / hbm-op records, launches,
+    clocks, last output)."""
+    import torch
+    from dmcf_b200 import ops
+    with torch.no_grad():
+        for _ in range(warmup):
+            out = sim.step(sample)
+        barrier()
+        ops.PROFILE = [] if profile else None
+        launches0 = ops.launch_count()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.25)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        ev0.record()
+        for _ in range(steps):
+            out = sim.step(sample)
+        ev1.record()
+        barrier()
+        w1 = time.time()
+        clocks = sampler.stop(w0, w1)
+        ms = ev0.elapsed_time(ev1)
+        launches = ops.launch_count() - launches0
+        prof, ops.PROFILE = (ops.PROFILE or []), None
+    return ms, prof, launches, clocks, out
+
+
+def e2e_steps_timed(sim, scene, box_d, bn_d, steps, barrier, dev):
+    """The same metric through the public API with HOST buffers: every step copies this rank's pos / vel from pinned host memory,
+    runs Simulator.step and copies the advanced pos / vel back to pinned host memory, all inside the timed region."""
+    import torch
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory()
+    h_pos, h_vel = pin(scene["pos"]), pin(scene["vel"])
+    o_pos, o_vel = torch.empty_like(h_pos).pin_memory(), torch.empty_like(h_vel).pin_memory()
+    with torch.no_grad():
+        def e2e_step():
+            p = h_pos.to(dev, non_blocking=True)
+            v = h_vel.to(dev, non_blocking=True)
+            res = sim.step([p, v, None, None, box_d, bn_d])
+            n = min(res[0].shape[0], o_pos.shape[0])  # slabs: migration may change the row count by a few
+            o_pos[:n].copy_(res[0][:n], non_blocking=True)
+            o_vel[:n].copy_(res[1][:n], non_blocking=True)
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            e2e_step()
+        e1.record()
+        barrier()
+    return e0.elapsed_time(e1), int(h_pos.numel() * 4 + h_vel.numel() * 4)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n-side", type=int, default=100, help="fluid lattice edge per GPU (100 -> 1M particles)")
-    ap.add_argument("--cpu-n-side", type=int, default=56, help="edge of the CPU-baseline sub-volume")
+    ap.add_argument("--n-side", type=int, default=100, help="fluid lattice edge of the scene (100 -> 1M particles)")
+    ap.add_argument("--cpu-n-side", type=int, default=0, help="edge of the CPU arm's scene (0 = the full --n-side scene)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="both", choices=["strong", "weak", "both"],
+                    help="N > 1: strong = ONE n_side^3 scene split into N slabs (the headline, BASELINE config 4); weak = every rank "
+                         "owns an n_side^3 slab of an N-times longer box (extra key `weak`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -222,8 +311,9 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dmcf_b200 import config, ops
+    from dmcf_b200 import config, ops, scenes
     from dmcf_b200.simulator import Simulator
+    from dmcf_b200.slab import SlabContext
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -235,56 +325,73 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
-
-    if world > 1:
-        from dmcf_b200 import scenes
-        from dmcf_b200.slab import SlabContext
-        scene, faces = scenes.slab_scene(args.n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0)
-        cfg = scenes.c4_model_cfg()
-    else:
-        scene, cfg = build_workload(args.n_side, seed=rank)
-    model = config.build_model(cfg)
-    model.init_weights(seed=0, device=dev, scale=0.1)
-    if world > 1:
-        model.set_slab(SlabContext(faces, axis=0))
-    sim = Simulator(model, device=f"cuda:{local_rank}")
-    n_fluid = scene["pos"].shape[0]
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
-    sample = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident arm ---------------------------------------------------------------------------
-    with torch.no_grad():
-        for _ in range(warmup):
-            out = sim.step(sample)
-        barrier()
-        ops.PROFILE = []
-        launches0 = ops.launch_count()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        time.sleep(0.25)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.time()
-        ev0.record()
-        for _ in range(args.steps):
-            out = sim.step(sample)
-        ev1.record()
-        barrier()
-        w1 = time.time()
-        clocks = sampler.stop(w0, w1)
-        ms = ev0.elapsed_time(ev1)
-        launches = ops.launch_count() - launches0
-        prof, ops.PROFILE = ops.PROFILE, None
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    def all_max(x):
+        v = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    def all_sum(x):
+        v = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return float(v.item())
+
+    def make_sim(scene, faces):
+        model = config.build_model(scenes.c4_model_cfg())
+        model.init_weights(seed=0, device=dev, scale=0.1)
+        if world > 1:
+            model.set_slab(SlabContext(faces, axis=0))
+        sim = Simulator(model, device=f"cuda:{local_rank}")
+        sample = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
+        return sim, sample
+
+    # ---- the headline arm: ONE n_side^3 scene (strong scaling for N > 1: slabs of n_side / N lattice layers) ---------------
+    full_scene, _ = build_workload(args.n_side, seed=0)
+    n_total = full_scene["pos"].shape[0]
+    n_wall_total = full_scene["box"].shape[0]
     if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
-    value = n_fluid * world * args.steps / (ms_max * 1e-3)
+        scene, faces = scenes.slab_partition(full_scene, rank, world, args.n_side, dx=0.05)
+    else:
+        scene, faces = full_scene, None
+    del full_scene
+    main_scaling = "weak" if (world > 1 and args.scaling == "weak") else "strong"
+    weak = None
+    if world > 1 and args.scaling in ("weak", "both"):
+        w_scene, w_faces = scenes.slab_scene(args.n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0)
+        sim_w, sample_w = make_sim(w_scene, w_faces)
+        w_steps = args.steps if main_scaling == "weak" else max(3, min(args.steps, 10))
+        ms_w, prof_w, launches_w, clocks_w, out_w = timed_steps(sim_w, sample_w, w_steps, warmup, barrier, local_rank,
+                                                                profile=main_scaling == "weak")
+        ms_w = all_max(ms_w)
+        n_w = int(all_sum(w_scene["pos"].shape[0]))
+        weak = {"value": n_w * w_steps / (ms_w * 1e-3), "unit": UNIT, "ms_per_step": ms_w / w_steps, "steps": w_steps,
+                "particles_total": n_w, "particles_per_gpu": w_scene["pos"].shape[0],
+                "workload": f"one {world}x{args.n_side} x {args.n_side} x {args.n_side} box, every rank owns an {args.n_side}^3 slab"}
+        if main_scaling != "weak":
+            del sim_w, sample_w, w_scene, out_w
+            torch.cuda.empty_cache()
+
+    if main_scaling == "weak":
+        sim, sample, scene = sim_w, sample_w, w_scene
+        ms, prof, launches, clocks, out = ms_w, prof_w, launches_w, clocks_w, out_w
+        steps = w_steps
+        n_total = weak["particles_total"]
+        ms_max = ms
+    else:
+        sim, sample = make_sim(scene, faces)
+        steps = args.steps
+        ms, prof, launches, clocks, out = timed_steps(sim, sample, steps, warmup, barrier, local_rank)
+        ms_max = all_max(ms)
+    n_own = scene["pos"].shape[0]
+    value = n_total * steps / (ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel (live CUDA events around each conv launch in the timed region) -------
     groups = {}
@@ -306,69 +413,56 @@ def main():
                               "algorithmic_GB": round(gb, 4), "GBps": round(gb / (avg_ms * 1e-3), 1),
                               "fp32_TFLOPs": round(conv_flops(g["rec"]) / (avg_ms * 1e-3) / 1e12, 2)})
         top = breakdown[0]
+        traffic = ncu_traffic(top) if world == 1 else None  # the capture is of the 1-GPU launch (1.06 M out points)
         roofline = {"bound": "hbm", "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": round(top["GBps"] / peak, 4),
-                    "traffic": ncu_traffic(top), "kernel": f"{top['kernel']} filter {top['filter']} {top['cin']}->{top['cout']}" + (" ascc" if top["ascc"] else ""),
+                    "traffic": traffic, "kernel": f"{top['kernel']} filter {top['filter']} {top['cin']}->{top['cout']}" + (" ascc" if top["ascc"] else ""),
                     "peak_source": peak_src, "avg_launch_ms": top["avg_ms"], "share_of_step": top["share_of_step"],
                     "fp32_tflops": top["fp32_TFLOPs"], "fp32_simt_peak_tflops": 74.0,
                     "note": "wide CConv layers are fp32-FLOP bound (SURVEY 8d): HBM fraction reported as BASELINE asks, "
-                            "fp32 TFLOP/s beside it"}
+                            "fp32 TFLOP/s beside it" + ("; rank 0's launches (its slab)" if world > 1 else "")}
 
     hbm_kernels = hbm_op_breakdown(hbm_ops, ms, peak)
 
     # ---- end-to-end arm: host buffers in, host buffers out, copies inside the timed region ----------------
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory()
-    h_pos, h_vel = pin(scene["pos"]), pin(scene["vel"])
-    o_pos, o_vel = torch.empty_like(h_pos).pin_memory(), torch.empty_like(h_vel).pin_memory()
-    box_d, bn_d = sample[4], sample[5]  # the boundary is static over a rollout and stays resident like in the reference
-    e2e_steps = max(3, min(args.steps, 10))
-    with torch.no_grad():
-        def e2e_step():
-            p = h_pos.to(dev, non_blocking=True)
-            v = h_vel.to(dev, non_blocking=True)
-            res = sim.step([p, v, None, None, box_d, bn_d])
-            o_pos.copy_(res[0], non_blocking=True)
-            o_vel.copy_(res[1], non_blocking=True)
-        e2e_step()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
-        e1.record()
-        barrier()
-        e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = n_fluid * world * e2e_steps / (float(e_ms.item()) * 1e-3)
-    copy_bytes = int(h_pos.numel() * 4 + h_vel.numel() * 4)
+    e2e_steps = max(3, min(steps, 10))
+    e_ms, copy_bytes = e2e_steps_timed(sim, scene, sample[4], sample[5], e2e_steps, barrier, dev)
+    e_ms = all_max(e_ms)
+    e2e_value = n_total * e2e_steps / (e_ms * 1e-3)
+    copy_bytes_total = int(all_sum(copy_bytes))
 
     # ---- sanity of the timed result (finite, particles moved) ------------------------------------------------
-    ok = bool(torch.isfinite(out[0]).all().item())
+    ok = bool(all_sum(0.0 if bool(torch.isfinite(out[0]).all().item()) else 1.0) == 0.0)
+    exchanged = None
+    if world > 1:
+        exchanged = int(all_sum(float(sim.model.slab.bytes_exchanged))) // max(1, warmup + steps + e2e_steps + 1)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_baseline(args.cpu_n_side, 2, 1)
+        cpu, _, _ = cpu_baseline(args.cpu_n_side or args.n_side, 2, 1, budget_s=40.0)
 
     if rank == 0:
+        layers = [args.n_side // world + (1 if k < args.n_side % world else 0) for k in range(world)]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": main_scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C4: synthetic 3-D box, {args.n_side}^3 = {n_fluid} fluid + {scene['box'].shape[0]} wall particles per "
-                                   "GPU, single-scale SymNet (input convs, 3x CConv 4x4x4 ->32 + Dense, ASCC 6x6x6 32->3), r=0.1, "
-                                   "seeded random weights",
-                       "parallelism": (f"{world} spatial slabs along x of one {world}x{args.n_side} x {args.n_side} x {args.n_side} box, "
-                                       "position halo per step + feature halo per conv layer over NCCL send/recv")
+            "config": {"workload": (workload_name(args.n_side) + f" ({n_total} fluid + {n_wall_total} wall particles in total)")
+                       if main_scaling == "strong" else
+                       f"C4 weak scaling: {world}x{args.n_side} x {args.n_side} x {args.n_side} box, {args.n_side}^3 fluid particles per GPU",
+                       "parallelism": (f"{world} spatial slabs along x" + (f" of {layers} lattice layers" if main_scaling == "strong" else "")
+                                       + ", position halo per step + feature halo per conv layer over NCCL send/recv, migration after the position update")
                        if world > 1 else "single GPU",
-                       "l2": "per-step working set (features 136 MB/layer + 140 MB neighbour list) exceeds the 126 MB L2; "
-                             "no explicit flush",
+                       "l2": ("per-step working set (features 136 MB/layer + 140 MB neighbour list per 1 M particles) exceeds the 126 MB L2 "
+                              "down to 8 slabs (17 MB/layer + 18 MB list each, but five layers + records > L2); no explicit flush"),
                        "state": "every step restarts from the same resident scene (fixed work per step)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": copy_bytes, "d2h_bytes_per_step": copy_bytes,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": copy_bytes_total, "d2h_bytes_per_step": copy_bytes_total,
                     "steps": e2e_steps, "api": "Simulator.step on pinned host pos/vel, results copied back to pinned host"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": breakdown,
-            "hbm_kernels": hbm_kernels,
-            "cpu_baseline": cpu, "finite": ok,
+            "hbm_kernels": hbm_kernels, "cpu_baseline": cpu, "finite": ok,
+            "particles_rank0": n_own, "halo_bytes_per_step": exchanged,
         }
+        if weak is not None and main_scaling != "weak":
+            line["weak"] = weak
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -82,3 +82,20 @@ def slab_scene(n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0):
     sc["pos"][:, 0] = np.clip(sc["pos"][:, 0], rank * length + 1e-4, (rank + 1) * length - 1e-4)
     sc["box"], sc["box_normals"] = box[own], normals[own]
     return sc, faces
+
+
+def slab_partition(scene, rank, world, n_side, dx=0.05):
+    """Strong scaling: rank ``rank``'s share of ONE ``lattice_scene`` with ``n_side`` lattice layers along x, split into ``world``
+    slabs whose faces sit on layer boundaries (layers dealt out as evenly as possible: 100 layers on 8 ranks = 13,13,13,13,12,12,12,12;
+    the jitter keeps every particle inside its layer, so no fluid particle sits on a face).  Wall particles are owned by
+    coordinate.  Returns (scene dict of the rank, slab faces along x)."""
+    layers = [n_side // world + (1 if k < n_side % world else 0) for k in range(world)]
+    inner = np.cumsum(layers)[:-1] * dx
+    inf = float("inf")
+    faces = [-inf] + [float(f) for f in inner] + [inf]
+    out = {}
+    own = (scene["pos"][:, 0] >= faces[rank]) & (scene["pos"][:, 0] < faces[rank + 1])
+    out["pos"], out["vel"] = scene["pos"][own], scene["vel"][own]
+    own_b = (scene["box"][:, 0] >= faces[rank]) & (scene["box"][:, 0] < faces[rank + 1])
+    out["box"], out["box_normals"] = scene["box"][own_b], scene["box_normals"][own_b]
+    return out, faces

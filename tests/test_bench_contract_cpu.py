@@ -12,8 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must set its thread count itself
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-n-side", "12"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--cpu-n-side", "12"], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert res.returncode == 0, res.stderr[-500:]
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -22,7 +24,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
                 "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["vs_baseline"] is None and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["cpu_baseline"]["kind"] == "port" and "sample" in line["cpu_baseline"]
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["scaling"] == "strong" and line["config"]["same_config_as_gpu_arm"] is False  # --cpu-n-side given: a sub-volume
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
 

@@ -373,3 +373,29 @@ def test_wbc_sph_checkpoint_holds_a_hydrostatic_block_only_with_the_restated_con
     drift_flip, _, _ = _hydrostatic_drift(cfg, spatial(lambda v: v[:, ::-1]), sc)
     drift_swap, _, _ = _hydrostatic_drift(cfg, spatial(lambda v: v.transpose(0, 2, 1, 3, 4)), sc)
     assert drift_flip > 0.5 and drift_swap > 0.5, (drift_flip, drift_swap)  # measured 2.05 / 1.44
+
+
+def test_timed_o32_build_agrees_with_the_parity_build():
+    """bench.py's CPU arm runs libo32_timed.so (same source; FMA contraction allowed, register-blocked patch x filter product):
+    same neighbour lists bit for bit, conv outputs within float32 rounding of the parity build and of O64."""
+    from oracle import o32
+    rng = np.random.default_rng(5)
+    pts = (rng.random((3000, 3)) * 0.8).astype(np.float32)
+    feats = rng.standard_normal((3000, 32)).astype(np.float32)
+    outs = {}
+    try:
+        for timed in (False, True):
+            o32.use_timed_build(timed)
+            idx, rs, d2 = o32.fixed_radius_search(pts, pts, 0.1)
+            res = [idx, rs, d2]
+            for cout in (32, 24, 3):
+                w = np.random.default_rng(cout).uniform(-0.3, 0.3, (4, 4, 4, 32, cout)).astype(np.float32)
+                res.append(o32.continuous_conv(w, pts, 0.2, None, pts, feats, None, idx, None, rs,
+                                               coordinate_mapping="ball_to_cube_volume_preserving", normalize=(cout == 24)))
+            outs[timed] = res
+    finally:
+        o32.use_timed_build(False)
+    for a, b in zip(outs[False][:3], outs[True][:3]):
+        assert np.array_equal(a, b)
+    for a, b in zip(outs[False][3:], outs[True][3:]):
+        assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max() + 1e-7
