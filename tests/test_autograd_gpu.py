@@ -212,7 +212,7 @@ def test_two_unrolled_steps_carry_the_gradient_through_pos_and_vel(cuda):
     # (a) two unrolled steps, one backward
     p1, v1 = model(sample, training=True)
     p2, _ = model([p1, v1] + sample[2:], training=True)
-    g_total = torch.autograd.grad(loss_of(p2), params, allow_unused=True)
+    g_total = torch.autograd.grad(loss_of(p2), params, allow_unused=True, retain_graph=True)  # step 1's graph is used again in (c)
     # (b) step 2 alone on leaf copies of the step-1 outputs
     p1l, v1l = p1.detach().requires_grad_(True), v1.detach().requires_grad_(True)
     p2b, _ = model([p1l, v1l] + sample[2:], training=True)
