@@ -242,7 +242,7 @@ def timed_steps(sim, sample, steps, warmup, barrier, local_rank, profile=True):
             out = sim.step(sample)
         barrier()
         ops.PROFILE = [] if profile else None
-        launches0 = ops.launch_count()
+        launches0 = ops.launch_count() + sim.stats.get("graph_kernel_launches", 0)
         sampler = ClockSampler(local_rank)
         sampler.start()
         time.sleep(0.25)
@@ -257,7 +257,8 @@ def timed_steps(sim, sample, steps, warmup, barrier, local_rank, profile=True):
         w1 = time.time()
         clocks = sampler.stop(w0, w1)
         ms = ev0.elapsed_time(ev1)
-        launches = ops.launch_count() - launches0
+        # kernels launched one by one plus the kernels inside every replayed CUDA graph (counted when the graph was captured)
+        launches = ops.launch_count() + sim.stats.get("graph_kernel_launches", 0) - launches0
         prof, ops.PROFILE = (ops.PROFILE or []), None
     return ms, prof, launches, clocks, out
 
@@ -300,6 +301,8 @@ def main():
                     help="N > 1: strong = ONE n_side^3 scene split into N slabs (the headline, BASELINE config 4); weak = every rank "
                          "owns an n_side^3 slab of an N-times longer box (extra key `weak`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--step-mode", default="graph", choices=["eager", "planned", "graph"],
+                    help="how Simulator.step drives the model (dmcf_b200/simulator.py); slab runs (N > 1) are eager")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -349,7 +352,7 @@ def main():
         model.init_weights(seed=0, device=dev, scale=0.1)
         if world > 1:
             model.set_slab(SlabContext(faces, axis=0))
-        sim = Simulator(model, device=f"cuda:{local_rank}")
+        sim = Simulator(model, device=f"cuda:{local_rank}", step_mode=args.step_mode if world == 1 else "eager")
         sample = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
         return sim, sample
 
@@ -382,14 +385,24 @@ def main():
     if main_scaling == "weak":
         sim, sample, scene = sim_w, sample_w, w_scene
         ms, prof, launches, clocks, out = ms_w, prof_w, launches_w, clocks_w, out_w
+        prof_region_ms = ms_w
         steps = w_steps
         n_total = weak["particles_total"]
         ms_max = ms
     else:
         sim, sample = make_sim(scene, faces)
         steps = args.steps
-        ms, prof, launches, clocks, out = timed_steps(sim, sample, steps, warmup, barrier, local_rank)
+        replayed = world == 1 and args.step_mode != "eager"
+        ms, prof, launches, clocks, out = timed_steps(sim, sample, steps, warmup, barrier, local_rank, profile=not replayed)
         ms_max = all_max(ms)
+        if replayed:
+            # per-kernel times for the roofline: the same step, plan and kernels launched one by one ("planned" mode) with CUDA
+            # events around every launch, right after the headline region (events cannot be recorded inside a graph replay)
+            sim_p = Simulator(sim.model, device=f"cuda:{local_rank}", step_mode="planned")
+            p_steps = max(3, min(steps, 5))
+            prof_region_ms, prof, _, _, _ = timed_steps(sim_p, sample, p_steps, 2, barrier, local_rank, profile=True)
+        else:
+            prof_region_ms = ms
     n_own = scene["pos"].shape[0]
     value = n_total * steps / (ms_max * 1e-3)
 
@@ -404,12 +417,13 @@ def main():
         g["n"] += 1
     roofline, breakdown = None, []
     peak, peak_src = peaks()
+    prof_ms_total = prof_region_ms  # the region the per-launch events were recorded in
     if groups:
         for k, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
             avg_ms = g["ms"] / g["n"]
             gb = conv_algorithmic_bytes(g["rec"]) / 1e9
             breakdown.append({"kernel": g["rec"]["kernel"], "filter": list(k[0]), "cin": k[1], "cout": k[2], "ascc": bool(k[3]),
-                              "launches": g["n"], "avg_ms": round(avg_ms, 4), "share_of_step": round(g["ms"] / ms, 4),
+                              "launches": g["n"], "avg_ms": round(avg_ms, 4), "share_of_step": round(g["ms"] / prof_ms_total, 4),
                               "algorithmic_GB": round(gb, 4), "GBps": round(gb / (avg_ms * 1e-3), 1),
                               "fp32_TFLOPs": round(conv_flops(g["rec"]) / (avg_ms * 1e-3) / 1e12, 2)})
         top = breakdown[0]
@@ -418,10 +432,13 @@ def main():
                     "traffic": traffic, "kernel": f"{top['kernel']} filter {top['filter']} {top['cin']}->{top['cout']}" + (" ascc" if top["ascc"] else ""),
                     "peak_source": peak_src, "avg_launch_ms": top["avg_ms"], "share_of_step": top["share_of_step"],
                     "fp32_tflops": top["fp32_TFLOPs"], "fp32_simt_peak_tflops": 74.0,
+                    "timed_in": ("per-launch CUDA events over %d steps launched kernel by kernel (step_mode planned: same plan, buffers and "
+                                 "kernels as the graph) right after the headline region" % p_steps) if (world == 1 and args.step_mode != "eager")
+                    else "per-launch CUDA events inside the headline timed region",
                     "note": "wide CConv layers are fp32-FLOP bound (SURVEY 8d): HBM fraction reported as BASELINE asks, "
                             "fp32 TFLOP/s beside it" + ("; rank 0's launches (its slab)" if world > 1 else "")}
 
-    hbm_kernels = hbm_op_breakdown(hbm_ops, ms, peak)
+    hbm_kernels = hbm_op_breakdown(hbm_ops, prof_region_ms, peak)
 
     # ---- end-to-end arm: host buffers in, host buffers out, copies inside the timed region ----------------
     e2e_steps = max(3, min(steps, 10))
@@ -454,7 +471,9 @@ def main():
                        if world > 1 else "single GPU",
                        "l2": ("per-step working set (features 136 MB/layer + 140 MB neighbour list per 1 M particles) exceeds the 126 MB L2 "
                               "down to 8 slabs (17 MB/layer + 18 MB list each, but five layers + records > L2); no explicit flush"),
-                       "state": "every step restarts from the same resident scene (fixed work per step)"},
+                       "state": "every step restarts from the same resident scene (fixed work per step)",
+                       "step_mode": (args.step_mode if world == 1 else "eager") + " (dmcf_b200/simulator.py)",
+                       "step_stats": dict(sim.stats)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": copy_bytes_total, "d2h_bytes_per_step": copy_bytes_total,
                     "steps": e2e_steps, "api": "Simulator.step on pinned host pos/vel, results copied back to pinned host"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": breakdown,

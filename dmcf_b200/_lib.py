@@ -21,7 +21,7 @@ class DmcfError(RuntimeError):
 class Grid(C.Structure):
     """struct dmcf_grid"""
     _fields_ = [("origin", c_f32 * 3), ("inv_cell", c_f32), ("dims", c_i32 * 3), ("n_points", c_i32),
-                ("cell_start", c_vp), ("sorted_index", c_vp), ("sorted_pos", c_vp)]
+                ("cell_start", c_vp), ("sorted_index", c_vp), ("sorted_pos", c_vp), ("n_points_dev", c_vp)]
 
 
 class ConvDesc(C.Structure):
@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
                 ("interpolation", c_i32), ("align_corners", c_i32), ("normalize", c_i32), ("window", c_i32),
                 ("window_fac", c_f32), ("extent", c_f32), ("offset", c_f32 * 3), ("relu_input", c_i32),
                 ("feat_scale", c_f32), ("ascc", c_i32), ("skip_self", c_i32), ("nbr_lo", c_i32), ("nbr_hi", c_i32),
-                ("dense_cin", c_i32), ("accumulate", c_i32), ("filter_antisym", c_i32)]
+                ("dense_cin", c_i32), ("accumulate", c_i32), ("filter_antisym", c_i32), ("n_out_dev", c_vp)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/dmcf_b200.h
@@ -40,8 +40,8 @@ SIGNATURES = {
     "dmcf_launch_count": (c_i64, []),
     "dmcf_grid_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "dmcf_grid_build": (c_i32, [c_vp, C.POINTER(Grid), c_vp, c_sz, c_vp]),
-    "dmcf_frs_count": (c_i32, [C.POINTER(Grid), c_vp, c_i64, c_f32, c_i32, c_vp, c_vp]),
-    "dmcf_frs_fill": (c_i32, [C.POINTER(Grid), c_vp, c_i64, c_f32, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "dmcf_frs_count": (c_i32, [C.POINTER(Grid), c_vp, c_i64, c_vp, c_f32, c_i32, c_vp, c_vp]),
+    "dmcf_frs_fill": (c_i32, [C.POINTER(Grid), c_vp, c_i64, c_vp, c_f32, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "dmcf_scan_workspace_bytes": (c_sz, [c_i64]),
     "dmcf_exclusive_scan_i32_i64": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "dmcf_exclusive_scan_i32_i32": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
@@ -55,10 +55,10 @@ SIGNATURES = {
     "dmcf_set_kernel_options": (c_i32, [c_i32]),
     "dmcf_dense_forward": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp]),
     "dmcf_integrate": (c_i32, [c_vp, c_vp, c_vp, C.POINTER(c_f32), c_f32, c_i64, c_vp, c_vp, c_vp]),
-    "dmcf_grid_pos_mark": (c_i32, [c_vp, c_i64, C.POINTER(c_f32), C.POINTER(c_f32), c_f32, C.POINTER(c_i32),
-                                   C.POINTER(c_i32), c_vp, c_vp]),
-    "dmcf_grid_pos_emit": (c_i32, [c_vp, c_vp, C.POINTER(c_f32), C.POINTER(c_f32), C.POINTER(c_i32), C.POINTER(c_i32),
-                                   c_vp, c_vp]),
+    "dmcf_grid_pos_mark": (c_i32, [c_vp, c_i64, c_vp, C.POINTER(c_f32), C.POINTER(c_f32), c_vp, c_f32, C.POINTER(c_i32),
+                                   C.POINTER(c_i32), c_vp, c_vp, c_vp]),
+    "dmcf_grid_pos_emit": (c_i32, [c_vp, c_vp, C.POINTER(c_f32), C.POINTER(c_f32), c_vp, C.POINTER(c_i32), C.POINTER(c_i32),
+                                   c_vp, c_i64, c_vp, c_vp]),
     "dmcf_correct": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_i64, c_vp, c_vp, c_vp]),
     "dmcf_farthest_point_sample": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     "dmcf_approx_match_workspace_bytes": (c_sz, [c_i32, c_i32]),
@@ -86,7 +86,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dmcf_version() < 103:
+    if lib.dmcf_version() < 104:
         raise DmcfError("libdmcf_b200.so is older than this package")
     _lib = lib
     return lib

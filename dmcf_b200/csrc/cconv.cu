@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_tile(const ConvParams p) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile_base = (int64_t)blockIdx.x * MT;
+    const int64_t n_out = conv_n_out(p);
+    if (tile_base >= n_out) return;
 
     // ---- phase 0: clear the patch tile ------------------------------------------------------------------
     {
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_tile(const ConvParams p) {
     const bool lane_ok = cg < n_cg;
     for (int m = warp; m < MT; m += NW) {
         const int64_t o = tile_base + m;
-        if (o >= p.n_out) break;
+        if (o >= n_out) break;
         float* prow = patch + (size_t)m * p.kc_pad;
         const float ox = __ldg(p.out_pos + 3 * o), oy = __ldg(p.out_pos + 3 * o + 1), oz = __ldg(p.out_pos + 3 * o + 2);
         const int64_t rs = p.row_splits[o], re = p.row_splits[o + 1];
@@ -140,12 +142,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_tile(const ConvParams p) {
         for (int idx = tid; idx < MT * p.kc_conv; idx += NW * 32) {
             const int m = idx / p.kc_conv, k = idx - m * p.kc_conv;
             const int64_t o = tile_base + m;
-            if (o < p.n_out) p.patch_out[o * p.patch_stride + k] = patch[(size_t)m * p.kc_pad + k];
+            if (o < n_out) p.patch_out[o * p.patch_stride + k] = patch[(size_t)m * p.kc_pad + k];
         }
         return;
     }
 
-    cconv_phase2<MT, NW, false>(p, patch, red, norm, tile_base);
+    cconv_phase2<MT, NW, false>(p, patch, red, norm, tile_base, n_out);
 }
 
 static int next_pow2(int v) {
@@ -224,6 +226,7 @@ static int fill_params(const dmcf_conv_desc* d, const float* filters, const floa
     p.relu_input = d->relu_input; p.feat_scale = d->feat_scale;
     p.ascc = d->ascc; p.skip_self = d->skip_self; p.nbr_lo = d->nbr_lo; p.nbr_hi = d->nbr_hi;
     p.dense_cin = d->dense_cin; p.accumulate = d->accumulate; p.filter_antisym = d->filter_antisym;
+    p.n_out_dev = d->n_out_dev;
     const int64_t cells = (int64_t)p.gp.kx * p.gp.ky * p.gp.kz;
     DMCF_REQUIRE(cells * d->cin + d->dense_cin < (1 << 24), "cconv: filter too large");
     p.kc_conv = (int)(cells * d->cin);
@@ -243,7 +246,8 @@ __global__ void __launch_bounds__(256) k_cconv_prepare(const ConvParams p, float
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t P = p.n_pairs;
-    for (int64_t o = warp0; o < p.n_out; o += n_warps) {
+    const int64_t n_out = conv_n_out(p);
+    for (int64_t o = warp0; o < n_out; o += n_warps) {
         const float ox = __ldg(p.out_pos + 3 * o), oy = __ldg(p.out_pos + 3 * o + 1), oz = __ldg(p.out_pos + 3 * o + 2);
         const int64_t rs = p.row_splits[o], re = p.row_splits[o + 1];
         for (int64_t c0 = rs; c0 < re; c0 += 32) {

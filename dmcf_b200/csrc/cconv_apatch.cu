@@ -48,8 +48,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_apatch(const ConvParams p)
     const int cell_stride = p.cin * COUT;
 
     const int64_t stride = (int64_t)gridDim.x * NW;
+    const int64_t n_out = conv_n_out(p);
     int64_t o = (int64_t)blockIdx.x * NW + warp;
-    bool o_ok = o < p.n_out;
+    bool o_ok = o < n_out;
     int64_t rs = 0, re = 0;
     float ox = 0.f, oy = 0.f, oz = 0.f;
     if (o_ok) {
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_apatch(const ConvParams p)
     while (o_ok) {
         // the warp's next point; its first chunk of records is in flight during this whole point
         const int64_t o_n = o + stride;
-        const bool n_ok = o_n < p.n_out;
+        const bool n_ok = o_n < n_out;
         int64_t rs_n = 0, re_n = 0;
         float ox_n = 0.f, oy_n = 0.f, oz_n = 0.f;
         if (n_ok) {

@@ -24,6 +24,7 @@ struct ConvParams {
     const float* inp_feat;
     int64_t inp_stride;
     int64_t n_out, n_inp;
+    const int32_t* n_out_dev;  // optional device-side out point count (n_out is then the capacity the grid was sized for)
     const float* inp_importance;
     const int32_t* nbr_index;
     const int64_t* row_splits;
@@ -45,6 +46,13 @@ struct ConvParams {
 };
 
 static constexpr int kRecordFields = 9;
+
+// Number of out points this launch really has: the device-side count when the caller runs capacity-sized buffers.
+__device__ __forceinline__ int64_t conv_n_out(const ConvParams& p) {
+    if (p.n_out_dev == nullptr) return p.n_out;
+    const int64_t n = (int64_t)__ldg(p.n_out_dev);
+    return n < p.n_out ? (n < 0 ? 0 : n) : p.n_out;
+}
 
 // One neighbour pair of an out point, ready for the scatter: feature row, corner cells and per-axis corner weights
 // with the pair's importance (window * neighbour importance * input importance) folded into the z weights.
@@ -119,7 +127,7 @@ __device__ __forceinline__ PairRec pair_record(const ConvParams& p, int64_t n, b
 // left the k loop, which the extra barrier guarantees).
 template <int MT, int NW, bool RED_ALIASES_PATCH>
 __device__ __forceinline__ void cconv_phase2(const ConvParams& p, const float* patch, float* red, const float* norm,
-                                             int64_t tile_base) {
+                                             int64_t tile_base, int64_t n_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cp = p.cp, ks = lane / cp, cl = lane % cp, n_ks = 32 / cp;
     const int kq_total = p.kc_pad / 4;
@@ -170,7 +178,7 @@ __device__ __forceinline__ void cconv_phase2(const ConvParams& p, const float* p
             const int m = t / cp, c = t % cp;
             const int64_t o = tile_base + m;
             const int oc = cb + c;
-            if (o < p.n_out && oc < p.cout) {
+            if (o < n_out && oc < p.cout) {
                 float v = 0.0f;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) v += red[((size_t)w * MT + m) * cp + c];
@@ -202,7 +210,7 @@ __device__ __forceinline__ int patchq_index(int m, int k) {
 
 template <int MT, int NW, bool RED_ALIASES_PATCH>
 __device__ __forceinline__ void cconv_phase2_v2(const ConvParams& p, const float* patchq, float* red, const float* norm,
-                                                int64_t tile_base) {
+                                                int64_t tile_base, int64_t n_out) {
     static_assert(MT % 4 == 0, "MT must be a multiple of 4");
     constexpr int R = MT / 4, MTP = MT + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -267,7 +275,7 @@ __device__ __forceinline__ void cconv_phase2_v2(const ConvParams& p, const float
             const int m = t >> 5, c = t & 31;
             const int64_t o = tile_base + m;
             const int oc = cb + c;
-            if (o < p.n_out && oc < p.cout) {
+            if (o < n_out && oc < p.cout) {
                 float v = 0.0f;
 #pragma unroll
                 for (int w2 = 0; w2 < NW; ++w2) v += red[((size_t)w2 * MT + m) * 32 + c];

@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(kDirWarps * 32, 1) k_cconv_direct(const ConvPa
     const int kx = p.gp.kx, kyx = p.gp.ky * p.gp.kx;
 
     const int64_t n_warps = (int64_t)gridDim.x * kDirWarps;
-    for (int64_t o = (int64_t)blockIdx.x * kDirWarps + warp; o < p.n_out; o += n_warps) {
+    const int64_t n_out = conv_n_out(p);
+    for (int64_t o = (int64_t)blockIdx.x * kDirWarps + warp; o < n_out; o += n_warps) {
         float acc[COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;

@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile_base = (int64_t)blockIdx.x * MT;
+    const int64_t n_out = conv_n_out(p);
+    if (tile_base >= n_out) return;  // capacity-sized launch: tiles beyond the device-side count have nothing to do
     float* wrec = recs + (size_t)warp * lean::kRecWords;
     const bool lane_ci = lane < p.cin;
     lean::WarpCtx cx;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
 
     // ================= phase 1: patch rows of this warp's points =================
     int64_t o = tile_base + warp;
-    bool o_ok = o < p.n_out;
+    bool o_ok = o < n_out;
     int64_t rs = 0, re = 0;
     float ox = 0.f, oy = 0.f, oz = 0.f;
     if (o_ok) {
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         const int m = warp + i * NW;
         // the warp's next point
         const int64_t o_n = o + NW;
-        const bool n_ok = (i + 1 < PPW) && o_n < p.n_out;
+        const bool n_ok = (i + 1 < PPW) && o_n < n_out;
         int64_t rs_n = 0, re_n = 0;
         float ox_n = 0.f, oy_n = 0.f, oz_n = 0.f;
         if (n_ok) {
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         for (int idx = tid; idx < MT * kq_conv; idx += NW * 32) {
             const int m = idx / kq_conv, kq = idx - m * kq_conv;
             const int64_t oo = tile_base + m;
-            if (oo >= p.n_out) continue;
+            if (oo >= n_out) continue;
             const float4 v = p4[(size_t)kq * MTP + m];
             float* dst = p.patch_out + oo * p.patch_stride + 4 * kq;
             if (vec) {
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     for (int t = tid; t < MT * 32; t += NW * 32) {
         const int m = t >> 5, c = t & 31;
         const int64_t oo = tile_base + m;
-        if (oo < p.n_out && c < cout) {
+        if (oo < n_out && c < cout) {
             float v = 0.0f;
 #pragma unroll
             for (int w2 = 0; w2 < NW; ++w2) v += red[((size_t)w2 * MT + m) * 32 + c];

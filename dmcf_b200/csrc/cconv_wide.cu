@@ -30,13 +30,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_cconv_wide(const ConvParams p
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile_base = (int64_t)blockIdx.x * MT;
+    const int64_t n_out = conv_n_out(p);
+    if (tile_base >= n_out) return;
     float* rec = scratch + (size_t)warp * 32 * kRecWords;
     const bool lane_ci = lane < p.cin;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     for (int m = warp; m < MT; m += NW) {
         const int64_t o = tile_base + m;
-        if (o >= p.n_out) {  // keep unused rows finite (they are multiplied, never stored)
+        if (o >= n_out) {  // keep unused rows finite (they are multiplied, never stored)
             for (int k = lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
             continue;
         }
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_cconv_wide(const ConvParams p
     }
     __syncthreads();
     if (p.debug_wrap_w & 2) return;  // timing experiment: phase 1 only
-    cconv_phase2_v2<MT, NW, RED_ALIAS>(p, patch, red, norm, tile_base);
+    cconv_phase2_v2<MT, NW, RED_ALIAS>(p, patch, red, norm, tile_base, n_out);
 }
 
 static size_t wide_smem_bytes(int mt, int nw, int kc_pad, int cp, bool alias) {

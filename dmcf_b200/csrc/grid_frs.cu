@@ -136,6 +136,7 @@ static int exclusive_scan(const int32_t* in, int64_t n, T* out, void* ws, size_t
 struct GridView {
     float ox, oy, oz, inv_cell;
     int nx, ny, nz, n_points;
+    const int32_t* n_points_dev;  // optional device-side count (n_points is then the capacity)
     const int32_t* cell_start;
     const int32_t* sorted_index;
     const float4* sorted_pos;
@@ -148,20 +149,26 @@ __device__ __forceinline__ int cell_of_point(const GridView& g, float x, float y
     return (cz * g.ny + cy) * g.nx + cx;
 }
 
+__device__ __forceinline__ int grid_n_points(const GridView& g) {
+    if (g.n_points_dev == nullptr) return g.n_points;
+    const int n = __ldg(g.n_points_dev);
+    return n < g.n_points ? (n < 0 ? 0 : n) : g.n_points;
+}
+
 __global__ void __launch_bounds__(256) k_cell_hist(GridView g, const float* __restrict__ pts, int32_t* __restrict__ cell_of,
                                                      int32_t* __restrict__ cell_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.n_points) return;
+    if (i >= grid_n_points(g)) return;
     const int c = cell_of_point(g, pts[3 * (int64_t)i], pts[3 * (int64_t)i + 1], pts[3 * (int64_t)i + 2]);
     cell_of[i] = c;
     atomicAdd(&cell_count[c], 1);
 }
 
-__global__ void __launch_bounds__(256) k_cell_scatter(int n, const int32_t* __restrict__ cell_of,
+__global__ void __launch_bounds__(256) k_cell_scatter(GridView g, const int32_t* __restrict__ cell_of,
                                                         const int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_fill,
                                                         int32_t* __restrict__ sorted_index) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= grid_n_points(g)) return;
     const int c = cell_of[i];
     const int slot = atomicAdd(&cell_fill[c], 1);
     sorted_index[cell_start[c] + slot] = i;
@@ -250,10 +257,10 @@ __global__ void __launch_bounds__(kCellSortWarps * 32) k_cell_sort(int64_t n_cel
     }
 }
 
-__global__ void __launch_bounds__(256) k_cell_gather_pos(int n, const float* __restrict__ pts,
+__global__ void __launch_bounds__(256) k_cell_gather_pos(GridView g, const float* __restrict__ pts,
                                                            const int32_t* __restrict__ sorted_index, float4* __restrict__ sorted_pos) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= grid_n_points(g)) return;
     const int id = sorted_index[i];
     sorted_pos[i] = make_float4(pts[3 * (int64_t)id], pts[3 * (int64_t)id + 1], pts[3 * (int64_t)id + 2], __int_as_float(id));
 }
@@ -262,7 +269,8 @@ __global__ void __launch_bounds__(256) k_cell_gather_pos(int n, const float* __r
 // radius queries: one warp per query, lanes stride over the contiguous candidate run of each (z,y) row.
 // ---------------------------------------------------------------------------------------------------------
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_frs(GridView g, const float* __restrict__ queries, int64_t n_queries, float radius, float thr,
+__global__ void __launch_bounds__(256) k_frs(GridView g, const float* __restrict__ queries, int64_t n_queries_cap,
+                                               const int32_t* __restrict__ n_queries_dev, float radius, float thr,
                                                int ignore_query_point, const int64_t* __restrict__ row_splits, int64_t capacity,
                                                int32_t* __restrict__ counts, int32_t* __restrict__ nbr_index,
                                                float* __restrict__ nbr_dist, int32_t* __restrict__ overflow) {
@@ -270,6 +278,13 @@ __global__ void __launch_bounds__(256) k_frs(GridView g, const float* __restrict
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
+    int64_t n_queries = n_queries_cap;
+    if (n_queries_dev != nullptr) {
+        const int64_t nd = (int64_t)__ldg(n_queries_dev);
+        n_queries = nd < n_queries_cap ? (nd < 0 ? 0 : nd) : n_queries_cap;
+        if (!FILL)  // rows beyond the device-side count are empty (the scan runs over the whole capacity)
+            for (int64_t q = n_queries + warp0 * 32 + lane; q < n_queries_cap; q += n_warps * 32) counts[q] = 0;
+    }
     for (int64_t q = warp0; q < n_queries; q += n_warps) {
         const float qx = __ldg(queries + 3 * q), qy = __ldg(queries + 3 * q + 1), qz = __ldg(queries + 3 * q + 2);
         const float rp = radius * 1.0001f;
@@ -339,6 +354,7 @@ __global__ void __launch_bounds__(256) k_frs(GridView g, const float* __restrict
 struct LatticeParams {
     float vx, vy, vz;     // voxel pitch
     float cx, cy, cz;     // centre (0 when not centralised)
+    const float* c_dev;   // centre in device memory instead (sync-free steps); overrides cx, cy, cz
     float hx, hy, hz;     // hysteresis per axis (0 on inactive axes)
     int ax, ay, az;       // axis active (voxel >= 1e-5)
     int lox, loy, loz, dx, dy, dz;
@@ -351,10 +367,11 @@ __device__ __forceinline__ int lattice_coord(float p, float c, float v, float h)
     return (int)floorf(__fadd_rn(__fdiv_rn(__fsub_rn(p, c), vm), h));
 }
 
-__global__ void __launch_bounds__(256) k_grid_pos_mark(const float* __restrict__ pos, int64_t n, LatticeParams L,
-                                                         int32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(256) k_grid_pos_mark(const float* __restrict__ pos, int64_t n, const int32_t* __restrict__ n_dev,
+                                                         LatticeParams L, int32_t* __restrict__ flags, int32_t* __restrict__ overflow) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (n_dev != nullptr && i >= (int64_t)__ldg(n_dev))) return;
+    if (L.c_dev != nullptr) { L.cx = __ldg(L.c_dev); L.cy = __ldg(L.c_dev + 1); L.cz = __ldg(L.c_dev + 2); }
     const float px = pos[3 * i], py = pos[3 * i + 1], pz = pos[3 * i + 2];
 #pragma unroll
     for (int sgn = 0; sgn < 2; ++sgn) {
@@ -368,14 +385,22 @@ __global__ void __launch_bounds__(256) k_grid_pos_mark(const float* __restrict__
                     const int x = bx + ox, y = by + oy, z = bz + oz;
                     if (x >= 0 && x < L.dx && y >= 0 && y < L.dy && z >= 0 && z < L.dz)
                         flags[((int64_t)z * L.dy + y) * L.dx + x] = 1;
+                    else if (overflow != nullptr)
+                        *overflow = 1;  // the particle left the planned lattice bounds: the caller re-plans
                 }
     }
 }
 
 __global__ void __launch_bounds__(256) k_grid_pos_emit(const int32_t* __restrict__ flags, const int32_t* __restrict__ offsets,
-                                                         int64_t n_cells, LatticeParams L, float* __restrict__ out) {
+                                                         int64_t n_cells, LatticeParams L, float* __restrict__ out, int64_t capacity,
+                                                         int32_t* __restrict__ overflow) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells || !flags[c]) return;
+    if (capacity >= 0 && (int64_t)offsets[c] >= capacity) {
+        if (overflow != nullptr) *overflow = 1;
+        return;
+    }
+    if (L.c_dev != nullptr) { L.cx = __ldg(L.c_dev); L.cy = __ldg(L.c_dev + 1); L.cz = __ldg(L.c_dev + 2); }
     const int x = (int)(c % L.dx) + L.lox;
     const int y = (int)((c / L.dx) % L.dy) + L.loy;
     const int z = (int)(c / ((int64_t)L.dx * L.dy)) + L.loz;
@@ -389,12 +414,15 @@ __global__ void __launch_bounds__(256) k_grid_pos_emit(const int32_t* __restrict
     out[3 * o + 2] = __fadd_rn(__fmul_rn((float)z, L.vz), az);
 }
 
-static int make_lattice(const float* v, const float* c, float hyst, const int32_t* lo, const int32_t* dims, LatticeParams* L) {
+static int make_lattice(const float* v, const float* c, const float* c_dev, float hyst, const int32_t* lo, const int32_t* dims,
+                        LatticeParams* L) {
     DMCF_REQUIRE(v && lo && dims, "grid_pos: NULL parameter");
+    DMCF_REQUIRE(!(c && c_dev), "grid_pos: give the centre in host OR device memory");
+    L->c_dev = c_dev;
     DMCF_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "grid_pos: dims must be positive");
     DMCF_REQUIRE((int64_t)dims[0] * dims[1] * dims[2] < ((int64_t)1 << 31), "grid_pos: lattice too large");
     L->vx = v[0]; L->vy = v[1]; L->vz = v[2];
-    L->centralize = c != nullptr;
+    L->centralize = c != nullptr || c_dev != nullptr;
     L->cx = c ? c[0] : 0.f; L->cy = c ? c[1] : 0.f; L->cz = c ? c[2] : 0.f;
     L->ax = v[0] >= 1e-5f; L->ay = v[1] >= 1e-5f; L->az = v[2] >= 1e-5f;
     L->hx = L->ax ? hyst : 0.f; L->hy = L->ay ? hyst : 0.f; L->hz = L->az ? hyst : 0.f;
@@ -415,6 +443,7 @@ static int make_view(const dmcf_grid* grid, GridView* v) {
     v->inv_cell = grid->inv_cell;
     v->nx = grid->dims[0]; v->ny = grid->dims[1]; v->nz = grid->dims[2];
     v->n_points = grid->n_points;
+    v->n_points_dev = grid->n_points_dev;
     v->cell_start = grid->cell_start;
     v->sorted_index = grid->sorted_index;
     v->sorted_pos = (const float4*)grid->sorted_pos;
@@ -474,11 +503,11 @@ extern "C" int dmcf_grid_build(const float* points, dmcf_grid* grid, void* works
     if (n > 0) {
         rc = check_cuda(cudaMemsetAsync(cell_count, 0, (size_t)n_cells * 4, st), "memset cell_fill");
         if (rc) return rc;
-        k_cell_scatter<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, cell_of, grid->cell_start, cell_count, grid->sorted_index);
+        k_cell_scatter<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g, cell_of, grid->cell_start, cell_count, grid->sorted_index);
         DMCF_LAUNCH_CHECK("k_cell_scatter");
         k_cell_sort<<<(unsigned)ceil_div(n_cells, kCellSortWarps), kCellSortWarps * 32, 0, st>>>(n_cells, grid->cell_start, grid->sorted_index);
         DMCF_LAUNCH_CHECK("k_cell_sort");
-        k_cell_gather_pos<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(n, points, grid->sorted_index, (float4*)grid->sorted_pos);
+        k_cell_gather_pos<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(g, points, grid->sorted_index, (float4*)grid->sorted_pos);
         DMCF_LAUNCH_CHECK("k_cell_gather_pos");
     }
     return DMCF_OK;
@@ -490,7 +519,7 @@ static unsigned frs_blocks(int64_t n_queries) {
     return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
-extern "C" int dmcf_frs_count(const dmcf_grid* grid, const float* queries, int64_t n_queries, float radius,
+extern "C" int dmcf_frs_count(const dmcf_grid* grid, const float* queries, int64_t n_queries, const int32_t* n_queries_dev, float radius,
                               int ignore_query_point, int32_t* counts, void* stream) {
     GridView g;
     int rc = make_view(grid, &g);
@@ -498,13 +527,13 @@ extern "C" int dmcf_frs_count(const dmcf_grid* grid, const float* queries, int64
     DMCF_REQUIRE(n_queries >= 0 && (n_queries == 0 || (queries && counts)), "frs_count: NULL buffer");
     DMCF_REQUIRE(radius >= 0.0f, "frs_count: negative radius");
     if (n_queries == 0) return DMCF_OK;
-    k_frs<false><<<frs_blocks(n_queries), 256, 0, (cudaStream_t)stream>>>(g, queries, n_queries, radius, radius * radius,
+    k_frs<false><<<frs_blocks(n_queries), 256, 0, (cudaStream_t)stream>>>(g, queries, n_queries, n_queries_dev, radius, radius * radius,
                                                                             ignore_query_point, nullptr, 0, counts, nullptr, nullptr, nullptr);
     DMCF_LAUNCH_CHECK("k_frs<count>");
     return DMCF_OK;
 }
 
-extern "C" int dmcf_frs_fill(const dmcf_grid* grid, const float* queries, int64_t n_queries, float radius,
+extern "C" int dmcf_frs_fill(const dmcf_grid* grid, const float* queries, int64_t n_queries, const int32_t* n_queries_dev, float radius,
                              int ignore_query_point, const int64_t* row_splits, int64_t capacity,
                              int32_t* neighbors_index, float* neighbors_distance, int32_t* overflow_flag, void* stream) {
     GridView g;
@@ -513,33 +542,36 @@ extern "C" int dmcf_frs_fill(const dmcf_grid* grid, const float* queries, int64_
     DMCF_REQUIRE(n_queries >= 0 && (n_queries == 0 || (queries && row_splits)), "frs_fill: NULL buffer");
     DMCF_REQUIRE(capacity >= 0 && (capacity == 0 || neighbors_index), "frs_fill: NULL neighbors_index");
     if (n_queries == 0) return DMCF_OK;
-    k_frs<true><<<frs_blocks(n_queries), 256, 0, (cudaStream_t)stream>>>(g, queries, n_queries, radius, radius * radius,
+    k_frs<true><<<frs_blocks(n_queries), 256, 0, (cudaStream_t)stream>>>(g, queries, n_queries, n_queries_dev, radius, radius * radius,
                                                                            ignore_query_point, row_splits, capacity, nullptr,
                                                                            neighbors_index, neighbors_distance, overflow_flag);
     DMCF_LAUNCH_CHECK("k_frs<fill>");
     return DMCF_OK;
 }
 
-extern "C" int dmcf_grid_pos_mark(const float* pos, int64_t n, const float* voxel, const float* center, float hyst,
-                                  const int32_t* lo, const int32_t* dims, int32_t* flags, void* stream) {
+extern "C" int dmcf_grid_pos_mark(const float* pos, int64_t n, const int32_t* n_dev, const float* voxel, const float* center,
+                                  const float* center_dev, float hyst, const int32_t* lo, const int32_t* dims, int32_t* flags,
+                                  int32_t* overflow_flag, void* stream) {
     LatticeParams L;
-    int rc = make_lattice(voxel, center, hyst, lo, dims, &L);
+    int rc = make_lattice(voxel, center, center_dev, hyst, lo, dims, &L);
     if (rc) return rc;
     DMCF_REQUIRE(n >= 0 && flags && (n == 0 || pos), "grid_pos_mark: NULL buffer");
     if (n == 0) return DMCF_OK;
-    k_grid_pos_mark<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, n, L, flags);
+    k_grid_pos_mark<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, n, n_dev, L, flags, overflow_flag);
     DMCF_LAUNCH_CHECK("k_grid_pos_mark");
     return DMCF_OK;
 }
 
 extern "C" int dmcf_grid_pos_emit(const int32_t* flags, const int32_t* offsets, const float* voxel, const float* center,
-                                  const int32_t* lo, const int32_t* dims, float* out, void* stream) {
+                                  const float* center_dev, const int32_t* lo, const int32_t* dims, float* out, int64_t capacity,
+                                  int32_t* overflow_flag, void* stream) {
     LatticeParams L;
-    int rc = make_lattice(voxel, center, 0.f, lo, dims, &L);
+    int rc = make_lattice(voxel, center, center_dev, 0.f, lo, dims, &L);
     if (rc) return rc;
     DMCF_REQUIRE(flags && offsets && out, "grid_pos_emit: NULL buffer");
     const int64_t n_cells = (int64_t)L.dx * L.dy * L.dz;
-    k_grid_pos_emit<<<(unsigned)ceil_div(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(flags, offsets, n_cells, L, out);
+    k_grid_pos_emit<<<(unsigned)ceil_div(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(flags, offsets, n_cells, L, out, capacity,
+                                                                                          overflow_flag);
     DMCF_LAUNCH_CHECK("k_grid_pos_emit");
     return DMCF_OK;
 }

@@ -48,7 +48,12 @@ def get_window_func(typ, fac=1.0, **kwargs):
 def point_mean(pos):
     """Mean position used by ``centralize`` (utils/tools/losses.py:137-139).  Accumulated in float64 and rounded
     once so that every implementation in this repo (CUDA, oracles, slab ranks) gets bit-identical lattices."""
-    return pos.to(torch.float64).mean(dim=0).to(torch.float32)
+    m = ops.valid_rows_mask(pos)
+    if m is None:
+        return pos.to(torch.float64).mean(dim=0).to(torch.float32)
+    # capacity-sized buffer: mean over the valid rows only (count on the device, no host sync)
+    p64 = torch.where(m[:, None], pos.to(torch.float64), torch.zeros((), dtype=torch.float64, device=pos.device))
+    return (p64.sum(dim=0) / ops.count_of(pos).to(torch.float64)).to(torch.float32)
 
 
 def grid_pos(pos, voxel_size, centralize=False, pad=0, hyst=0.1, center=None):

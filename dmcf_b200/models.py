@@ -49,18 +49,18 @@ class Dense(torch.nn.Module):
 
 
 def align_vector(v0, v1):
-    """Rotation taking v0 onto v1 (models/pbf_model.py:12-28); 3x3 float32 tensor on v1's device."""
+    """Rotation taking v0 onto v1 (models/pbf_model.py:12-28); 3x3 float32 tensor on v1's device.  Branch-free (the
+    degenerate parallel / antiparallel case is a select on the device): no host sync, CUDA-graph capturable."""
     v0n = v0 / (torch.linalg.norm(v0) + 1e-9)
     v1n = v1 / (torch.linalg.norm(v1) + 1e-9)
     v = torch.linalg.cross(v0n, v1n)
     c = torch.dot(v0n, v1n)
     s = torch.linalg.norm(v)
     eye = torch.eye(3, device=v1.device, dtype=v1.dtype)
-    if float(s) < 1e-6:
-        return eye * (-1.0 if float(c) < 0 else 1.0)
     z = torch.zeros((), device=v1.device, dtype=v1.dtype)
     vx = torch.stack([torch.stack([z, -v[2], v[1]]), torch.stack([v[2], z, -v[0]]), torch.stack([-v[1], v[0], z])])
-    return eye + vx + (vx @ vx) / (1 + c)
+    general = eye + vx + (vx @ vx) / torch.where(s < 1e-6, torch.ones_like(c), 1 + c)
+    return torch.where(s < 1e-6, eye * torch.where(c < 0, -torch.ones_like(c), torch.ones_like(c)), general)
 
 
 class BaseModel(torch.nn.Module):
@@ -236,15 +236,15 @@ class PBFNet(BaseModel):
         dev = pos.device
         tr = self.transformation
         if "translate" in tr:
-            t = torch.tensor(tr["translate"], dtype=torch.float32, device=dev)
+            t = self._const("translate", tr["translate"], dev)
             pos, box = pos + t, box + t
         if "scale" in tr:
-            s = torch.tensor(tr["scale"], dtype=torch.float32, device=dev)
+            s = self._const("scale", tr["scale"], dev)
             pos, box, vel = pos * s, box * s, vel * s
             if acc is not None:
                 acc = acc * s
         if "grav_eqvar" in tr:
-            g = torch.tensor(tr["grav_eqvar"], dtype=torch.float32, device=dev)
+            g = self._const("grav_eqvar", tr["grav_eqvar"], dev)
             if acc is None or acc.shape[0] == 0:
                 raise ValueError("grav_eqvar needs the per-particle acceleration of at least one particle (data[2])")
             self.R = align_vector(g, acc[0])
@@ -259,11 +259,18 @@ class PBFNet(BaseModel):
             Rt = self.R.t()
             pos, vel = pos @ Rt, vel @ Rt
         if "scale" in tr:
-            s = torch.clamp(torch.tensor(tr["scale"], dtype=torch.float32, device=dev), min=1e-5)
+            s = torch.clamp(self._const("scale", tr["scale"], dev), min=1e-5)
             pos, vel = pos / s, vel / s
         if "translate" in tr:
-            pos = pos - torch.tensor(tr["translate"], dtype=torch.float32, device=dev)
+            pos = pos - self._const("translate", tr["translate"], dev)
         return pos, vel
+
+    def _const(self, name, value, device):
+        """Small constant of the config as a device tensor, uploaded once (an upload per step would be a host sync)."""
+        key = ("const", name, str(device))
+        if key not in self._wcache:
+            self._wcache[key] = torch.tensor(value, dtype=torch.float32, device=device)
+        return self._wcache[key]
 
     # -- full step ------------------------------------------------------------------------------------------
     def call(self, data, training=False, **kwargs):
@@ -294,7 +301,8 @@ class PBFNet(BaseModel):
         key = (box.data_ptr(), bfeats.data_ptr(), box.shape[0], box._version, bfeats._version)
         if self._box_cache is None or self._box_cache[0] != key:
             if box.shape[0] > 0:
-                perm = ops.CellList(box, self.particle_radii[0]).sorted_index[: box.shape[0]].long()
+                with ops.no_plan():  # static over the rollout: not one of the step's data-dependent sizes
+                    perm = ops.CellList(box, self.particle_radii[0]).sorted_index[: box.shape[0]].long()
                 self._box_cache = (key, box[perm].contiguous(), bfeats[perm].contiguous(), box, bfeats)
             else:
                 self._box_cache = (key, box, bfeats, box, bfeats)
@@ -307,6 +315,7 @@ class PBFNet(BaseModel):
         filter_extent = [np.float32(r) * np.float32(2) for r in self.particle_radii]
         e_last = float(filter_extent[-1])
         slab = self.slab if (self.slab is not None and self.slab.world > 1) else None
+        n_box_dev = None
         if pos.shape[0] > 0 or slab is not None:
             if pos.shape[0] > 0:
                 lo, hi = pos.amin(dim=0), pos.amax(dim=0)
@@ -316,7 +325,17 @@ class PBFNet(BaseModel):
             if slab is not None:  # the cull uses the GLOBAL fluid bounding box (models/pbf_model.py:330-334)
                 lo, hi = slab.all_reduce_minmax(lo, hi)
             fltr = ((box >= lo - e_last) & (box <= hi + e_last)).all(dim=1)
-            box, bfeats = box[fltr], bfeats[fltr]
+            plan = ops.PLAN if self.fused else None
+            if plan is not None and plan.mode == "replay":
+                # sync-free cull: stable compaction into a capacity-sized buffer, the count stays on the device
+                e, slot = plan.next("rows")
+                cap = min(box.shape[0], int(e["n"] * ops.StepPlan.ROW_SLACK) + 256)
+                idx, n_box_dev = ops.compact_mask(fltr, cap, plan.hard(slot))
+                box, bfeats = box[idx], bfeats[idx]
+            else:
+                box, bfeats = box[fltr], bfeats[fltr]
+                if plan is not None:
+                    plan.record("rows", n=box.shape[0])
         n_f, n_b = pos.shape[0], box.shape[0]
         fluid_feats = [torch.ones_like(pos[:, :1])]
         if self.use_vel:
@@ -333,6 +352,8 @@ class PBFNet(BaseModel):
         if self.use_box_feats:
             box_feats.append(bfeats)
         all_pos = torch.cat([pos, box], dim=0)
+        if n_box_dev is not None:  # rows [n_f + n_box_dev, n_f + capacity) are padding
+            all_pos = ops.with_count(all_pos, (n_box_dev + n_f).to(torch.int32))
         self.all_pos = all_pos
         dens0 = None
         if self.dens_feats or self.dens_norm or self.pres_feats:  # models/pbf_model.py:351-367

@@ -30,6 +30,104 @@ MAX_CELLS = 1 << 24
 # bench.py sets this to a list to get one {start,end CUDA events + shape metadata} record per conv launch
 PROFILE = None
 
+# ---- sync-free steps: capacity-sized buffers, device-side counts, a plan of the data-dependent sizes ---------------------
+# A step has a handful of data-dependent sizes (cell-grid extents, neighbour pairs per list, culled boundary rows, lattice
+# points per scale).  The reference's graph mode (pipelines/simulator.py:57, tf.function) hides them inside TensorFlow's
+# dynamic shapes; here a StepPlan records them once in a MEASURING step (exact sizes read back from the device, i.e. with host
+# syncs) and every later step REPLAYS the plan: buffers get the recorded size plus slack, the true counts stay in device
+# memory (`with_count`), kernels are launched for the capacity and ignore rows beyond the count, and anything that outgrows
+# its capacity raises a flag in `StepPlan.flags` that the caller reads ONCE at the end of the step (dmcf_b200/simulator.py).
+# Such a step makes no host sync and can be captured in a CUDA graph.
+PLAN = None
+
+
+class StepPlan:
+    """Sequence of the data-dependent size decisions of one model step, in call order (the control flow of a step is fixed by
+    the model, so the i-th decision of every step is the same one)."""
+
+    PAIR_SLACK, ROW_SLACK, GRID_PAD_CELLS = 1.25, 1.25, 2
+
+    def __init__(self, device):
+        self.entries = []
+        self.mode = "measure"
+        self.i = 0
+        self.device = device
+        self.flags = None  # int32 [2 * n_entries]: hard (results invalid) flags first, soft (re-plan, results fine) after
+
+    def begin(self, mode):
+        self.mode, self.i = mode, 0
+        if mode == "measure":
+            self.entries = []
+            self.flags = None
+        else:
+            if self.flags is None:
+                self.flags = torch.zeros(2 * max(len(self.entries), 1), dtype=torch.int32, device=self.device)
+            else:
+                self.flags.zero_()
+
+    def record(self, kind, **vals):
+        self.entries.append(dict(kind=kind, **vals))
+
+    def next(self, kind):
+        if self.i >= len(self.entries) or self.entries[self.i]["kind"] != kind:
+            raise DmcfError(f"step plan out of sequence at entry {self.i}: wanted {kind!r}, plan has "
+                            f"{self.entries[self.i]['kind'] if self.i < len(self.entries) else 'nothing'!r}")
+        e = self.entries[self.i]
+        slot = self.i
+        self.i += 1
+        return e, slot
+
+    def hard(self, slot):
+        """int32 view of the hard-overflow flag of entry ``slot``."""
+        return self.flags[slot:slot + 1]
+
+    def soft(self, slot):
+        return self.flags[len(self.entries) + slot:len(self.entries) + slot + 1]
+
+
+class no_plan:
+    """Context: run ops outside the plan (static, cached pieces such as the cell order of the boundary)."""
+
+    def __enter__(self):
+        global PLAN
+        self.saved, PLAN = PLAN, None
+
+    def __exit__(self, *exc):
+        global PLAN
+        PLAN = self.saved
+
+
+def with_count(t, n_dev):
+    """Marks ``t`` ([capacity, ...]) as holding only ``n_dev`` (int32 device tensor [1]) valid leading rows."""
+    t._dmcf_n_dev = n_dev
+    return t
+
+
+def count_of(t):
+    return getattr(t, "_dmcf_n_dev", None)
+
+
+def valid_rows_mask(t):
+    """Bool [capacity] mask of the valid rows of a capacity-sized tensor (all True without a device-side count)."""
+    n_dev = count_of(t)
+    if n_dev is None:
+        return None
+    return torch.arange(t.shape[0], device=t.device, dtype=torch.int32) < n_dev
+
+
+def compact_mask(mask, capacity, overflow=None):
+    """Stable compaction of the True rows of ``mask`` without a host sync: (index int64 [capacity] -- entries beyond the count
+    are 0 --, count int32 [1]).  More than ``capacity`` True rows set ``overflow``."""
+    n = mask.shape[0]
+    c = torch.cumsum(mask.to(torch.int32), 0, dtype=torch.int32)
+    count = c[-1:].clone() if n > 0 else torch.zeros(1, dtype=torch.int32, device=mask.device)
+    dst = torch.where(mask & (c <= capacity), (c - 1).to(torch.int64), torch.full((), capacity, dtype=torch.int64, device=mask.device))
+    idx = torch.zeros(capacity + 1, dtype=torch.int64, device=mask.device)
+    idx.scatter_(0, dst, torch.arange(n, device=mask.device, dtype=torch.int64))
+    if overflow is not None:
+        overflow.copy_(torch.maximum(overflow, (count > capacity).to(torch.int32)))
+    return idx[:capacity], torch.clamp(count, max=capacity)
+
 
 def _prof_begin(kind, **meta):
     """bench.py's per-op timing hook for the HBM-bound ops around the convs (record has a ``kind`` key; conv records do not)."""
@@ -86,8 +184,10 @@ def _pos(t, name):
 class CellList:
     """Uniform cell list over a point set (the reference's ``build_spatial_hash_table`` result)."""
 
-    def __init__(self, points, cell_size, origin=None, dims=None):
+    def __init__(self, points, cell_size, origin=None, dims=None, n_dev=None):
         lib = _lib.load()
+        if n_dev is None:
+            n_dev = count_of(points)
         points = _pos(points, "points")
         n = points.shape[0]
         if n >= 2 ** 31:
@@ -95,14 +195,40 @@ class CellList:
         cell_size = float(cell_size)
         if not cell_size > 0:
             raise ValueError("cell_size must be positive")
+        if (origin is None or dims is None) and PLAN is not None and PLAN.mode == "replay":
+            # planned grid: the measured bounding box padded by a few cells; points that leave it are clamped into the border
+            # cells (always correct) and raise the SOFT flag so that the caller re-plans after this step
+            e, slot = PLAN.next("grid")
+            pad = [StepPlan.GRID_PAD_CELLS * cell_size + 0.05 * (e["hi"][a] - e["lo"][a]) for a in range(3)]
+            origin = [e["lo"][a] - pad[a] for a in range(3)]
+            while True:
+                dims = [int((e["hi"][a] + pad[a] - origin[a]) / cell_size) + 1 for a in range(3)]
+                if dims[0] * dims[1] * dims[2] <= MAX_CELLS:
+                    break
+                cell_size *= 1.26
+            if n > 0:
+                bounds = e.get("_bounds")
+                if bounds is None:  # uploaded once per plan (outside any graph capture: the first replay runs eagerly)
+                    lo_t = torch.tensor(origin, dtype=torch.float32)
+                    hi_t = torch.tensor([origin[a] + dims[a] * cell_size for a in range(3)], dtype=torch.float32)
+                    bounds = e["_bounds"] = (lo_t.to(points.device), hi_t.to(points.device))
+                out = (points < bounds[0]) | (points > bounds[1])
+                m = None if n_dev is None else (torch.arange(n, device=points.device, dtype=torch.int32) < n_dev)
+                out = out.any(dim=1) if m is None else (out.any(dim=1) & m)
+                soft = PLAN.soft(slot)
+                soft.copy_(torch.maximum(soft, out.any().to(torch.int32).reshape(1)))
         if origin is None or dims is None:
             if n > 0:
+                if n_dev is not None:
+                    raise DmcfError("a capacity-sized point set needs a planned grid (origin / dims)")
                 lo = points.amin(dim=0)
                 hi = points.amax(dim=0)
-                lohi = torch.stack([lo, hi]).cpu()  # one host sync per build; pass origin/dims to avoid it
+                lohi = torch.stack([lo, hi]).cpu()  # one host sync per build; pass origin/dims (or run under a StepPlan) to avoid it
                 lo, hi = lohi[0].tolist(), lohi[1].tolist()
             else:
                 lo, hi = [0.0] * 3, [0.0] * 3
+            if PLAN is not None and PLAN.mode == "measure":
+                PLAN.record("grid", lo=lo, hi=hi)
             while True:
                 dims = [int((hi[a] - lo[a]) / cell_size) + 1 for a in range(3)]
                 if dims[0] * dims[1] * dims[2] <= MAX_CELLS:
@@ -114,8 +240,10 @@ class CellList:
         self.n_cells = int(dims[0]) * int(dims[1]) * int(dims[2])
         dev = points.device
         self.cell_start = torch.empty(self.n_cells + 1, dtype=torch.int32, device=dev)
-        self.sorted_index = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        # with a device-side count the entries beyond it are never written: keep them valid indices (callers gather with them)
+        self.sorted_index = (torch.zeros if n_dev is not None else torch.empty)(max(n, 1), dtype=torch.int32, device=dev)
         self.sorted_pos = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+        self.n_dev = n_dev
         g = Grid()
         g.origin[:] = [float(v) for v in origin]
         g.inv_cell = 1.0 / cell_size
@@ -124,6 +252,7 @@ class CellList:
         g.cell_start = self.cell_start.data_ptr()
         g.sorted_index = self.sorted_index.data_ptr()
         g.sorted_pos = self.sorted_pos.data_ptr()
+        g.n_points_dev = None if n_dev is None else n_dev.data_ptr()
         self.grid = g
         ws_bytes = lib.dmcf_grid_workspace_bytes(n, self.n_cells)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -148,39 +277,61 @@ def exclusive_scan(counts, out_dtype=torch.int64):
 def neighbor_counts(points, queries, radius, ignore_query_point=False, cell_list=None):
     """Per-query neighbour count (== reduce_subarrays_sum(ones, row_splits), models/pbf_model.py:450-453)."""
     lib = _lib.load()
+    nq_dev = count_of(queries)
     queries = _pos(queries, "queries")
     if cell_list is None:
         cell_list = CellList(points, max(float(radius), 1e-30))
     counts = torch.empty(queries.shape[0], dtype=torch.int32, device=queries.device)
-    check(lib.dmcf_frs_count(C.byref(cell_list.grid), _p(queries), queries.shape[0], float(radius),
+    check(lib.dmcf_frs_count(C.byref(cell_list.grid), _p(queries), queries.shape[0], _p(nq_dev), float(radius),
                              int(bool(ignore_query_point)), _p(counts), _stream()))
     return counts, cell_list
 
 
 def fixed_radius_search(points, queries, radius, ignore_query_point=False, return_distances=True, cell_list=None,
-                        metric="L2"):
+                        metric="L2", capacity=None, overflow=None):
     """CSR neighbour lists within ``radius`` (L2, inclusive).  Same outputs as the reference layer:
-    neighbors_index int32 [P], neighbors_row_splits int64 [Nq+1], neighbors_distance float32 [P] (squared)."""
+    neighbors_index int32 [P], neighbors_row_splits int64 [Nq+1], neighbors_distance float32 [P] (squared).
+
+    The number of pairs is data dependent: by default it is read back from the device (ONE host sync, like the reference op's
+    output allocation).  With ``capacity`` (or under a replaying StepPlan) nothing is read back: ``neighbors_index`` has
+    ``capacity`` entries, the true total stays in ``neighbors_row_splits[-1]`` on the device, and a list that outgrows the
+    capacity is truncated and raises ``overflow`` (int32 device tensor [1])."""
     if metric != "L2":
         raise NotImplementedError("only the L2 metric is supported (DMCF never uses another one)")
     lib = _lib.load()
-    points = _pos(points, "points")
-    queries = _pos(queries, "queries")
+    nq_dev = count_of(queries)
+    points_c = _pos(points, "points")
+    queries_c = _pos(queries, "queries")
     radius = float(radius)
     if cell_list is None:  # built (and profiled) on its own
         cell_list = CellList(points, max(radius, 1e-30))
+    points, queries = points_c, queries_c
     rec = _prof_begin("frs_count", n_points=points.shape[0], n_queries=queries.shape[0])
-    counts, cell_list = neighbor_counts(points, queries, radius, ignore_query_point, cell_list)
+    counts = torch.empty(queries.shape[0], dtype=torch.int32, device=queries.device)
+    check(lib.dmcf_frs_count(C.byref(cell_list.grid), _p(queries), queries.shape[0], _p(nq_dev), radius,
+                             int(bool(ignore_query_point)), _p(counts), _stream()))
     row_splits = exclusive_scan(counts, torch.int64)
     _prof_end(rec)
     nq = queries.shape[0]
-    total = int(row_splits[-1].item())  # data-dependent output size: the one host sync of the op
+    if capacity is None and PLAN is not None and PLAN.mode == "replay":
+        e, slot = PLAN.next("pairs")
+        capacity = int(e["total"] * StepPlan.PAIR_SLACK) + 4096
+        overflow = PLAN.hard(slot)
+    if capacity is None:
+        total = int(row_splits[-1].item())  # data-dependent output size: the one host sync of the op
+        if PLAN is not None and PLAN.mode == "measure":
+            PLAN.record("pairs", total=total)
+    else:
+        total = int(capacity)
+        if overflow is not None:  # flag here as well: the fill below only sees rows, the convs only see the clamped offsets
+            overflow.copy_(torch.maximum(overflow, (row_splits[-1:] > total).to(torch.int32)))
+        row_splits.clamp_(max=total)  # a truncated list must never send a consumer beyond the buffers
     index = torch.empty(total, dtype=torch.int32, device=queries.device)
     dist = torch.empty(total if return_distances else 0, dtype=torch.float32, device=queries.device)
     if total > 0:
         rec = _prof_begin("frs_fill", n_points=points.shape[0], n_queries=nq, pairs=total, distances=bool(return_distances))
-        check(lib.dmcf_frs_fill(C.byref(cell_list.grid), _p(queries), nq, radius, int(bool(ignore_query_point)),
-                                _p(row_splits), total, _p(index), _p(dist) if return_distances else None, None,
+        check(lib.dmcf_frs_fill(C.byref(cell_list.grid), _p(queries), nq, _p(nq_dev), radius, int(bool(ignore_query_point)),
+                                _p(row_splits), total, _p(index), _p(dist) if return_distances else None, _p(overflow),
                                 _stream()))
         _prof_end(rec)
     return NeighborSearchResult(index, row_splits, dist)
@@ -202,6 +353,7 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     extras (see include/dmcf_b200.h).  ``filters`` is [kz,ky,kx,Cin,Cout] or, with a fused Dense, the flattened
     [(kz*ky*kx*Cin + dense_cin), Cout] matrix together with ``kernel_size``."""
     lib = _lib.load()
+    n_out_dev = count_of(out_positions)
     _req(filters, "filters")
     if filters.dim() == 5:
         kz, ky, kx, cin, cout = filters.shape
@@ -260,6 +412,7 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     d.dense_cin = int(dense_cin)
     d.accumulate = int(bool(accumulate))
     d.filter_antisym = int(bool(antisymmetric_filter))  # promise: filters[rev(cell)] == -filters[cell] exactly
+    d.n_out_dev = None if n_out_dev is None else n_out_dev.data_ptr()
     dense_stride = 0
     if dense_cin:
         dense_inp, dense_stride = _rows(dense_inp, "dense_inp")
@@ -364,6 +517,7 @@ def prepare_pair_records(kernel_size, out_positions, extents, offset, inp_positi
     """Per-pair geometry of a neighbour list, evaluated once and shared by every conv with the same geometry arguments
     (dmcf_cconv_prepare).  Returns a [9, n_pairs] float32 tensor to pass as ``pair_records`` to continuous_conv."""
     lib = _lib.load()
+    n_out_dev = count_of(out_positions)
     out_positions = _pos(out_positions, "out_positions")
     inp_positions = _pos(inp_positions, "inp_positions")
     _req(neighbors_index, "neighbors_index", torch.int32, 1)
@@ -387,6 +541,7 @@ def prepare_pair_records(kernel_size, out_positions, extents, offset, inp_positi
     d.feat_scale = 1.0
     d.skip_self = int(bool(skip_self))
     d.nbr_lo, d.nbr_hi = (0, 0) if nbr_range is None else (int(nbr_range[0]), int(nbr_range[1]))
+    d.n_out_dev = None if n_out_dev is None else n_out_dev.data_ptr()
     n_pairs = int(neighbors_index.shape[0])
     records = torch.empty((9, n_pairs), dtype=torch.float32, device=out_positions.device)
     rec = _prof_begin("pair_records", n_inp=inp_positions.shape[0], n_out=out_positions.shape[0], pairs=n_pairs)
@@ -446,15 +601,42 @@ def correct(pos, pos2, net, out_scale, dt):
 
 
 def grid_pos(pos, voxel, center=None, hyst=0.1):
-    """Lattice sampling of utils/tools/losses.py:136-181 (``center`` is None when not centralised)."""
+    """Lattice sampling of utils/tools/losses.py:136-181 (``center`` is None when not centralised).
+
+    The number of lattice points (and the integer bounds of the lattice) are data dependent: by default they are read back from
+    the device (two host syncs).  Under a replaying StepPlan the bounds and the capacity come from the plan, ``center`` stays on
+    the device and the result is a capacity-sized tensor with its count attached (``count_of``)."""
     import numpy as np
     lib = _lib.load()
+    n_dev = count_of(pos)
     pos = _pos(pos, "pos")
     n = pos.shape[0]
-    if n == 0:
-        return torch.empty((0, 3), dtype=torch.float32, device=pos.device)
     f32 = np.float32
     v = np.asarray(voxel, f32).reshape(3)
+    cv = (C.c_float * 3)(*[float(x) for x in v])
+    if PLAN is not None and PLAN.mode == "replay":
+        e, slot = PLAN.next("lattice")
+        active = (v >= f32(1e-5)).astype(np.int64)
+        lo = np.asarray(e["lo"], np.int64) - 2 * active
+        dims = np.asarray(e["dims"], np.int64) + 4 * active
+        capacity = int(e["count"] * StepPlan.ROW_SLACK) + 64
+        n_cells = int(dims[0]) * int(dims[1]) * int(dims[2])
+        clo = (C.c_int32 * 3)(*[int(x) for x in lo])
+        cd = (C.c_int32 * 3)(*[int(x) for x in dims])
+        c_dev = None if center is None else _req(center, "center", dim=1).contiguous()
+        flags = torch.zeros(n_cells, dtype=torch.int32, device=pos.device)
+        ovf = PLAN.hard(slot)
+        check(lib.dmcf_grid_pos_mark(_p(pos), n, _p(n_dev), cv, None, _p(c_dev), float(hyst), clo, cd, _p(flags), _p(ovf), _stream()))
+        offsets = exclusive_scan(flags, torch.int32)
+        out = torch.zeros((capacity, 3), dtype=torch.float32, device=pos.device)
+        check(lib.dmcf_grid_pos_emit(_p(flags), _p(offsets), cv, None, _p(c_dev), clo, cd, _p(out), capacity, _p(ovf), _stream()))
+        return with_count(out, torch.clamp(offsets[-1:], max=capacity))
+    if n_dev is not None:
+        raise DmcfError("grid_pos of a capacity-sized point set needs a replaying StepPlan")
+    if n == 0:
+        if PLAN is not None and PLAN.mode == "measure":
+            raise DmcfError("cannot plan a step on an empty particle set")
+        return torch.empty((0, 3), dtype=torch.float32, device=pos.device)
     stats = [pos.amin(dim=0), pos.amax(dim=0)]
     if center is not None:
         stats.append(_req(center, "center", dim=1))
@@ -470,17 +652,18 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
     n_cells = int(dims[0]) * int(dims[1]) * int(dims[2])
     if n_cells >= 2 ** 31 or np.any(np.abs(lo) >= 2 ** 30):
         raise DmcfError(f"grid_pos lattice of {dims.tolist()} voxels is too large")
-    cv = (C.c_float * 3)(*[float(x) for x in v])
     cc = (C.c_float * 3)(*[float(x) for x in c]) if center is not None else None
     clo = (C.c_int32 * 3)(*[int(x) for x in lo])
     cd = (C.c_int32 * 3)(*[int(x) for x in dims])
     flags = torch.zeros(n_cells, dtype=torch.int32, device=pos.device)
-    check(lib.dmcf_grid_pos_mark(_p(pos), n, cv, cc, float(hyst), clo, cd, _p(flags), _stream()))
+    check(lib.dmcf_grid_pos_mark(_p(pos), n, None, cv, cc, None, float(hyst), clo, cd, _p(flags), None, _stream()))
     offsets = exclusive_scan(flags, torch.int32)
     count = int(offsets[-1].item())
+    if PLAN is not None and PLAN.mode == "measure":
+        PLAN.record("lattice", lo=[int(x) for x in lo], dims=[int(x) for x in dims], count=count)
     out = torch.empty((count, 3), dtype=torch.float32, device=pos.device)
     if count:
-        check(lib.dmcf_grid_pos_emit(_p(flags), _p(offsets), cv, cc, clo, cd, _p(out), _stream()))
+        check(lib.dmcf_grid_pos_emit(_p(flags), _p(offsets), cv, cc, None, clo, cd, _p(out), -1, None, _stream()))
     return out
 
 

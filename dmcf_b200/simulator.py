@@ -22,23 +22,72 @@ def _to_dev(a, device):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
 
 
+class _PlannedStep:
+    """State of the sync-free step of one (particle count, boundary) signature: the plan of its data-dependent sizes, the
+    pinned copy of its overflow flags, and (graph mode) the captured CUDA graph with its static input / output buffers."""
+
+    def __init__(self, sig):
+        self.sig = sig
+        self.plan = None
+        self.replays = 0
+        self.graph = None
+        self.graph_failed = False
+        self.static_in = None
+        self.static_out = None
+        self.graph_launches = 0  # kernels of libdmcf_b200 inside one replay of the graph
+        self.flags_host = None
+        self.event = None
+
+
 class Simulator:
-    """Pipeline for the trainable simulator (inference only)."""
+    """Pipeline for the trainable simulator (inference only).
+
+    ``step_mode`` selects how ``step`` drives the model (the reference compiles its step with tf.function,
+    pipelines/simulator.py:57):
+      * ``"eager"``   every data-dependent size (cell-grid extent, pairs per neighbour list, culled boundary rows, lattice
+                      points per scale) is read back from the device when it is needed: ~10-60 host syncs per step;
+      * ``"planned"`` the first step of a scene measures those sizes (eager), later steps replay the plan on capacity-sized
+                      buffers with device-side counts: NO host sync inside the step, one overflow-flag read after it;
+      * ``"graph"``   (default) the planned step captured in a CUDA graph and replayed: one launch per step.
+    A step whose plan overflows (or whose particles leave the planned cell grids) is detected by the flag read, recomputed
+    exactly by a fresh measuring step and re-planned; results returned by ``step`` are always those of a valid step.
+    Models that cannot be planned (layer-by-layer path, slab decomposition) run eagerly."""
 
     def __init__(self, model, dataset=None, name="Simulator", main_log_dir="./logs/", device="cuda", split="test",
-                 **kwargs):
+                 step_mode="graph", **kwargs):
         self.model = model
         self.dataset = dataset
         self.name = name
         self.device = torch.device(device if device != "gpu" else "cuda")
         if self.device.type != "cuda":
             raise RuntimeError("dmcf_b200 runs on CUDA devices only (no CPU fallback)")
+        if step_mode not in ("eager", "planned", "graph"):
+            raise ValueError("step_mode must be 'eager', 'planned' or 'graph'")
+        self.step_mode = step_mode
         self.cfg = dict(kwargs, main_log_dir=main_log_dir, split=split)
         self.timing = []
+        self._planned = None
+        self.stats = {"measured": 0, "replayed": 0, "graph_replays": 0, "replans": 0, "captures": 0}
+
+    # -- one step ---------------------------------------------------------------------------------------------------------
+    def _plannable(self, inputs):
+        m = self.model
+        slab = getattr(m, "slab", None)
+        if self.step_mode == "eager" or not getattr(m, "fused", False) or (slab is not None and slab.world > 1):
+            return False
+        if inputs[0].shape[0] == 0 or inputs[4].shape[0] == 0:
+            return False
+        # the planned step is inference only (no autograd through capacity-sized buffers)
+        return not any(p.requires_grad for p in m.parameters()) and not any(
+            t is not None and t.requires_grad for t in inputs[:3])
 
     def step(self, inputs):
         """One model call on one sample ``[pos, vel, acc|None, feats|None, box, box_normals]`` -> the next sample
         (the body of run_inference, pipelines/simulator.py:68-70)."""
+        if self._plannable(inputs):
+            with torch.no_grad():
+                pos, vel = self._step_planned(inputs)
+            return [pos, vel] + list(inputs[2:])
         pos, vel = self.model(inputs, training=False)
         slab = getattr(self.model, "slab", None)
         if slab is not None and slab.world > 1:
@@ -48,6 +97,92 @@ class Simulator:
                 return [pos, vel, acc] + list(inputs[3:])
             pos, vel = slab.migrate(pos, vel)
         return [pos, vel] + list(inputs[2:])
+
+    def _run_model(self, inputs, plan, mode):
+        from . import ops
+        plan.begin(mode)
+        ops.PLAN = plan
+        try:
+            return self.model(inputs, training=False)
+        finally:
+            ops.PLAN = None
+
+    def _step_planned(self, inputs):
+        from . import ops
+        pos, vel, acc, feats, box, bn = inputs
+        sig = (pos.shape[0], acc is None, box.data_ptr(), box.shape[0], box._version, bn.data_ptr(), bn._version)
+        st = self._planned
+        if st is None or st.sig != sig:
+            st = self._planned = _PlannedStep(sig)  # new scene / particle count (inflow): plan again
+        if st.plan is None:
+            # measuring step: the eager path (exact sizes, host syncs) with the sizes recorded
+            plan = ops.StepPlan(pos.device)
+            out = self._run_model(inputs, plan, "measure")
+            st.plan, st.replays, st.graph = plan, 0, None
+            self.stats["measured"] += 1
+            return out
+        if st.event is None:
+            st.event = torch.cuda.Event()
+        if self.step_mode == "graph" and st.graph is None and not st.graph_failed and st.replays >= 1:
+            self._capture(st, inputs)
+        if st.graph is not None:
+            st.static_in[0].copy_(pos)
+            st.static_in[1].copy_(vel)
+            if acc is not None:
+                st.static_in[2].copy_(acc)
+            st.graph.replay()
+            out = (st.static_out[0].clone(), st.static_out[1].clone())
+            self.stats["graph_replays"] += 1
+            self.stats["graph_kernel_launches"] = self.stats.get("graph_kernel_launches", 0) + st.graph_launches
+        else:
+            out = self._run_model(inputs, st.plan, "replay")
+            if st.flags_host is None or st.flags_host.shape != st.plan.flags.shape:
+                st.flags_host = torch.zeros(st.plan.flags.shape, dtype=torch.int32).pin_memory()
+            st.flags_host.copy_(st.plan.flags, non_blocking=True)
+        st.replays += 1
+        self.stats["replayed"] += 1
+        # the ONE read-back of the step: its overflow flags, after everything was enqueued
+        st.event.record()
+        st.event.synchronize()
+        n = len(st.plan.entries)
+        hard, soft = bool(st.flags_host[:n].any()), bool(st.flags_host[n:].any())
+        if hard:  # something outgrew its capacity: the results are invalid -> exact step + new plan
+            log.info("step plan overflowed (entries %s): re-planning", torch.nonzero(st.flags_host[:n]).flatten().tolist())
+            st.plan, st.graph = None, None
+            self.stats["replans"] += 1
+            return self._step_planned(inputs)
+        if soft:  # particles left a planned cell grid (results are fine, the grid is just no longer tight): plan again next step
+            st.plan, st.graph = None, None
+            self.stats["replans"] += 1
+        return out
+
+    def _capture(self, st, inputs):
+        """Captures the replaying step on static input buffers.  Any failure (an op that cannot be captured) leaves the
+        simulator in planned mode."""
+        from . import ops
+        pos, vel, acc, feats, box, bn = inputs
+        saved_profile, ops.PROFILE = ops.PROFILE, None  # per-launch CUDA events cannot be recorded into a capture
+        try:
+            st.static_in = [torch.empty_like(pos), torch.empty_like(vel), None if acc is None else torch.empty_like(acc)]
+            for dst, src in zip(st.static_in, (pos, vel, acc)):
+                if dst is not None:
+                    dst.copy_(src)
+            if st.flags_host is None or st.flags_host.shape != st.plan.flags.shape:
+                st.flags_host = torch.zeros(st.plan.flags.shape, dtype=torch.int32).pin_memory()
+            torch.cuda.synchronize(pos.device)
+            g = torch.cuda.CUDAGraph()
+            launches0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                out = self._run_model([st.static_in[0], st.static_in[1], st.static_in[2], feats, box, bn], st.plan, "replay")
+                st.flags_host.copy_(st.plan.flags, non_blocking=True)
+            st.graph, st.static_out, st.graph_launches = g, out, ops.launch_count() - launches0
+            self.stats["captures"] += 1
+        except Exception as e:  # noqa: BLE001
+            log.warning("CUDA graph capture of the step failed (%s: %s); staying in planned mode", type(e).__name__, e)
+            st.graph, st.graph_failed = None, True
+            torch.cuda.synchronize(pos.device)
+        finally:
+            ops.PROFILE = saved_profile
 
     @torch.no_grad()
     def run_inference(self, inputs):

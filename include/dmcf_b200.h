@@ -17,6 +17,11 @@
  *     (the library never allocates or frees device memory);
  *   - every entry point takes the CUDA stream to enqueue on (a cudaStream_t passed as void*), never
  *     synchronises the device and is CUDA-graph capturable unless stated otherwise;
+ *   - DEVICE-SIDE COUNTS (sync-free, CUDA-graph capturable steps): a point set may be a capacity-sized buffer whose number of
+ *     valid rows lives in device memory (dmcf_grid::n_points_dev, n_queries_dev, dmcf_conv_desc::n_out_dev; NULL = the host
+ *     count is exact).  The host count is then the CAPACITY; kernels are launched for it and ignore rows >= the device count.
+ *     Data-dependent OUTPUT sizes (neighbour pairs, lattice points) are bounded by a caller-given capacity; exceeding it sets
+ *     the caller's overflow flag (device int32, read once at the end of the step) instead of writing out of bounds;
  *   - return value 0 = success; otherwise an error code, message via dmcf_last_error() (thread local);
  *   - positions are float32 [n,3] row-major; features float32 row-major with an explicit row stride
  *     (in floats); neighbour lists are CSR: int32 index [P], int64 row_splits [n_out+1].
@@ -31,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DMCF_B200_VERSION 103
+#define DMCF_B200_VERSION 104
 
 enum dmcf_status {
     DMCF_OK = 0,
@@ -67,6 +72,8 @@ typedef struct dmcf_grid {
     int32_t* cell_start;   /* [dims[0]*dims[1]*dims[2] + 1] */
     int32_t* sorted_index; /* [n_points] */
     float* sorted_pos;     /* [n_points,4], 16-byte aligned */
+    const int32_t* n_points_dev; /* optional device-side count: only rows [0, *n_points_dev) of `points` are inserted (n_points is
+                                    then the capacity; sorted_index / sorted_pos entries beyond the count are not written) */
 } dmcf_grid;
 
 size_t dmcf_grid_workspace_bytes(int64_t n_points, int64_t n_cells);
@@ -81,9 +88,11 @@ int dmcf_grid_build(const float* points, dmcf_grid* grid, void* workspace, size_
  *   dmcf_frs_fill   -> neighbors_index[P] (original point ids), neighbors_distance[P] (squared; may be NULL)
  * Row order: cells ascending (z,y,x), ascending point id inside a cell.
  * ------------------------------------------------------------------------------------------------- */
-int dmcf_frs_count(const dmcf_grid* grid, const float* queries, int64_t n_queries, float radius,
+int dmcf_frs_count(const dmcf_grid* grid, const float* queries, int64_t n_queries, const int32_t* n_queries_dev, float radius,
                    int ignore_query_point, int32_t* counts, void* stream);
-int dmcf_frs_fill(const dmcf_grid* grid, const float* queries, int64_t n_queries, float radius,
+/* `capacity` bounds the pairs written; a row that would pass it sets *overflow_flag = 1 (if given) and is truncated.  With
+ * n_queries_dev the rows >= *n_queries_dev get count 0 / are skipped. */
+int dmcf_frs_fill(const dmcf_grid* grid, const float* queries, int64_t n_queries, const int32_t* n_queries_dev, float radius,
                   int ignore_query_point, const int64_t* row_splits, int64_t capacity,
                   int32_t* neighbors_index, float* neighbors_distance, int32_t* overflow_flag, void* stream);
 
@@ -126,6 +135,8 @@ typedef struct dmcf_conv_desc {
     int32_t filter_antisym; /* the caller guarantees filters[kz-1-z][ky-1-y][kx-1-x] == -filters[z][y][x] (bit exact), as
                                the antisymmetric layer builds its effective kernel (utils/convolutions.py:410-412):
                                allows the folded half-patch kernel k_cconv_apatch.  0 is always safe */
+    const int32_t* n_out_dev; /* optional device-side number of out points (<= n_out, which is then the capacity the kernels
+                                 are launched for); rows >= *n_out_dev of `out` are not written */
 } dmcf_conv_desc;
 
 int dmcf_cconv_forward(const dmcf_conv_desc* desc, const float* filters,
@@ -196,12 +207,18 @@ int dmcf_correct(const float* pos, const float* pos2, const float* net, int64_t 
  *   dmcf_grid_pos_mark -> flags;  dmcf_exclusive_scan_i32_i32(flags) -> offsets (offsets[n_cells] = count);
  *   dmcf_grid_pos_emit -> out[count,3] in ascending linear voxel id (the reference's tf.unique order is
  *   first-occurrence; consumers are order independent).
- * `center_host3` NULL = not centralised (points sit at voxel centres g*v + v/2, else g*v + center).
+ * `center_host3` / `center_dev3` (the same 3 floats in host or in device memory; at most one of them) both NULL = not
+ * centralised (points sit at voxel centres g*v + v/2, else g*v + center).  Sync-free use: lo/dims come from a plan instead of
+ * this step's min/max; a particle that falls outside them sets *overflow_flag (mark), as does a lattice of more than
+ * `capacity` points (emit, which then writes only the first `capacity`; capacity < 0 = unbounded); n_dev = optional device-side
+ * particle count.
  * ------------------------------------------------------------------------------------------------- */
-int dmcf_grid_pos_mark(const float* pos, int64_t n, const float* voxel_host3, const float* center_host3, float hyst,
-                       const int32_t* lo_host3, const int32_t* dims_host3, int32_t* flags, void* stream);
+int dmcf_grid_pos_mark(const float* pos, int64_t n, const int32_t* n_dev, const float* voxel_host3, const float* center_host3,
+                       const float* center_dev3, float hyst, const int32_t* lo_host3, const int32_t* dims_host3, int32_t* flags,
+                       int32_t* overflow_flag, void* stream);
 int dmcf_grid_pos_emit(const int32_t* flags, const int32_t* offsets, const float* voxel_host3, const float* center_host3,
-                       const int32_t* lo_host3, const int32_t* dims_host3, float* out, void* stream);
+                       const float* center_dev3, const int32_t* lo_host3, const int32_t* dims_host3, float* out,
+                       int64_t capacity, int32_t* overflow_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Point-set ops of the reference's in-repo CUDA extensions.
