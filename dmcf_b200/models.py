@@ -297,16 +297,23 @@ class PBFNet(BaseModel):
         return pos, vel
 
     def _sorted_box(self, box, bfeats):
-        """The boundary is static over a rollout: put it in cell order once and reuse."""
+        """The boundary is static over a rollout: put it in cell order once and reuse (a few boundaries are remembered, so
+        that two simulators sharing the model -- or alternating scenes -- do not evict each other)."""
         key = (box.data_ptr(), bfeats.data_ptr(), box.shape[0], box._version, bfeats._version)
-        if self._box_cache is None or self._box_cache[0] != key:
+        if not isinstance(self._box_cache, dict):
+            self._box_cache = {}
+        hit = self._box_cache.get(key)
+        if hit is None:
             if box.shape[0] > 0:
                 with ops.no_plan():  # static over the rollout: not one of the step's data-dependent sizes
                     perm = ops.CellList(box, self.particle_radii[0]).sorted_index[: box.shape[0]].long()
-                self._box_cache = (key, box[perm].contiguous(), bfeats[perm].contiguous(), box, bfeats)
+                hit = (box[perm].contiguous(), bfeats[perm].contiguous(), box, bfeats)  # keeps the keyed tensors alive
             else:
-                self._box_cache = (key, box, bfeats, box, bfeats)
-        return self._box_cache[1], self._box_cache[2]
+                hit = (box, bfeats, box, bfeats)
+            if len(self._box_cache) >= 4:
+                self._box_cache.pop(next(iter(self._box_cache)))
+            self._box_cache[key] = hit
+        return hit[0], hit[1]
 
     # -- preprocess: models/pbf_model.py:303-438 ----------------------------------------------------------------
     def preprocess(self, data, training=False, **kwargs):
