@@ -303,6 +303,7 @@ def fixed_radius_search(points, queries, radius, ignore_query_point=False, retur
     points_c = _pos(points, "points")
     queries_c = _pos(queries, "queries")
     radius = float(radius)
+    true_pairs = None
     if cell_list is None:  # built (and profiled) on its own
         cell_list = CellList(points, max(radius, 1e-30))
     points, queries = points_c, queries_c
@@ -317,6 +318,7 @@ def fixed_radius_search(points, queries, radius, ignore_query_point=False, retur
         e, slot = PLAN.next("pairs")
         capacity = int(e["total"] * StepPlan.PAIR_SLACK) + 4096
         overflow = PLAN.hard(slot)
+        true_pairs = e["total"]  # for the profiling records only (the measured count of the planning step)
     if capacity is None:
         total = int(row_splits[-1].item())  # data-dependent output size: the one host sync of the op
         if PLAN is not None and PLAN.mode == "measure":
@@ -329,11 +331,14 @@ def fixed_radius_search(points, queries, radius, ignore_query_point=False, retur
     index = torch.empty(total, dtype=torch.int32, device=queries.device)
     dist = torch.empty(total if return_distances else 0, dtype=torch.float32, device=queries.device)
     if total > 0:
-        rec = _prof_begin("frs_fill", n_points=points.shape[0], n_queries=nq, pairs=total, distances=bool(return_distances))
+        rec = _prof_begin("frs_fill", n_points=points.shape[0], n_queries=nq, pairs=true_pairs if true_pairs is not None else total,
+                          distances=bool(return_distances))
         check(lib.dmcf_frs_fill(C.byref(cell_list.grid), _p(queries), nq, _p(nq_dev), radius, int(bool(ignore_query_point)),
                                 _p(row_splits), total, _p(index), _p(dist) if return_distances else None, _p(overflow),
                                 _stream()))
         _prof_end(rec)
+    if true_pairs is not None:
+        index._dmcf_true_pairs = true_pairs
     return NeighborSearchResult(index, row_splits, dist)
 
 
@@ -438,7 +443,8 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     if PROFILE is not None:
         rec = dict(kernel=conv_kernel_name((kz, ky, kx), cin, cout, interpolation, int(dense_cin), bool(antisymmetric_filter)),
                    kernel_size=(kz, ky, kx), cin=cin, cout=cout, ascc=bool(ascc), n_inp=n_inp, n_out=n_out,
-                   rows=kz * ky * kx * cin + int(dense_cin), pairs=int(neighbors_index.shape[0]),
+                   rows=kz * ky * kx * cin + int(dense_cin),
+                   pairs=int(getattr(neighbors_index, "_dmcf_true_pairs", neighbors_index.shape[0])),
                    residual=residual is not None, start=torch.cuda.Event(enable_timing=True),
                    end=torch.cuda.Event(enable_timing=True))
         rec["start"].record()
@@ -544,7 +550,8 @@ def prepare_pair_records(kernel_size, out_positions, extents, offset, inp_positi
     d.n_out_dev = None if n_out_dev is None else n_out_dev.data_ptr()
     n_pairs = int(neighbors_index.shape[0])
     records = torch.empty((9, n_pairs), dtype=torch.float32, device=out_positions.device)
-    rec = _prof_begin("pair_records", n_inp=inp_positions.shape[0], n_out=out_positions.shape[0], pairs=n_pairs)
+    rec = _prof_begin("pair_records", n_inp=inp_positions.shape[0], n_out=out_positions.shape[0],
+                      pairs=int(getattr(neighbors_index, "_dmcf_true_pairs", n_pairs)))
     check(lib.dmcf_cconv_prepare(C.byref(d), _p(out_positions), out_positions.shape[0], _p(inp_positions),
                                  inp_positions.shape[0], _p(inp_importance), _p(neighbors_index), _p(neighbors_row_splits),
                                  _p(neighbors_importance), n_pairs, _p(records), _stream()))

@@ -32,22 +32,34 @@ if wname is None:
     model.init_weights(seed=0, device=dev, scale=0.1)
 else:
     model.load_weights(T.load_npz_weights(wname), device=dev)
-sim = Simulator(model, device='cuda')
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
 sample = [t(scene['pos']), t(scene['vel']), None if acc is None else t(acc), None, t(scene['box']), t(scene['box_normals'])]
 print(which, 'fluid', scene['pos'].shape[0], 'boundary', scene['box'].shape[0])
-for _ in range(3): sim.step(sample)
-ops.PROFILE = []
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(steps): out = sim.step(sample)
-e1.record(); torch.cuda.synchronize()
-prof, ops.PROFILE = ops.PROFILE, None
+
+
+def timed(mode, steps, profile=False):
+    sim = Simulator(model, device='cuda', step_mode=mode)
+    with torch.no_grad():
+        for _ in range(4): sim.step(sample)
+        ops.PROFILE = [] if profile else None
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launch_count()
+        e0.record()
+        for _ in range(steps): out = sim.step(sample)
+        e1.record(); torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    return e0.elapsed_time(e1) / steps, prof, (ops.launch_count() - l0) // steps, sim
+
+
+for mode in ('eager', 'planned', 'graph'):
+    ms, _, launches, sim = timed(mode, steps)
+    print('%-8s ms/step %.3f  particles*steps/s %.3e  (host launches/step %d, graph kernels/step %d, stats %s)' % (
+        mode, ms, scene['pos'].shape[0] / ms * 1e3, launches, sim._planned.graph_launches if sim._planned else 0, sim.stats))
+ms, prof, _, _ = timed('planned', steps, profile=True)
 hbm = [r for r in prof if 'kind' in r]
 prof = [r for r in prof if 'kind' not in r]  # conv launches only
-ms = e0.elapsed_time(e1) / steps
-print('ms/step %.2f  particles*steps/s %.3e' % (ms, scene['pos'].shape[0] / ms * 1e3))
+print('per-kernel times below: planned mode with per-launch events, ms/step %.2f' % ms)
 g = {}
 for r in prof:
     k = (r['kernel'], r['kernel_size'], r['cin'], r['cout'], r['n_inp'], r['n_out'], r['pairs'])
