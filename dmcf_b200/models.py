@@ -281,19 +281,28 @@ class PBFNet(BaseModel):
         if len(data) != 6:
             raise ValueError("data must be [pos, vel, acc, feats, box, box_normals]")
         perm = None
+        n_dev = ops.count_of(data[0]) if self.fused else None  # capacity-sized particle set (sync-free slab rollouts)
         if self.fused and data[0].shape[0] > 0:
             # cell order for locality; undone on the outputs.  Not part of the reference semantics.
             cl = ops.CellList(data[0], self.particle_radii[0])
             perm = cl.sorted_index[: data[0].shape[0]].long()
+            if n_dev is not None:  # padding rows stay where they are (their sorted_index entries are not written)
+                ar = torch.arange(perm.shape[0], device=perm.device)
+                perm = torch.where(ar < n_dev, perm, ar)
             data[0], data[1] = data[0][perm], data[1][perm]
             if data[2] is not None:
                 data[2] = data[2][perm]
+            if n_dev is not None:
+                ops.with_count(data[0], n_dev)
             data[4], data[5] = self._sorted_box(data[4], data[5])
         pos, vel = super().call(data, training=training, **kwargs)
         if perm is not None:
             pos_o, vel_o = torch.empty_like(pos), torch.empty_like(vel)
             pos_o[perm], vel_o[perm] = pos, vel
             pos, vel = pos_o, vel_o
+        if n_dev is not None:
+            ops.with_count(pos, n_dev)
+            ops.with_count(vel, n_dev)
         return pos, vel
 
     def _sorted_box(self, box, bfeats):
@@ -318,13 +327,20 @@ class PBFNet(BaseModel):
     # -- preprocess: models/pbf_model.py:303-438 ----------------------------------------------------------------
     def preprocess(self, data, training=False, **kwargs):
         _pos, _vel, acc, feats, box, bfeats = data
+        n_fluid_dev = ops.count_of(_pos) if self.fused else None
         pos, vel = self.integrate_pos_vel(_pos, _vel, acc)
+        if n_fluid_dev is not None:
+            ops.with_count(pos, n_fluid_dev)
         filter_extent = [np.float32(r) * np.float32(2) for r in self.particle_radii]
         e_last = float(filter_extent[-1])
         slab = self.slab if (self.slab is not None and self.slab.world > 1) else None
         n_box_dev = None
         if pos.shape[0] > 0 or slab is not None:
-            if pos.shape[0] > 0:
+            if n_fluid_dev is not None:  # bounding box of the valid rows only
+                m = ops.valid_rows_mask(pos)[:, None]
+                inf = torch.full((), float("inf"), device=pos.device)
+                lo, hi = torch.where(m, pos, inf).amin(dim=0), torch.where(m, pos, -inf).amax(dim=0)
+            elif pos.shape[0] > 0:
                 lo, hi = pos.amin(dim=0), pos.amax(dim=0)
             else:
                 inf = torch.full((3,), float("inf"), device=pos.device)
@@ -338,7 +354,7 @@ class PBFNet(BaseModel):
                 e, slot = plan.next("rows")
                 cap = min(box.shape[0], int(e["n"] * ops.StepPlan.ROW_SLACK) + 256)
                 idx, n_box_dev = ops.compact_mask(fltr, cap, plan.hard(slot))
-                box, bfeats = box[idx], bfeats[idx]
+                box, bfeats = ops.with_count(box[idx], n_box_dev), bfeats[idx]
             else:
                 box, bfeats = box[fltr], bfeats[fltr]
                 if plan is not None:
@@ -358,9 +374,8 @@ class PBFNet(BaseModel):
         box_feats = [torch.ones_like(box[:, :1])]
         if self.use_box_feats:
             box_feats.append(bfeats)
-        all_pos = torch.cat([pos, box], dim=0)
-        if n_box_dev is not None:  # rows [n_f + n_box_dev, n_f + capacity) are padding
-            all_pos = ops.with_count(all_pos, (n_box_dev + n_f).to(torch.int32))
+        # [fluid | boundary]; with capacity-sized parts the valid rows of both form the valid prefix
+        all_pos = ops.concat_rows([pos, box]) if self.fused else torch.cat([pos, box], dim=0)
         self.all_pos = all_pos
         dens0 = None
         if self.dens_feats or self.dens_norm or self.pres_feats:  # models/pbf_model.py:351-367
@@ -398,17 +413,24 @@ class PBFNet(BaseModel):
         else:
             cf, cb = fluid_feats.shape[1], box_feats.shape[1]
             self._ensure_built_inputs(cf, cb, pos.device)
-            x = torch.zeros((n_f + n_b, cf + cb), dtype=torch.float32, device=pos.device)
-            x[:n_f, :cf] = fluid_feats
-            x[n_f:, cf:] = box_feats
+            if ops.count_of(all_pos) is None:
+                x = torch.zeros((n_f + n_b, cf + cb), dtype=torch.float32, device=pos.device)
+                x[:n_f, :cf] = fluid_feats
+                x[n_f:, cf:] = box_feats
+            else:  # capacity-sized parts: pad each block to the full width, then join their valid rows
+                xf = torch.cat([fluid_feats, torch.zeros((n_f, cb), dtype=torch.float32, device=pos.device)], dim=1)
+                xb = torch.cat([torch.zeros((n_b, cf), dtype=torch.float32, device=pos.device), box_feats], dim=1)
+                x = ops.concat_rows([ops.with_count(xf, n_fluid_dev) if n_fluid_dev is not None else xf,
+                                     ops.with_count(xb, n_box_dev) if n_box_dev is not None else xb])
             w, b = self._input_weights(cf, cb)
             all_in = all_pos
             self._halo = None
+            self._pos_own = [all_pos]
             if slab is not None:  # ghosts of the two neighbouring slabs: positions once per step, features per layer
                 # halo width = the largest radius any conv applies to these points (coarse scales read scale 0 with it)
                 self._halo = [slab.make_halo(all_pos, max(self.particle_radii))]
-                all_in = torch.cat([all_pos, self._halo[0].ghost_pos], dim=0)
-                x = self._halo[0].with_ghosts(x)
+                all_in = ops.concat_rows([all_pos, self._halo[0].ghost_pos])
+                x = self._with_ghosts(0, x)
             self._pos_in = [all_in]
             nns = self._step.search((0, 0), all_in, all_pos, 0.5 * ext0)
             win = self.fluid_convs.window_function
@@ -435,6 +457,13 @@ class PBFNet(BaseModel):
                 dens.append(torch.clamp(d, min=1e-2))
         return [dilated_pos, feats_out, idx, dens]
 
+    def _with_ghosts(self, scale, x):
+        """Layer input of one scale under slab decomposition: [owned rows | ghost rows refreshed from the neighbours]."""
+        cnt = ops.count_of(self._pos_own[scale])
+        if cnt is not None and ops.count_of(x) is None:
+            ops.with_count(x, cnt)  # feature rows follow the owned points of their scale
+        return self._halo[scale].with_ghosts(x)
+
     def _slab_dilated_pos(self, slab, all_own, all_in):
         """Multi-scale lattices under slab decomposition: every rank builds the lattice from its owned + ghost particles
         (all particles within one coarse voxel of the slab are among the ghosts), keeps the lattice points whose
@@ -448,19 +477,27 @@ class PBFNet(BaseModel):
                 out.append(all_own)
                 continue
             if self.centralize and center is None:  # global mean, float64 accumulate, rounded once (losses.point_mean)
-                acc = torch.cat([all_own.to(torch.float64).sum(dim=0),
-                                 torch.tensor([float(all_own.shape[0])], dtype=torch.float64, device=all_own.device)])
-                acc = slab.all_reduce_sum(acc)
+                m = ops.valid_rows_mask(all_own)
+                p64 = all_own.to(torch.float64)
+                if m is not None:
+                    p64 = torch.where(m[:, None], p64, torch.zeros((), dtype=torch.float64, device=all_own.device))
+                    n64 = ops.count_of(all_own).to(torch.float64)
+                else:
+                    n64 = torch.full((1,), float(all_own.shape[0]), dtype=torch.float64, device=all_own.device)
+                acc = slab.all_reduce_sum(torch.cat([p64.sum(dim=0), n64]))
                 center = (acc[:3] / acc[3]).to(torch.float32)
             vs = torch.as_tensor(self.voxel_size, dtype=torch.float32) * float(stride)
             lat = grid_pos(all_in, vs, self.centralize, self.sample_pad, self.sample_hyst, center)
-            own = lat[slab.owned_mask(lat)].contiguous()
+            (own,) = slab._select(slab.owned_mask(lat), lat)
+            own = own.contiguous() if ops.count_of(own) is None else own
             plan = slab.make_halo(own, max(self.particle_radii))
             while len(self._halo) <= si:
                 self._halo.append(None)
                 self._pos_in.append(None)
+                self._pos_own.append(None)
             self._halo[si] = plan
-            self._pos_in[si] = torch.cat([own, plan.ghost_pos], dim=0)
+            self._pos_in[si] = ops.concat_rows([own, plan.ghost_pos])
+            self._pos_own[si] = own
             out.append(own)
         return out
 
@@ -531,7 +568,7 @@ class PBFNet(BaseModel):
         w, b = self._block_weights(conv, dense)
         if self.slab is not None and self.slab.world > 1:
             # owned rows out, [owned | ghost] rows in: refresh the ghost rows of this layer's input from the neighbours
-            x = self._halo[inp_scale].with_ghosts(x)
+            x = self._with_ghosts(inp_scale, x)
             inp_pos = self._pos_in[inp_scale]
         nns = self._step.search(key, inp_pos, out_pos, 0.5 * float(extent))
         win = conv.window_function

@@ -181,6 +181,83 @@ def _pos(t, name):
     return t.contiguous()
 
 
+def select_rows(mask, *tensors, bounded=True):
+    """Rows of every tensor where ``mask`` is True (the mask must already exclude padding rows).  Eager: boolean indexing (a
+    host sync).  Under a StepPlan the measured count is recorded and a replay returns capacity-sized tensors (measured count
+    plus slack) with the device-side count attached.  ``bounded=False``: do not cap the capacity at the number of mask rows
+    (message buffers whose size two ranks must derive from the same measured count)."""
+    if PLAN is not None and PLAN.mode == "replay":
+        e, slot = PLAN.next("rows")
+        cap = int(e["n"] * StepPlan.ROW_SLACK) + 256
+        if bounded:
+            cap = min(cap, max(int(mask.shape[0]), 1))
+        idx, cnt = compact_mask(mask, cap, PLAN.hard(slot))
+        return [with_count(t[idx], cnt) for t in tensors]
+    out = [t[mask] for t in tensors]
+    if PLAN is not None and PLAN.mode == "measure":
+        PLAN.record("rows", n=int(out[0].shape[0]))
+    return out
+
+
+def planned_rows(n_measured=None):
+    """Capacity of a buffer whose row count another rank decides (halo / migration arrivals): measure mode records the exact
+    count and returns it; replay returns (capacity, hard-overflow flag) derived from the recorded count."""
+    if PLAN is not None and PLAN.mode == "replay":
+        e, slot = PLAN.next("rows")
+        return int(e["n"] * StepPlan.ROW_SLACK) + 256, PLAN.hard(slot)
+    if PLAN is not None and PLAN.mode == "measure":
+        PLAN.record("rows", n=int(n_measured))
+    return int(n_measured), None
+
+
+def concat_rows(parts, extra_rows=0):
+    """Row-wise concatenation of point sets / feature blocks that may be capacity-sized: the valid rows of every part, in
+    order, form the valid prefix of the result (capacity = sum of the capacities, count = sum of the counts, on the device).
+    All parts exact -> plain torch.cat."""
+    if all(count_of(t) is None for t in parts):
+        return torch.cat(parts, dim=0)
+    dev = parts[0].device
+    cap = sum(int(t.shape[0]) for t in parts) + int(extra_rows)
+    out = torch.zeros((cap + 1, *parts[0].shape[1:]), dtype=parts[0].dtype, device=dev)  # last row: dump for padding rows
+    base = torch.zeros(1, dtype=torch.int32, device=dev)
+    for t in parts:
+        n = int(t.shape[0])
+        if n == 0:
+            continue
+        cnt = count_of(t)
+        ar = torch.arange(n, device=dev, dtype=torch.int32)
+        if cnt is None:
+            dst = (base + ar).to(torch.int64)
+            base = base + n
+        else:
+            dst = torch.where(ar < cnt, base + ar, torch.full((), cap, dtype=torch.int32, device=dev)).to(torch.int64)
+            base = base + cnt
+        out.index_copy_(0, dst, t)
+    return with_count(out[:cap], base)
+
+
+def pad_rows(t, capacity, count=None):
+    """``t`` (exact rows, or capacity-sized with a count) in a buffer of ``capacity`` rows with the count on the device."""
+    n = int(t.shape[0])
+    cnt = count_of(t) if count is None else count
+    if cnt is None:
+        cnt = torch.full((1,), n, dtype=torch.int32, device=t.device)
+    if n == capacity:
+        return with_count(t, cnt)
+    out = torch.zeros((capacity, *t.shape[1:]), dtype=t.dtype, device=t.device)
+    m = min(n, capacity)
+    out[:m] = t[:m]
+    return with_count(out, torch.clamp(cnt, max=capacity))
+
+
+def trim(t):
+    """Exact-sized copy of a capacity-sized tensor (ONE host sync: reads the count)."""
+    cnt = count_of(t)
+    if cnt is None:
+        return t
+    return t[: int(cnt.item())]
+
+
 class CellList:
     """Uniform cell list over a point set (the reference's ``build_spatial_hash_table`` result)."""
 

@@ -73,10 +73,10 @@ class Simulator:
     def _plannable(self, inputs):
         m = self.model
         slab = getattr(m, "slab", None)
-        if self.step_mode == "eager" or not getattr(m, "fused", False) or (slab is not None and slab.world > 1):
+        if self.step_mode == "eager" or not getattr(m, "fused", False):
             return False
-        if inputs[0].shape[0] == 0 or inputs[4].shape[0] == 0:
-            return False
+        if (slab is None or slab.world == 1) and inputs[0].shape[0] == 0:
+            return False  # (under slab decomposition every rank must take the same path: empty slabs are planned as well)
         # the planned step is inference only (no autograd through capacity-sized buffers)
         return not any(p.requires_grad for p in m.parameters()) and not any(
             t is not None and t.requires_grad for t in inputs[:3])
@@ -86,8 +86,8 @@ class Simulator:
         (the body of run_inference, pipelines/simulator.py:68-70)."""
         if self._plannable(inputs):
             with torch.no_grad():
-                pos, vel = self._step_planned(inputs)
-            return [pos, vel] + list(inputs[2:])
+                out = self._step_planned(inputs)
+            return list(out) + list(inputs[len(out):])
         pos, vel = self.model(inputs, training=False)
         slab = getattr(self.model, "slab", None)
         if slab is not None and slab.world > 1:
@@ -98,19 +98,34 @@ class Simulator:
             pos, vel = slab.migrate(pos, vel)
         return [pos, vel] + list(inputs[2:])
 
+    def _slab(self):
+        slab = getattr(self.model, "slab", None)
+        return slab if (slab is not None and slab.world > 1) else None
+
     def _run_model(self, inputs, plan, mode):
+        """The model step (plus, under slab decomposition, the migration of particles that crossed a face) under ``plan``.
+        Returns (pos, vel) or (pos, vel, acc)."""
         from . import ops
         plan.begin(mode)
         ops.PLAN = plan
         try:
-            return self.model(inputs, training=False)
+            pos, vel = self.model(inputs, training=False)
+            slab = self._slab()
+            if slab is None:
+                return pos, vel
+            if inputs[2] is not None:
+                return slab.migrate(pos, vel, inputs[2])
+            return slab.migrate(pos, vel)
         finally:
             ops.PLAN = None
 
     def _step_planned(self, inputs):
         from . import ops
         pos, vel, acc, feats, box, bn = inputs
-        sig = (pos.shape[0], acc is None, box.data_ptr(), box.shape[0], box._version, bn.data_ptr(), bn._version)
+        slab = self._slab()
+        # a slab's particle count changes with every migration: its plan is bounded by capacities, not by the input shape
+        sig = (pos.shape[0] if slab is None else -1, acc is None, box.data_ptr(), box.shape[0], box._version, bn.data_ptr(),
+               bn._version)
         st = self._planned
         if st is None or st.sig != sig:
             st = self._planned = _PlannedStep(sig)  # new scene / particle count (inflow): plan again
@@ -123,7 +138,7 @@ class Simulator:
             return out
         if st.event is None:
             st.event = torch.cuda.Event()
-        if self.step_mode == "graph" and st.graph is None and not st.graph_failed and st.replays >= 1:
+        if self.step_mode == "graph" and slab is None and st.graph is None and not st.graph_failed and st.replays >= 1:
             self._capture(st, inputs)
         if st.graph is not None:
             st.static_in[0].copy_(pos)
@@ -138,6 +153,8 @@ class Simulator:
             out = self._run_model(inputs, st.plan, "replay")
             if st.flags_host is None or st.flags_host.shape != st.plan.flags.shape:
                 st.flags_host = torch.zeros(st.plan.flags.shape, dtype=torch.int32).pin_memory()
+            if slab is not None:  # every rank must reach the same verdict: message capacities are derived from the shared plan
+                slab.all_reduce_max(st.plan.flags)
             st.flags_host.copy_(st.plan.flags, non_blocking=True)
         st.replays += 1
         self.stats["replayed"] += 1

@@ -33,12 +33,13 @@ class DistTransport:
         return t
 
     def sendrecv(self, rank, sends, recvs):
-        """``sends`` / ``recvs``: {peer rank: tensor}; receives are filled in place.  One batched isend/irecv group."""
+        """``sends`` / ``recvs``: lists of (peer rank, tensor) in matching order on both sides; receives are filled in place.
+        One batched isend/irecv group; waiting on it orders the current stream behind the transfer (no host sync with NCCL)."""
         ops = []
-        for peer, t in sends.items():
+        for peer, t in sends:
             if t.numel():
                 ops.append(dist.P2POp(dist.isend, t, peer, self.group))
-        for peer, t in recvs.items():
+        for peer, t in recvs:
             if t.numel():
                 ops.append(dist.P2POp(dist.irecv, t, peer, self.group))
         if ops:
@@ -68,13 +69,36 @@ class LocalTransport:
         return t
 
     def sendrecv(self, rank, sends, recvs):
-        for peer, t in sends.items():
+        for peer, t in sends:
             self._q[(rank, peer)].put(t.clone())
-        for peer, t in recvs.items():
+        for peer, t in recvs:
             src = self._q[(peer, rank)].get(timeout=120)
             if src.shape != t.shape:
                 raise RuntimeError(f"LocalTransport: rank {rank} expected {tuple(t.shape)} from {peer}, got {tuple(src.shape)}")
             t.copy_(src)
+
+
+def _ops():
+    from . import ops  # CUDA-only module: imported lazily so that the halo logic also runs on CPU tensors (tests/test_slab_cpu.py)
+    return ops
+
+
+def _plan():
+    import sys
+    mod = sys.modules.get("dmcf_b200.ops")
+    return getattr(mod, "PLAN", None) if mod is not None else None
+
+
+def _count_of(t):
+    return getattr(t, "_dmcf_n_dev", None)
+
+
+def _valid(t):
+    """Bool mask of the valid rows of a capacity-sized tensor, or None when every row is valid."""
+    cnt = _count_of(t)
+    if cnt is None:
+        return None
+    return torch.arange(t.shape[0], device=t.device, dtype=torch.int32) < cnt
 
 
 class SlabContext:
@@ -109,7 +133,9 @@ class SlabContext:
 
     def owned_mask(self, pos):
         x = pos[:, self.axis]
-        return (x >= self.lo) & (x < self.hi)
+        m = (x >= self.lo) & (x < self.hi)
+        v = _valid(pos)
+        return m if v is None else (m & v)
 
     # -- collectives -----------------------------------------------------------------------------------------
     def all_reduce_minmax(self, lo, hi):
@@ -125,33 +151,69 @@ class SlabContext:
             self.transport.all_reduce(self.rank, t, "sum")
         return t
 
-    def _exchange(self, to_left, to_right, n_from_left=None, n_from_right=None):
-        """Sends row blocks to the two neighbours, returns (from_left, from_right).  Row counts are exchanged first
-        unless the caller already knows them (feature halos reuse the counts of the position halo)."""
+    def all_reduce_max(self, t):
+        if self.world > 1:
+            self.transport.all_reduce(self.rank, t, "max")
+        return t
+
+    def _exchange(self, to_left, to_right, known=None):
+        """Sends row blocks to the two neighbours, returns (from_left, from_right, known).
+
+        Eager / measuring step: the row counts are exchanged first and read back (one host sync) unless ``known`` (the
+        counts of an earlier exchange of the same rows: feature halos reuse those of the position halo).  Replaying step
+        (dmcf_b200.ops.StepPlan): both sides derive the same message capacity from the count measured when the plan was made,
+        the true counts travel as device tensors next to the payload, nothing is read back."""
         dev, dt = to_left.device, to_left.dtype
         cols = to_left.shape[1:]
-        if n_from_left is None:
+        plan = _plan()
+        peers = [p for p in (self.left, self.right) if p is not None]
+        payload = {self.left: to_left.contiguous(), self.right: to_right.contiguous()}
+        if plan is not None and plan.mode == "replay":
+            ops = _ops()
+            if known is None:
+                caps = [ops.planned_rows() for _ in (0, 1)]  # (capacity, overflow flag) of the arrivals from left / right
+                cnt_in = {p: torch.zeros(1, dtype=torch.int32, device=dev) for p in peers}
+                cnt_out = {p: _count_of(payload[p]) for p in peers}
+                self.transport.sendrecv(self.rank, [(p, cnt_out[p]) for p in peers], [(p, cnt_in[p]) for p in peers])
+                known = dict(cap_left=caps[0][0], cap_right=caps[1][0], cnt_left=cnt_in.get(self.left), cnt_right=cnt_in.get(self.right))
+            from_left = torch.zeros((known["cap_left"] if self.left is not None else 0, *cols), dtype=dt, device=dev)
+            from_right = torch.zeros((known["cap_right"] if self.right is not None else 0, *cols), dtype=dt, device=dev)
+            recv = {self.left: from_left, self.right: from_right}
+            self.transport.sendrecv(self.rank, [(p, payload[p]) for p in peers], [(p, recv[p]) for p in peers])
+            zero = torch.zeros(1, dtype=torch.int32, device=dev)
+            from_left = ops.with_count(from_left, known["cnt_left"] if self.left is not None else zero)
+            from_right = ops.with_count(from_right, known["cnt_right"] if self.right is not None else zero)
+            self.bytes_exchanged += sum(payload[p].numel() for p in peers) * to_left.element_size()
+            return from_left, from_right, known
+        if known is None:
             cnt_out = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=dev)
             cnt_l = torch.zeros(1, dtype=torch.int64, device=dev)
             cnt_r = torch.zeros(1, dtype=torch.int64, device=dev)
-            sends, recvs = {}, {}
+            sends, recvs = [], []
             if self.left is not None:
-                sends[self.left], recvs[self.left] = cnt_out[0:1], cnt_l
+                sends.append((self.left, cnt_out[0:1]))
+                recvs.append((self.left, cnt_l))
             if self.right is not None:
-                sends[self.right], recvs[self.right] = cnt_out[1:2], cnt_r
+                sends.append((self.right, cnt_out[1:2]))
+                recvs.append((self.right, cnt_r))
             self.transport.sendrecv(self.rank, sends, recvs)
-            n_from_left, n_from_right = int(cnt_l.item()), int(cnt_r.item())
-        from_left = torch.empty((n_from_left, *cols), dtype=dt, device=dev)
-        from_right = torch.empty((n_from_right, *cols), dtype=dt, device=dev)
-        to_left, to_right = to_left.contiguous(), to_right.contiguous()
-        sends, recvs = {}, {}
-        if self.left is not None:
-            sends[self.left], recvs[self.left] = to_left, from_left
-        if self.right is not None:
-            sends[self.right], recvs[self.right] = to_right, from_right
-        self.transport.sendrecv(self.rank, sends, recvs)
-        self.bytes_exchanged += (to_left.numel() + to_right.numel()) * to_left.element_size()
-        return from_left, from_right, n_from_left, n_from_right
+            known = dict(n_left=int(cnt_l.item()), n_right=int(cnt_r.item()))
+            if plan is not None:  # measuring step: the arrivals' counts are sizes of the plan
+                ops = _ops()
+                ops.planned_rows(known["n_left"])
+                ops.planned_rows(known["n_right"])
+        from_left = torch.empty((known["n_left"], *cols), dtype=dt, device=dev)
+        from_right = torch.empty((known["n_right"], *cols), dtype=dt, device=dev)
+        recv = {self.left: from_left, self.right: from_right}
+        self.transport.sendrecv(self.rank, [(p, payload[p]) for p in peers], [(p, recv[p]) for p in peers])
+        self.bytes_exchanged += sum(payload[p].numel() for p in peers) * to_left.element_size()
+        return from_left, from_right, known
+
+    def _select(self, mask, *tensors, bounded=True):
+        """Rows where ``mask`` holds: boolean indexing, or (on CUDA under a StepPlan) the plan-aware capacity version."""
+        if _plan() is not None:
+            return _ops().select_rows(mask, *tensors, bounded=bounded)
+        return [t[mask] for t in tensors]
 
     # -- halos -----------------------------------------------------------------------------------------------
     def make_halo(self, pos, radius):
@@ -160,13 +222,34 @@ class SlabContext:
         ``radius`` (padded like the search) of a face is sent."""
         x = pos[:, self.axis]
         pad = float(radius) * 1.0001 + 1e-6 * max(abs(self.lo) if self.lo > -1e30 else 0.0, abs(self.hi) if self.hi < 1e30 else 0.0)
-        empty = torch.zeros(0, dtype=torch.int64, device=pos.device)
+        valid = _valid(pos)
+        none = torch.zeros(pos.shape[0], dtype=torch.bool, device=pos.device)
+        m_left = (x < self.lo + pad) if self.left is not None else none
+        m_right = (x >= self.hi - pad) if self.right is not None else none
+        if valid is not None:
+            m_left, m_right = m_left & valid, m_right & valid
+        rows = torch.arange(pos.shape[0], device=pos.device, dtype=torch.int64)
         plan = HaloPlan(self)
-        plan.send_left = torch.nonzero(x < self.lo + pad).flatten() if self.left is not None else empty
-        plan.send_right = torch.nonzero(x >= self.hi - pad).flatten() if self.right is not None else empty
-        gl, gr, plan.n_from_left, plan.n_from_right = self._exchange(pos[plan.send_left], pos[plan.send_right])
-        plan.ghost_pos = torch.cat([gl, gr], dim=0)
+        (plan.send_left,) = self._select(m_left, rows, bounded=False)
+        (plan.send_right,) = self._select(m_right, rows, bounded=False)
+        gl, gr, plan.known = self._exchange(self._gather(pos, plan.send_left), self._gather(pos, plan.send_right))
+        plan.ghost_left, plan.ghost_right = gl, gr
+        plan.ghost_pos = self._cat([gl, gr])
         return plan
+
+    @staticmethod
+    def _gather(t, idx):
+        out = t[idx]
+        cnt = _count_of(idx)
+        if cnt is not None:
+            out._dmcf_n_dev = cnt
+        return out
+
+    @staticmethod
+    def _cat(parts):
+        if all(_count_of(t) is None for t in parts):
+            return torch.cat(parts, dim=0)
+        return _ops().concat_rows(parts)
 
     # single-plan convenience API (one point set per step)
     def position_halo(self, pos, radius):
@@ -188,16 +271,31 @@ class SlabContext:
         if self.world == 1:
             return (pos, *others)
         x = pos[:, self.axis]
+        valid = _valid(pos)
         go_l = x < self.lo
         go_r = x >= self.hi
+        if self.left is None:
+            go_l = torch.zeros_like(go_l)
+        if self.right is None:
+            go_r = torch.zeros_like(go_r)
         stay = ~(go_l | go_r)
+        if valid is not None:
+            go_l, go_r, stay = go_l & valid, go_r & valid, stay & valid
         packed = torch.cat([pos] + [o.reshape(o.shape[0], -1) for o in others], dim=1)
-        fl, fr, _, _ = self._exchange(packed[go_l], packed[go_r])
-        new = torch.cat([packed[stay], fl, fr], dim=0)
+        (out_l,) = self._select(go_l, packed, bounded=False)
+        (out_r,) = self._select(go_r, packed, bounded=False)
+        fl, fr, _ = self._exchange(out_l, out_r)
+        (kept,) = self._select(stay, packed)
+        new = self._cat([kept, fl, fr])
+        cnt = _count_of(new)
         outs, c = [], 0
         for t in (pos, *others):
             w = t.reshape(t.shape[0], -1).shape[1]
-            outs.append(new[:, c:c + w].reshape(-1, *t.shape[1:]))
+            part = new[:, c:c + w].reshape(-1, *t.shape[1:])
+            if cnt is not None:
+                part = part.contiguous()
+                part._dmcf_n_dev = cnt
+            outs.append(part)
             c += w
         return tuple(outs)
 
@@ -208,15 +306,17 @@ class HaloPlan:
     def __init__(self, slab):
         self.slab = slab
         self.send_left = self.send_right = None
-        self.n_from_left = self.n_from_right = 0
+        self.known = None
+        self.ghost_left = self.ghost_right = None
         self.ghost_pos = None
 
     def feature_halo(self, feats):
         """Ghost rows of ``feats`` (same order as ``ghost_pos``)."""
-        gl, gr, _, _ = self.slab._exchange(feats[self.send_left], feats[self.send_right], self.n_from_left, self.n_from_right)
-        return torch.cat([gl, gr], dim=0)
+        gl, gr, _ = self.slab._exchange(SlabContext._gather(feats, self.send_left), SlabContext._gather(feats, self.send_right),
+                                        self.known)
+        return SlabContext._cat([gl, gr])
 
     def with_ghosts(self, feats):
         if self.slab.world == 1:
             return feats
-        return torch.cat([feats, self.feature_halo(feats)], dim=0)
+        return SlabContext._cat([feats, self.feature_halo(feats)])
