@@ -348,7 +348,7 @@ class PBFNet(BaseModel):
             if slab is not None:  # the cull uses the GLOBAL fluid bounding box (models/pbf_model.py:330-334)
                 lo, hi = slab.all_reduce_minmax(lo, hi)
             fltr = ((box >= lo - e_last) & (box <= hi + e_last)).all(dim=1)
-            plan = ops.PLAN if self.fused else None
+            plan = ops.get_plan() if self.fused else None
             if plan is not None and plan.mode == "replay":
                 # sync-free cull: stable compaction into a capacity-sized buffer, the count stays on the device
                 e, slot = plan.next("rows")

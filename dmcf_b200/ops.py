@@ -11,6 +11,7 @@ there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from collections import namedtuple
 
 import torch
@@ -38,7 +39,20 @@ PROFILE = None
 # memory (`with_count`), kernels are launched for the capacity and ignore rows beyond the count, and anything that outgrows
 # its capacity raises a flag in `StepPlan.flags` that the caller reads ONCE at the end of the step (dmcf_b200/simulator.py).
 # Such a step makes no host sync and can be captured in a CUDA graph.
-PLAN = None
+_TLS = threading.local()  # the active plan is per thread (slab ranks may run as threads of one process)
+
+
+def _PLAN():
+    return getattr(_TLS, "plan", None)
+
+
+def get_plan():
+    """The StepPlan the calling thread is measuring / replaying under, or None (eager)."""
+    return getattr(_TLS, "plan", None)
+
+
+def set_plan(plan):
+    _TLS.plan = plan
 
 
 class StepPlan:
@@ -89,12 +103,11 @@ class no_plan:
     """Context: run ops outside the plan (static, cached pieces such as the cell order of the boundary)."""
 
     def __enter__(self):
-        global PLAN
-        self.saved, PLAN = PLAN, None
+        self.saved = get_plan()
+        set_plan(None)
 
     def __exit__(self, *exc):
-        global PLAN
-        PLAN = self.saved
+        set_plan(self.saved)
 
 
 def with_count(t, n_dev):
@@ -186,27 +199,27 @@ def select_rows(mask, *tensors, bounded=True):
     host sync).  Under a StepPlan the measured count is recorded and a replay returns capacity-sized tensors (measured count
     plus slack) with the device-side count attached.  ``bounded=False``: do not cap the capacity at the number of mask rows
     (message buffers whose size two ranks must derive from the same measured count)."""
-    if PLAN is not None and PLAN.mode == "replay":
-        e, slot = PLAN.next("rows")
+    if _PLAN() is not None and _PLAN().mode == "replay":
+        e, slot = _PLAN().next("rows")
         cap = int(e["n"] * StepPlan.ROW_SLACK) + 256
         if bounded:
             cap = min(cap, max(int(mask.shape[0]), 1))
-        idx, cnt = compact_mask(mask, cap, PLAN.hard(slot))
+        idx, cnt = compact_mask(mask, cap, _PLAN().hard(slot))
         return [with_count(t[idx], cnt) for t in tensors]
     out = [t[mask] for t in tensors]
-    if PLAN is not None and PLAN.mode == "measure":
-        PLAN.record("rows", n=int(out[0].shape[0]))
+    if _PLAN() is not None and _PLAN().mode == "measure":
+        _PLAN().record("rows", n=int(out[0].shape[0]))
     return out
 
 
 def planned_rows(n_measured=None):
     """Capacity of a buffer whose row count another rank decides (halo / migration arrivals): measure mode records the exact
     count and returns it; replay returns (capacity, hard-overflow flag) derived from the recorded count."""
-    if PLAN is not None and PLAN.mode == "replay":
-        e, slot = PLAN.next("rows")
-        return int(e["n"] * StepPlan.ROW_SLACK) + 256, PLAN.hard(slot)
-    if PLAN is not None and PLAN.mode == "measure":
-        PLAN.record("rows", n=int(n_measured))
+    if _PLAN() is not None and _PLAN().mode == "replay":
+        e, slot = _PLAN().next("rows")
+        return int(e["n"] * StepPlan.ROW_SLACK) + 256, _PLAN().hard(slot)
+    if _PLAN() is not None and _PLAN().mode == "measure":
+        _PLAN().record("rows", n=int(n_measured))
     return int(n_measured), None
 
 
@@ -272,10 +285,10 @@ class CellList:
         cell_size = float(cell_size)
         if not cell_size > 0:
             raise ValueError("cell_size must be positive")
-        if (origin is None or dims is None) and PLAN is not None and PLAN.mode == "replay":
+        if (origin is None or dims is None) and _PLAN() is not None and _PLAN().mode == "replay":
             # planned grid: the measured bounding box padded by a few cells; points that leave it are clamped into the border
             # cells (always correct) and raise the SOFT flag so that the caller re-plans after this step
-            e, slot = PLAN.next("grid")
+            e, slot = _PLAN().next("grid")
             pad = [StepPlan.GRID_PAD_CELLS * cell_size + 0.05 * (e["hi"][a] - e["lo"][a]) for a in range(3)]
             origin = [e["lo"][a] - pad[a] for a in range(3)]
             while True:
@@ -292,7 +305,7 @@ class CellList:
                 out = (points < bounds[0]) | (points > bounds[1])
                 m = None if n_dev is None else (torch.arange(n, device=points.device, dtype=torch.int32) < n_dev)
                 out = out.any(dim=1) if m is None else (out.any(dim=1) & m)
-                soft = PLAN.soft(slot)
+                soft = _PLAN().soft(slot)
                 soft.copy_(torch.maximum(soft, out.any().to(torch.int32).reshape(1)))
         if origin is None or dims is None:
             if n > 0:
@@ -304,8 +317,8 @@ class CellList:
                 lo, hi = lohi[0].tolist(), lohi[1].tolist()
             else:
                 lo, hi = [0.0] * 3, [0.0] * 3
-            if PLAN is not None and PLAN.mode == "measure":
-                PLAN.record("grid", lo=lo, hi=hi)
+            if _PLAN() is not None and _PLAN().mode == "measure":
+                _PLAN().record("grid", lo=lo, hi=hi)
             while True:
                 dims = [int((hi[a] - lo[a]) / cell_size) + 1 for a in range(3)]
                 if dims[0] * dims[1] * dims[2] <= MAX_CELLS:
@@ -391,15 +404,15 @@ def fixed_radius_search(points, queries, radius, ignore_query_point=False, retur
     row_splits = exclusive_scan(counts, torch.int64)
     _prof_end(rec)
     nq = queries.shape[0]
-    if capacity is None and PLAN is not None and PLAN.mode == "replay":
-        e, slot = PLAN.next("pairs")
+    if capacity is None and _PLAN() is not None and _PLAN().mode == "replay":
+        e, slot = _PLAN().next("pairs")
         capacity = int(e["total"] * StepPlan.PAIR_SLACK) + 4096
-        overflow = PLAN.hard(slot)
+        overflow = _PLAN().hard(slot)
         true_pairs = e["total"]  # for the profiling records only (the measured count of the planning step)
     if capacity is None:
         total = int(row_splits[-1].item())  # data-dependent output size: the one host sync of the op
-        if PLAN is not None and PLAN.mode == "measure":
-            PLAN.record("pairs", total=total)
+        if _PLAN() is not None and _PLAN().mode == "measure":
+            _PLAN().record("pairs", total=total)
     else:
         total = int(capacity)
         if overflow is not None:  # flag here as well: the fill below only sees rows, the convs only see the clamped offsets
@@ -698,8 +711,8 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
     f32 = np.float32
     v = np.asarray(voxel, f32).reshape(3)
     cv = (C.c_float * 3)(*[float(x) for x in v])
-    if PLAN is not None and PLAN.mode == "replay":
-        e, slot = PLAN.next("lattice")
+    if _PLAN() is not None and _PLAN().mode == "replay":
+        e, slot = _PLAN().next("lattice")
         active = (v >= f32(1e-5)).astype(np.int64)
         lo = np.asarray(e["lo"], np.int64) - 2 * active
         dims = np.asarray(e["dims"], np.int64) + 4 * active
@@ -709,7 +722,7 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
         cd = (C.c_int32 * 3)(*[int(x) for x in dims])
         c_dev = None if center is None else _req(center, "center", dim=1).contiguous()
         flags = torch.zeros(n_cells, dtype=torch.int32, device=pos.device)
-        ovf = PLAN.hard(slot)
+        ovf = _PLAN().hard(slot)
         check(lib.dmcf_grid_pos_mark(_p(pos), n, _p(n_dev), cv, None, _p(c_dev), float(hyst), clo, cd, _p(flags), _p(ovf), _stream()))
         offsets = exclusive_scan(flags, torch.int32)
         out = torch.zeros((capacity, 3), dtype=torch.float32, device=pos.device)
@@ -718,7 +731,7 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
     if n_dev is not None:
         raise DmcfError("grid_pos of a capacity-sized point set needs a replaying StepPlan")
     if n == 0:
-        if PLAN is not None and PLAN.mode == "measure":
+        if _PLAN() is not None and _PLAN().mode == "measure":
             raise DmcfError("cannot plan a step on an empty particle set")
         return torch.empty((0, 3), dtype=torch.float32, device=pos.device)
     stats = [pos.amin(dim=0), pos.amax(dim=0)]
@@ -743,8 +756,8 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
     check(lib.dmcf_grid_pos_mark(_p(pos), n, None, cv, cc, None, float(hyst), clo, cd, _p(flags), None, _stream()))
     offsets = exclusive_scan(flags, torch.int32)
     count = int(offsets[-1].item())
-    if PLAN is not None and PLAN.mode == "measure":
-        PLAN.record("lattice", lo=[int(x) for x in lo], dims=[int(x) for x in dims], count=count)
+    if _PLAN() is not None and _PLAN().mode == "measure":
+        _PLAN().record("lattice", lo=[int(x) for x in lo], dims=[int(x) for x in dims], count=count)
     out = torch.empty((count, 3), dtype=torch.float32, device=pos.device)
     if count:
         check(lib.dmcf_grid_pos_emit(_p(flags), _p(offsets), cv, cc, None, clo, cd, _p(out), -1, None, _stream()))

@@ -107,7 +107,7 @@ class Simulator:
         Returns (pos, vel) or (pos, vel, acc)."""
         from . import ops
         plan.begin(mode)
-        ops.PLAN = plan
+        ops.set_plan(plan)
         try:
             pos, vel = self.model(inputs, training=False)
             slab = self._slab()
@@ -117,7 +117,7 @@ class Simulator:
                 return slab.migrate(pos, vel, inputs[2])
             return slab.migrate(pos, vel)
         finally:
-            ops.PLAN = None
+            ops.set_plan(None)
 
     def _step_planned(self, inputs):
         from . import ops

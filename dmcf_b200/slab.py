@@ -86,7 +86,7 @@ def _ops():
 def _plan():
     import sys
     mod = sys.modules.get("dmcf_b200.ops")
-    return getattr(mod, "PLAN", None) if mod is not None else None
+    return mod.get_plan() if mod is not None else None
 
 
 def _count_of(t):
