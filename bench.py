@@ -302,7 +302,7 @@ def main():
                          "owns an n_side^3 slab of an N-times longer box (extra key `weak`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--step-mode", default="graph", choices=["eager", "planned", "graph"],
-                    help="how Simulator.step drives the model (dmcf_b200/simulator.py); slab runs (N > 1) are eager")
+                    help="how Simulator.step drives the model (dmcf_b200/simulator.py); slab runs (N > 1) use 'planned' for 'graph'")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -352,7 +352,9 @@ def main():
         model.init_weights(seed=0, device=dev, scale=0.1)
         if world > 1:
             model.set_slab(SlabContext(faces, axis=0))
-        sim = Simulator(model, device=f"cuda:{local_rank}", step_mode=args.step_mode if world == 1 else "eager")
+        # slabs: the sync-free planned step (no CUDA graph around the NCCL exchanges yet)
+        mode = args.step_mode if world == 1 else ("planned" if args.step_mode == "graph" else args.step_mode)
+        sim = Simulator(model, device=f"cuda:{local_rank}", step_mode=mode)
         sample = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
         return sim, sample
 
@@ -472,7 +474,7 @@ def main():
                        "l2": ("per-step working set (features 136 MB/layer + 140 MB neighbour list per 1 M particles) exceeds the 126 MB L2 "
                               "down to 8 slabs (17 MB/layer + 18 MB list each, but five layers + records > L2); no explicit flush"),
                        "state": "every step restarts from the same resident scene (fixed work per step)",
-                       "step_mode": (args.step_mode if world == 1 else "eager") + " (dmcf_b200/simulator.py)",
+                       "step_mode": sim.step_mode + " (dmcf_b200/simulator.py)",
                        "step_stats": dict(sim.stats)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": copy_bytes_total, "d2h_bytes_per_step": copy_bytes_total,
                     "steps": e2e_steps, "api": "Simulator.step on pinned host pos/vel, results copied back to pinned host"},
