@@ -352,8 +352,7 @@ def main():
         model.init_weights(seed=0, device=dev, scale=0.1)
         if world > 1:
             model.set_slab(SlabContext(faces, axis=0))
-        # slabs: the sync-free planned step (no CUDA graph around the NCCL exchanges yet)
-        mode = args.step_mode if world == 1 else ("planned" if args.step_mode == "graph" else args.step_mode)
+        mode = args.step_mode
         sim = Simulator(model, device=f"cuda:{local_rank}", step_mode=mode)
         sample = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
         return sim, sample
@@ -368,6 +367,7 @@ def main():
         scene, faces = full_scene, None
     del full_scene
     main_scaling = "weak" if (world > 1 and args.scaling == "weak") else "strong"
+    p_steps = 0
     weak = None
     if world > 1 and args.scaling in ("weak", "both"):
         w_scene, w_faces = scenes.slab_scene(args.n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0)
@@ -394,7 +394,7 @@ def main():
     else:
         sim, sample = make_sim(scene, faces)
         steps = args.steps
-        replayed = world == 1 and args.step_mode != "eager"
+        replayed = args.step_mode != "eager"
         ms, prof, launches, clocks, out = timed_steps(sim, sample, steps, warmup, barrier, local_rank, profile=not replayed)
         ms_max = all_max(ms)
         if replayed:
@@ -435,7 +435,7 @@ def main():
                     "peak_source": peak_src, "avg_launch_ms": top["avg_ms"], "share_of_step": top["share_of_step"],
                     "fp32_tflops": top["fp32_TFLOPs"], "fp32_simt_peak_tflops": 74.0,
                     "timed_in": ("per-launch CUDA events over %d steps launched kernel by kernel (step_mode planned: same plan, buffers and "
-                                 "kernels as the graph) right after the headline region" % p_steps) if (world == 1 and args.step_mode != "eager")
+                                 "kernels as the graph) right after the headline region" % p_steps) if p_steps
                     else "per-launch CUDA events inside the headline timed region",
                     "note": "wide CConv layers are fp32-FLOP bound (SURVEY 8d): HBM fraction reported as BASELINE asks, "
                             "fp32 TFLOP/s beside it" + ("; rank 0's launches (its slab)" if world > 1 else "")}

@@ -171,20 +171,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     const int it_last = (kq_total - 1) / NW;
     const int last_fix = ((kq_total - 1) % NW == warp && (kq_total - 1) * 4 + cp_row > p.kc - 1)
                              ? ((kq_total - 1) * 4 + cp_row - (p.kc - 1)) * cout : 0;
-    // Filter k-quads whose 4 rows all exist (kc % 4 == 0: every shipped net) travel as ONE TMA bulk copy per k-quad and warp
-    // (cp.async.bulk -> UBLKCP, issued by lane 0, completing on a per-slot mbarrier); otherwise 32 lanes x 16-byte cp.async.
-    const bool bulk = (p.kc & 3) == 0 && (p.debug_wrap_w & 4) == 0;
-    const uint32_t slot_bytes = (uint32_t)(16 * cout);
-    // the three mbarriers of this warp live behind its two filter slots in its own record block (free in phase 2)
-    const uint32_t bar0 = lean::smem_u32(wrec + 256), bar1 = bar0 + 8, bar2 = bar0 + 16;
-    auto issue = [&](int it, float* slot, uint32_t bar) {  // fetch k-quad warp + it*NW into `slot`
-        if (bulk) {
-            if (lane == 0 && it < n_it) {
-                lean::mbar_expect_tx(bar, slot_bytes);
-                lean::bulk_g2s(lean::smem_u32(slot), p.filters + ((size_t)warp + (size_t)it * NW) * 4 * cout, slot_bytes, bar);
-            }
-            return;
-        }
+    // (A per-warp TMA bulk copy per k-quad -- cp.async.bulk completing on an mbarrier -- was built and measured here: 4.28 ms
+    // against 3.88 ms per 32->32 launch over 531 k points, profiles/README.md: with 512-byte slots and two k-quads of lookahead
+    // the higher latency of the bulk path is not covered, and there is no shared memory left for deeper / larger stages.)
+    auto issue = [&](int it, float* slot) {  // fetch k-quad warp + it*NW into `slot`
         const float* src = fsrc - (it == it_last ? last_fix : 0);
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + lane * 4);
         const int pred = (it < n_it) && cp_lane;
@@ -194,14 +184,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         fsrc += fstep;
     };
     __syncwarp();
-    if (bulk && !p.patch_out) {
-        if (lane == 0) {
-            lean::mbar_init(bar0, 1); lean::mbar_init(bar1, 1); lean::mbar_init(bar2, 1);
-            lean::mbar_fence_init();
-        }
-        __syncwarp();
-    }
-    if (!p.patch_out) { issue(0, slot0, bar0); issue(1, slot1, bar1); }
+    if (!p.patch_out) { issue(0, slot0); issue(1, slot1); }
     __syncthreads();  // patch tile complete
     if (p.patch_out) {
         // dmcf_cconv_patches: the patch tile goes to global memory (row o = [kc_conv] floats), consecutive threads take
@@ -247,15 +230,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         for (int h = 0; h < 8; ++h) acc2[i][h] = make_float2(0.0f, 0.0f);
     const float* pw = patch + ((size_t)warp * MTP + pr * 6) * 4 + q;  // word q of point 6*pr of k-quad `warp`
     // one k-quad: operands of slot FR, refill of the slot consumed in the previous step (WS) with k-quad it+2
-#define DMCF_LEAN_STEP(FR, WS, BFR, BWS, PH)                                                                     \
+#define DMCF_LEAN_STEP(FR, WS)                                                                                   \
     {                                                                                                            \
-        if (bulk) { lean::mbar_wait(BFR, PH); PH ^= 1u; } else lean::cp_wait<1>();                               \
+        lean::cp_wait<1>();                                                                                      \
         __syncwarp(); /* every lane's part of this slot landed; every lane is done with the previous slot */    \
         float4 w[4];                                                                                             \
         _Pragma("unroll") for (int h = 0; h < 4; ++h) w[h] = *FR[h];                                              \
         float pv[6];                                                                                             \
         _Pragma("unroll") for (int i = 0; i < 6; ++i) pv[i] = pw[i * 4];                                          \
-        issue(it + 2, WS, BWS);                                                                                  \
+        issue(it + 2, WS);                                                                                       \
         pw += (size_t)NW * MTP * 4;                                                                              \
         _Pragma("unroll") for (int i = 0; i < 6; ++i) {                                                          \
             const float2 pp = make_float2(pv[i], pv[i]);                                                         \
@@ -268,15 +251,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     }
     {
         int it = 0;
-        uint32_t ph0 = 0, ph1 = 0, ph2 = 0;  // phase parity of the slots' mbarriers
 #pragma unroll 1
         while (it + 3 <= n_it) {
-            DMCF_LEAN_STEP(fw0, slot2, bar0, bar2, ph0)
-            DMCF_LEAN_STEP(fw1, slot0, bar1, bar0, ph1)
-            DMCF_LEAN_STEP(fw2, slot1, bar2, bar1, ph2)
+            DMCF_LEAN_STEP(fw0, slot2)
+            DMCF_LEAN_STEP(fw1, slot0)
+            DMCF_LEAN_STEP(fw2, slot1)
         }
-        if (it < n_it) DMCF_LEAN_STEP(fw0, slot2, bar0, bar2, ph0)
-        if (it < n_it) DMCF_LEAN_STEP(fw1, slot0, bar1, bar0, ph1)
+        if (it < n_it) DMCF_LEAN_STEP(fw0, slot2)
+        if (it < n_it) DMCF_LEAN_STEP(fw1, slot0)
     }
 #undef DMCF_LEAN_STEP
     lean::cp_wait<0>();

@@ -35,6 +35,7 @@ class _PlannedStep:
         self.static_in = None
         self.static_out = None
         self.graph_launches = 0  # kernels of libdmcf_b200 inside one replay of the graph
+        self.graph_shape = None
         self.flags_host = None
         self.event = None
 
@@ -138,15 +139,22 @@ class Simulator:
             return out
         if st.event is None:
             st.event = torch.cuda.Event()
-        if self.step_mode == "graph" and slab is None and st.graph is None and not st.graph_failed and st.replays >= 1:
+        from . import ops as _o
+        shape_key = (tuple(pos.shape), _o.count_of(pos) is not None)
+        if st.graph is not None and st.graph_shape != shape_key:
+            st.graph = None  # a slab's row capacity settles over the first steps of a rollout: capture again for the new shape
+        graphable = slab is None or getattr(slab.transport, "graph_capturable", False)
+        if self.step_mode == "graph" and graphable and st.graph is None and not st.graph_failed and st.replays >= 1:
             self._capture(st, inputs)
+            st.graph_shape = shape_key
         if st.graph is not None:
-            st.static_in[0].copy_(pos)
-            st.static_in[1].copy_(vel)
-            if acc is not None:
-                st.static_in[2].copy_(acc)
+            for dst, src in zip(st.static_in, (pos, vel, acc)):
+                if dst is not None:
+                    dst.copy_(src)
+                    if _o.count_of(dst) is not None:
+                        _o.count_of(dst).copy_(_o.count_of(src))
             st.graph.replay()
-            out = (st.static_out[0].clone(), st.static_out[1].clone())
+            out = tuple(self._clone_with_count(t) for t in st.static_out)
             self.stats["graph_replays"] += 1
             self.stats["graph_kernel_launches"] = self.stats.get("graph_kernel_launches", 0) + st.graph_launches
         else:
@@ -173,6 +181,14 @@ class Simulator:
             self.stats["replans"] += 1
         return out
 
+    @staticmethod
+    def _clone_with_count(t):
+        from . import ops
+        c = t.clone()
+        if ops.count_of(t) is not None:
+            ops.with_count(c, ops.count_of(t).clone())
+        return c
+
     def _capture(self, st, inputs):
         """Captures the replaying step on static input buffers.  Any failure (an op that cannot be captured) leaves the
         simulator in planned mode."""
@@ -181,16 +197,24 @@ class Simulator:
         saved_profile, ops.PROFILE = ops.PROFILE, None  # per-launch CUDA events cannot be recorded into a capture
         try:
             st.static_in = [torch.empty_like(pos), torch.empty_like(vel), None if acc is None else torch.empty_like(acc)]
+            cnt = ops.count_of(pos)
+            static_cnt = None if cnt is None else cnt.clone()
             for dst, src in zip(st.static_in, (pos, vel, acc)):
                 if dst is not None:
                     dst.copy_(src)
+                    if static_cnt is not None:
+                        ops.with_count(dst, static_cnt)
             if st.flags_host is None or st.flags_host.shape != st.plan.flags.shape:
                 st.flags_host = torch.zeros(st.plan.flags.shape, dtype=torch.int32).pin_memory()
             torch.cuda.synchronize(pos.device)
             g = torch.cuda.CUDAGraph()
             launches0 = ops.launch_count()
-            with torch.cuda.graph(g):
+            slab = self._slab()
+            # thread_local: other threads (NCCL's watchdog, the rank threads of an in-process transport) keep using CUDA freely
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 out = self._run_model([st.static_in[0], st.static_in[1], st.static_in[2], feats, box, bn], st.plan, "replay")
+                if slab is not None:
+                    slab.all_reduce_max(st.plan.flags)
                 st.flags_host.copy_(st.plan.flags, non_blocking=True)
             st.graph, st.static_out, st.graph_launches = g, out, ops.launch_count() - launches0
             self.stats["captures"] += 1

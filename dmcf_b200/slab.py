@@ -25,8 +25,12 @@ import torch.distributed as dist
 class DistTransport:
     """The production transport: torch.distributed point-to-point / all-reduce (NCCL on GPUs, gloo in the CPU tests)."""
 
+    graph_capturable = True  # NCCL send / recv / all-reduce can be captured in a CUDA graph (gloo cannot)
+
     def __init__(self, group=None):
         self.group = group
+        if dist.is_initialized() and dist.get_backend(group) != "nccl":
+            self.graph_capturable = False
 
     def all_reduce(self, rank, t, op):
         dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.group)
