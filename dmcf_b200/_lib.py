@@ -60,6 +60,7 @@ SIGNATURES = {
     "dmcf_grid_pos_emit": (c_i32, [c_vp, c_vp, C.POINTER(c_f32), C.POINTER(c_f32), c_vp, C.POINTER(c_i32), C.POINTER(c_i32),
                                    c_vp, c_i64, c_vp, c_vp]),
     "dmcf_correct": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, C.POINTER(c_f32), c_f32, c_i64, c_vp, c_vp, c_vp]),
+    "dmcf_rows_append": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "dmcf_farthest_point_sample": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     "dmcf_approx_match_workspace_bytes": (c_sz, [c_i32, c_i32]),
     "dmcf_approx_match": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),

@@ -436,12 +436,13 @@ class PBFNet(BaseModel):
             win = self.fluid_convs.window_function
             recs = self._step.records((0, 0), nns, self.kernel_size, all_in, all_pos, ext0, self.coordinate_mapping,
                                       self.interpolation, win, self.ignore_query_points)
-            feats_out = ops.continuous_conv(
+            feats_out, own_rows = self._feature_buffer(0, all_pos.shape[0], w.shape[1], pos.device)
+            ops.continuous_conv(
                 w, all_pos, ext0, None, all_in, x, None, nns.neighbors_index, None, nns.neighbors_row_splits,
                 align_corners=True, coordinate_mapping=self.coordinate_mapping, normalize=False,
                 interpolation=self.interpolation, window=win.typ if win else None, window_fac=win.fac if win else 1.0,
                 feat_scale=self.part_scale, skip_self=self.ignore_query_points, bias=b, dense_inp=x,
-                dense_cin=cf + cb, kernel_size=self.kernel_size, pair_records=recs)
+                dense_cin=cf + cb, kernel_size=self.kernel_size, pair_records=recs, out=own_rows)
         src = all_pos if self.use_bnds else pos
         if slab is not None and self.fused:
             dilated_pos, idx = self._slab_dilated_pos(slab, all_pos, all_in), [None] * len(self.strides)
@@ -458,11 +459,26 @@ class PBFNet(BaseModel):
         return [dilated_pos, feats_out, idx, dens]
 
     def _with_ghosts(self, scale, x):
-        """Layer input of one scale under slab decomposition: [owned rows | ghost rows refreshed from the neighbours]."""
-        cnt = ops.count_of(self._pos_own[scale])
+        """Layer input of one scale under slab decomposition: [owned rows | ghost rows refreshed from the neighbours].  A
+        buffer allocated by ``_feature_buffer`` has room for the ghost rows behind its owned rows and is filled in place;
+        anything else is copied into a new [owned | ghost] array."""
+        own = self._pos_own[scale]
+        cnt = ops.count_of(own)
+        if x.shape[0] == self._pos_in[scale].shape[0] and x.shape[0] > own.shape[0]:
+            return self._halo[scale].fill_ghosts(x, cnt if cnt is not None else int(own.shape[0]))
         if cnt is not None and ops.count_of(x) is None:
             ops.with_count(x, cnt)  # feature rows follow the owned points of their scale
         return self._halo[scale].with_ghosts(x)
+
+    def _feature_buffer(self, scale, n_rows, channels, device):
+        """Output buffer of a conv on the points of ``scale``: under slab decomposition with room for the ghost rows of the
+        next layer's input behind the ``n_rows`` owned rows (returns (whole buffer, view of the owned rows))."""
+        rows = n_rows
+        if self.slab is not None and self.slab.world > 1 and self._halo is not None and scale < len(self._pos_in) \
+                and self._pos_in[scale] is not None:
+            rows = max(n_rows, int(self._pos_in[scale].shape[0]))
+        buf = torch.empty((rows, channels), dtype=torch.float32, device=device)
+        return buf, buf[:n_rows]
 
     def _slab_dilated_pos(self, slab, all_own, all_in):
         """Multi-scale lattices under slab decomposition: every rank builds the lattice from its owned + ghost particles
@@ -833,14 +849,16 @@ class HRNet(PBFNet):
                 ext = filter_extent[scale]
                 if self.fused:
                     cw = self.convs[layer][scale][0][0].filters
-                    buf = torch.empty((pos[scale].shape[0], cw if self.add_merge else cw * n_inp),
-                                      dtype=torch.float32, device=feats.device)
+                    n_rows = pos[scale].shape[0]
+                    buf, own_rows = self._feature_buffer(scale, n_rows, cw if self.add_merge else cw * n_inp, feats.device)
                     for inp_scale in range(n_inp):
                         x = ans_convs[-1][inp_scale]
                         ext = filter_extent[max(inp_scale, scale)]
                         same = scale == inp_scale
                         res = ans_convs[-1][scale] if same and cw == ans_convs[-1][scale].shape[-1] else None
-                        o = buf if self.add_merge else buf[:, inp_scale * cw:(inp_scale + 1) * cw]
+                        if res is not None:
+                            res = res[:n_rows]
+                        o = own_rows if self.add_merge else own_rows[:, inp_scale * cw:(inp_scale + 1) * cw]
                         self.conv_block(self.convs[layer][scale][0][inp_scale],
                                         self.denses[layer][scale][0][inp_scale] if same else None, x, pos[inp_scale],
                                         pos[scale], ext, self._set_key(inp_scale, scale), relu=True, scale=importance,

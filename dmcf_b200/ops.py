@@ -223,30 +223,56 @@ def planned_rows(n_measured=None):
     return int(n_measured), None
 
 
+def append_rows(dst, base, src, index=None, overflow=None, want_count=True):
+    """dst[base + i] = src[index[i] if index is given else i] for the valid rows i of ``src`` (``index`` / ``src`` may be capacity
+    sized with a count); ``base`` is an int or an int32 device tensor [1].  One kernel (dmcf_rows_append), no host sync.
+    Returns the new count (int32 device tensor [1]) when ``want_count``."""
+    lib = _lib.load()
+    if dst.dtype != torch.float32 or src.dtype != torch.float32 or dst.dim() != 2 or src.dim() != 2:
+        raise TypeError("append_rows moves float32 [rows, width] blocks")
+    if dst.stride(1) != 1 or (src.shape[1] > 1 and src.stride(1) != 1):
+        raise ValueError("append_rows needs unit-stride rows")
+    width = int(src.shape[1])
+    if dst.shape[1] != width:
+        raise ValueError("append_rows: widths differ")
+    lead = index if index is not None else src
+    n_src = int(lead.shape[0])
+    cnt = count_of(lead)
+    if index is not None:
+        _req(index, "index", torch.int64, 1)
+        index = index.contiguous()
+    new_cnt = torch.empty(1, dtype=torch.int32, device=dst.device) if want_count else None
+    base_dev = base if isinstance(base, torch.Tensor) else None
+    check(lib.dmcf_rows_append(_p(dst), dst.stride(0) if dst.shape[0] > 1 else max(width, dst.stride(0)), dst.shape[0],
+                               0 if base_dev is not None else int(base), _p(base_dev), _p(src),
+                               src.stride(0) if src.shape[0] > 1 else max(width, src.stride(0)), n_src, _p(cnt), _p(index), width,
+                               _p(new_cnt), _p(overflow), _stream()))
+    return new_cnt
+
+
 def concat_rows(parts, extra_rows=0):
     """Row-wise concatenation of point sets / feature blocks that may be capacity-sized: the valid rows of every part, in
     order, form the valid prefix of the result (capacity = sum of the capacities, count = sum of the counts, on the device).
     All parts exact -> plain torch.cat."""
     if all(count_of(t) is None for t in parts):
         return torch.cat(parts, dim=0)
-    dev = parts[0].device
     cap = sum(int(t.shape[0]) for t in parts) + int(extra_rows)
-    out = torch.zeros((cap + 1, *parts[0].shape[1:]), dtype=parts[0].dtype, device=dev)  # last row: dump for padding rows
-    base = torch.zeros(1, dtype=torch.int32, device=dev)
+    first = parts[0]
+    if first.dim() != 2 or first.dtype != torch.float32:
+        raise TypeError("concat_rows of capacity-sized parts moves float32 [rows, width] blocks")
+    out = torch.zeros((cap, first.shape[1]), dtype=torch.float32, device=first.device)  # padding rows stay finite
+    base = 0
     for t in parts:
-        n = int(t.shape[0])
-        if n == 0:
+        if int(t.shape[0]) == 0:
             continue
-        cnt = count_of(t)
-        ar = torch.arange(n, device=dev, dtype=torch.int32)
-        if cnt is None:
-            dst = (base + ar).to(torch.int64)
-            base = base + n
+        if count_of(t) is None and not isinstance(base, torch.Tensor):
+            out[base:base + t.shape[0]] = t
+            base += int(t.shape[0])
         else:
-            dst = torch.where(ar < cnt, base + ar, torch.full((), cap, dtype=torch.int32, device=dev)).to(torch.int64)
-            base = base + cnt
-        out.index_copy_(0, dst, t)
-    return with_count(out[:cap], base)
+            base = append_rows(out, base, t if t.stride(-1) == 1 else t.contiguous())
+    if not isinstance(base, torch.Tensor):
+        base = torch.full((1,), base, dtype=torch.int32, device=first.device)
+    return with_count(out, base)
 
 
 def pad_rows(t, capacity, count=None):

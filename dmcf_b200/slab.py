@@ -324,3 +324,18 @@ class HaloPlan:
         if self.slab.world == 1:
             return feats
         return SlabContext._cat([feats, self.feature_halo(feats)])
+
+    def fill_ghosts(self, feats, n_own):
+        """In-place variant for a feature buffer that has room behind its owned rows (rows = owned capacity + ghost
+        capacities, like the [owned | ghost] position array of the same point set): the ghost rows of this layer's input go to
+        rows [n_own, n_own + ghosts).  ``n_own``: int (exact) or int32 device tensor [1]."""
+        gl, gr, _ = self.slab._exchange(SlabContext._gather(feats, self.send_left), SlabContext._gather(feats, self.send_right),
+                                        self.known)
+        if isinstance(n_own, torch.Tensor) or _count_of(gl) is not None or _count_of(gr) is not None:
+            ops = _ops()
+            base = ops.append_rows(feats, n_own, gl)
+            ops.append_rows(feats, base, gr, want_count=False)
+        else:
+            feats[n_own:n_own + gl.shape[0]] = gl
+            feats[n_own + gl.shape[0]:n_own + gl.shape[0] + gr.shape[0]] = gr
+        return feats

@@ -221,6 +221,18 @@ int dmcf_grid_pos_emit(const int32_t* flags, const int32_t* offsets, const float
                        int64_t capacity, int32_t* overflow_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Row mover for capacity-sized point sets (no reference counterpart: TensorFlow's dynamic shapes hide this; here it is the glue
+ * of the sync-free multi-GPU step -- halo packing, ghost rows appended behind the owned rows, migration):
+ *   dst[(base + i) * dst_stride + c] = src[row(i) * src_stride + c],   i < count, c < width
+ *   base = base_host + (base_dev ? *base_dev : 0);  count = src_count_dev ? min(*src_count_dev, n_src) : n_src;
+ *   row(i) = src_index ? src_index[i] : i  (gather and append in one pass);  *new_count_dev (optional) = base + count.
+ * Rows that would pass dst_capacity are dropped and set *overflow_flag.
+ * ------------------------------------------------------------------------------------------------- */
+int dmcf_rows_append(float* dst, int64_t dst_stride, int64_t dst_capacity, int64_t base_host, const int32_t* base_dev,
+                     const float* src, int64_t src_stride, int64_t n_src, const int32_t* src_count_dev,
+                     const int64_t* src_index, int32_t width, int32_t* new_count_dev, int32_t* overflow_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Point-set ops of the reference's in-repo CUDA extensions.
  *
  * dmcf_farthest_point_sample  replaces op FarthestPointSample (utils/tools/sampling.cpp:49-61,115-148, kernel
