@@ -167,6 +167,7 @@ class PBFNet(BaseModel):
         self.num_fluid_neighbors = None
         self._all_convs = []
         self._box_cache = None
+        self._halo = self._pos_in = self._pos_own = None
         self._wcache = {}
         self.fluid_convs = self.get_cconv(name="fluid_obs", filters=channels, window_func=self.window, circular=circular)
         self.fluid_dense = Dense(channels, name="fluid_dense")
@@ -430,6 +431,7 @@ class PBFNet(BaseModel):
                 # halo width = the largest radius any conv applies to these points (coarse scales read scale 0 with it)
                 self._halo = [slab.make_halo(all_pos, max(self.particle_radii))]
                 all_in = ops.concat_rows([all_pos, self._halo[0].ghost_pos])
+                self._pos_in = [all_in]
                 x = self._with_ghosts(0, x)
             self._pos_in = [all_in]
             nns = self._step.search((0, 0), all_in, all_pos, 0.5 * ext0)
