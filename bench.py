@@ -489,7 +489,12 @@ def main():
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL kernels are still alive: leave without tearing the communicator down under them
+        # (destroy_process_group was seen to hang in that state); every rank has finished its work at this barrier
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

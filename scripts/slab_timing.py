@@ -61,4 +61,4 @@ for mode in modes:
         if rank == 0:
             print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=25))
             print(prof.key_averages().table(sort_by='cpu_time_total', row_limit=25))
-dist.destroy_process_group()
+dist.barrier(); torch.cuda.synchronize(); sys.stdout.flush(); os._exit(0)
