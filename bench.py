@@ -289,6 +289,126 @@ def e2e_steps_timed(sim, scene, box_d, bn_d, steps, barrier, dev):
     return e0.elapsed_time(e1), int(h_pos.numel() * 4 + h_vel.numel() * 4)
 
 
+def run_c5(args):
+    """BASELINE config 5: synthetic 3-D open box of N x n_side^3 particles (4 M at N = 8, n_side = 80), the full multi-scale
+    Liquid3d net with the shipped checkpoint, slab partitioned, an EVOLVING rollout: every step advances the state of the one
+    before, particles migrate between slabs, neighbour counts / lattices / culled walls change, plans are re-made when a
+    capacity overflows.  K timed steps after W warm-up steps."""
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import torch.distributed as dist
+    from dmcf_b200 import config, ops, scenes
+    from dmcf_b200.simulator import Simulator
+    from dmcf_b200.slab import SlabContext
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_side = args.n_side if args.n_side != 100 else 80
+    scene, faces = scenes.slab_scene(n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.05, seed=2, open_top=True)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ckpt_Liquid3d.npz"))
+    weights = {k.replace("|", "/"): z[k] for k in z.files}
+    model = config.build_model(scenes.liquid3d_model_cfg())
+    assert model.load_weights(weights, device=dev) == []
+    if world > 1:
+        model.set_slab(SlabContext(faces, axis=0))
+    sim = Simulator(model, device=f"cuda:{local_rank}", step_mode=args.step_mode)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    state = [t(scene["pos"]), t(scene["vel"]), None, None, t(scene["box"]), t(scene["box_normals"])]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def all_red(x, op):
+        v = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(v, op=op)
+        return float(v.item())
+
+    warmup, steps = max(args.warmup, 3), args.steps
+    torch.cuda.reset_peak_memory_stats(dev)
+    with torch.no_grad():
+        for _ in range(warmup):
+            state = sim.step(state)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.25)
+        barrier()
+        stats0 = dict(sim.stats)
+        launches0 = ops.launch_count() + sim.stats.get("graph_kernel_launches", 0)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        ev0.record()
+        for _ in range(steps):
+            state = sim.step(state)
+        ev1.record()
+        barrier()
+        w1 = time.time()
+        clocks = sampler.stop(w0, w1)
+        ms = all_red(ev0.elapsed_time(ev1), dist.ReduceOp.MAX if world > 1 else None)
+        launches = ops.launch_count() + sim.stats.get("graph_kernel_launches", 0) - launches0
+        # end to end: the evolving state lives in pinned host memory between steps (capacity-sized rows, count read back)
+        e2e_steps = max(3, min(steps, 10))
+        pos_h = ops.trim(state[0]).cpu().pin_memory()
+        vel_h = ops.trim(state[1]).cpu().pin_memory()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        copied = 0
+        for _ in range(e2e_steps):
+            st_in = [pos_h.to(dev, non_blocking=True), vel_h.to(dev, non_blocking=True)] + state[2:]
+            out = sim.step(st_in)
+            p_out, v_out = ops.trim(out[0]), ops.trim(out[1])
+            pos_h = torch.empty(p_out.shape, dtype=torch.float32).pin_memory()
+            vel_h = torch.empty(v_out.shape, dtype=torch.float32).pin_memory()
+            pos_h.copy_(p_out, non_blocking=True)
+            vel_h.copy_(v_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            copied += 2 * pos_h.numel() * 4
+        e1.record()
+        barrier()
+        e_ms = all_red(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
+    n_now = int(all_red(float(ops.trim(state[0]).shape[0]), dist.ReduceOp.SUM if world > 1 else None))
+    n_total = int(all_red(float(scene["pos"].shape[0]), dist.ReduceOp.SUM if world > 1 else None))
+    finite = all_red(0.0 if bool(torch.isfinite(ops.trim(state[0])).all().item()) else 1.0, dist.ReduceOp.SUM if world > 1 else None) == 0.0
+    peak_gb = all_red(torch.cuda.max_memory_allocated(dev) / 2 ** 30, dist.ReduceOp.MAX if world > 1 else None)
+    copied_total = int(all_red(float(copied), dist.ReduceOp.SUM if world > 1 else None)) // e2e_steps
+    if rank == 0:
+        d = {k: sim.stats.get(k, 0) - stats0.get(k, 0) for k in sim.stats}
+        line = {"metric": METRIC, "value": n_total * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C5: synthetic 3-D open box, {world} x {n_side}^3 = {n_total} fluid particles, full multi-scale "
+                                       "Liquid3d net (3 scales, shipped checkpoint), EVOLVING rollout (state advances every step, "
+                                       "migration between slabs, re-planning on overflow)",
+                           "parallelism": f"{world} spatial slabs along x, halos per scale and layer over NCCL" if world > 1 else "single GPU",
+                           "step_mode": sim.step_mode, "step_stats_timed_region": d, "particles_after": n_now,
+                           "l2": "working set >> 126 MB L2", "peak_memory_GB_per_gpu": round(peak_gb, 2)},
+                "e2e": {"value": n_total * e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": copied_total // 2,
+                        "d2h_bytes_per_step": copied_total // 2, "steps": e2e_steps,
+                        "api": "Simulator.step; the evolving pos / vel travel host -> device and back through pinned memory every step"},
+                "gpu_launches": int(launches), "clocks": clocks, "finite": bool(finite), "roofline": None, "cpu_baseline": None}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+    if world > 1:
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -303,9 +423,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--step-mode", default="graph", choices=["eager", "planned", "graph"],
                     help="how Simulator.step drives the model (dmcf_b200/simulator.py); slab runs (N > 1) use 'planned' for 'graph'")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4 (default): the ~1 M-particle single-scale scene BASELINE's metric is quoted on; c5: N x 80^3 particles, full "
+                         "multi-scale Liquid3d net, evolving rollout (BASELINE config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        return run_c5(args)
     # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner at the first
     # communicator) are sent to stderr until the result line is written
     sys.stdout.flush()

@@ -65,7 +65,18 @@ def c4_model_cfg():
                 use_acc=False)
 
 
-def slab_scene(n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0):
+def liquid3d_model_cfg():
+    """BASELINE.json configs 3 and 5: the full multi-scale net of configs/Liquid3d.yml (three scales, voxel strides 1 / 2 / 4,
+    antisymmetric output layer); the shipped checkpoint tests/golden/ckpt_Liquid3d.npz fits it."""
+    return dict(name="SymNet", layer_channels=[[[8]], [[16], [8], [4]], [[32], [16], [8]], [[32]], [[3]]],
+                kernel_size=[4, 4, 4], sym_kernel_size=[6, 6, 6], coordinate_mapping="ball_to_cube_volume_preserving",
+                interpolation="linear", window="poly6", window_sym="peak", window_dens="poly6", strides=[1, 2, 4],
+                particle_radii=[0.1, 0.2, 0.4], timestep=0.02, grav=-9.81, out_scale=[0.0078125] * 3, centralize=True,
+                voxel_size=[0.025] * 3, sym_axis=1, rest_dens=8.0, circular=False, add_merge=True, use_pre_adv=False,
+                use_acc=False, dens_norm=False, dens_feats=False, pres_feats=False)
+
+
+def slab_scene(n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0, open_top=False):
     """Rank ``rank``'s share of a (world*n_side) x n_side x n_side box split into slabs along x (weak scaling: every
     rank owns n_side^3 fluid particles).  Walls exist on the outer faces only; wall particles are owned by
     coordinate.  Returns (scene dict, slab faces along x)."""
@@ -74,7 +85,7 @@ def slab_scene(n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0):
                        origin=(rank * length, 0.0, 0.0))
     lo = np.zeros(3)
     hi = np.array([world * length, length, length])
-    box, normals = _walls(lo, hi, dx, [0, 1, 2])
+    box, normals = _walls(lo, hi, dx, [0, 1, 2], open_top)
     inf = float("inf")
     faces = [-inf] + [k * length for k in range(1, world)] + [inf]
     own = (box[:, 0] >= faces[rank]) & (box[:, 0] < faces[rank + 1])

@@ -13,12 +13,8 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
 def liquid3d_cfg():
-    return dict(name="SymNet", layer_channels=[[[8]], [[16], [8], [4]], [[32], [16], [8]], [[32]], [[3]]],
-                kernel_size=[4, 4, 4], sym_kernel_size=[6, 6, 6], coordinate_mapping="ball_to_cube_volume_preserving",
-                interpolation="linear", window="poly6", window_sym="peak", window_dens="poly6", strides=[1, 2, 4],
-                particle_radii=[0.1, 0.2, 0.4], timestep=0.02, grav=-9.81, out_scale=[0.0078125] * 3, centralize=True,
-                voxel_size=[0.025] * 3, sym_axis=1, rest_dens=8.0, circular=False, add_merge=True, use_pre_adv=False,
-                use_acc=False, dens_norm=False, dens_feats=False, pres_feats=False)
+    from dmcf_b200 import scenes
+    return scenes.liquid3d_model_cfg()
 
 
 def wbc_cfg():
