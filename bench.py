@@ -393,6 +393,7 @@ def run_c5(args):
                                        "migration between slabs, re-planning on overflow)",
                            "parallelism": f"{world} spatial slabs along x, halos per scale and layer over NCCL" if world > 1 else "single GPU",
                            "step_mode": sim.step_mode, "step_stats_timed_region": d, "particles_after": n_now,
+                           "replan_reasons_first5": [list(r) for r in sim.replan_log[:5]],
                            "l2": "working set >> 126 MB L2", "peak_memory_GB_per_gpu": round(peak_gb, 2)},
                 "e2e": {"value": n_total * e2e_steps / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": copied_total // 2,
                         "d2h_bytes_per_step": copied_total // 2, "steps": e2e_steps,

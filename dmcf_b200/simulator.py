@@ -68,6 +68,7 @@ class Simulator:
         self.cfg = dict(kwargs, main_log_dir=main_log_dir, split=split)
         self.timing = []
         self._planned = None
+        self.replan_log = []  # (hard | soft, [(plan entry, kind), ...]) of every re-plan
         self.stats = {"measured": 0, "replayed": 0, "graph_replays": 0, "replans": 0, "captures": 0}
 
     # -- one step ---------------------------------------------------------------------------------------------------------
@@ -131,8 +132,10 @@ class Simulator:
         if st is None or st.sig != sig:
             st = self._planned = _PlannedStep(sig)  # new scene / particle count (inflow): plan again
         if st.plan is None:
-            # measuring step: the eager path (exact sizes, host syncs) with the sizes recorded
+            # measuring step: the eager path (exact sizes, host syncs) with the sizes recorded; capacity-sized inputs (the state
+            # a replayed slab step returned) are cut to their exact size first
             plan = ops.StepPlan(pos.device)
+            inputs = [ops.trim(t) if (i < 3 and t is not None) else t for i, t in enumerate(inputs)]
             out = self._run_model(inputs, plan, "measure")
             st.plan, st.replays, st.graph = plan, 0, None
             self.stats["measured"] += 1
@@ -171,10 +174,14 @@ class Simulator:
         st.event.synchronize()
         n = len(st.plan.entries)
         hard, soft = bool(st.flags_host[:n].any()), bool(st.flags_host[n:].any())
+        if hard or soft:
+            idx = torch.nonzero(st.flags_host).flatten().tolist()
+            self.replan_log.append(("hard" if hard else "soft", [(i % n, st.plan.entries[i % n]["kind"]) for i in idx]))
         if hard:  # something outgrew its capacity: the results are invalid -> exact step + new plan
-            log.info("step plan overflowed (entries %s): re-planning", torch.nonzero(st.flags_host[:n]).flatten().tolist())
+            log.info("step plan overflowed (%s): re-planning", self.replan_log[-1][1])
             st.plan, st.graph = None, None
             self.stats["replans"] += 1
+            self.stats["replans_hard"] = self.stats.get("replans_hard", 0) + 1
             return self._step_planned(inputs)
         if soft:  # particles left a planned cell grid (results are fine, the grid is just no longer tight): plan again next step
             st.plan, st.graph = None, None
