@@ -315,7 +315,10 @@ def run_c5(args):
     scene, faces = scenes.slab_scene(n_side, rank, world, dx=0.05, jitter=0.2, vel_sigma=0.05, seed=2, open_top=True)
     z = np.load(os.path.join(ROOT, "tests", "golden", "ckpt_Liquid3d.npz"))
     weights = {k.replace("|", "/"): z[k] for k in z.files}
-    model = config.build_model(scenes.liquid3d_model_cfg())
+    # gravity off: the shipped checkpoint does not hold a synthetic lattice block against a synthetic floor (particles leak through
+    # it and the scene explodes, scripts/dbg_stability.py); without gravity its corrections let the block relax and expand slowly
+    # (|v| ~ 0.3-0.7 m/s): a tame state that still changes every step -- neighbour counts, lattices, culled walls, slab ownership
+    model = config.build_model(dict(scenes.liquid3d_model_cfg(), grav=0.0))
     assert model.load_weights(weights, device=dev) == []
     if world > 1:
         model.set_slab(SlabContext(faces, axis=0))
@@ -389,7 +392,7 @@ def run_c5(args):
                 "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"C5: synthetic 3-D open box, {world} x {n_side}^3 = {n_total} fluid particles, full multi-scale "
-                                       "Liquid3d net (3 scales, shipped checkpoint), EVOLVING rollout (state advances every step, "
+                                       "Liquid3d net (3 scales, shipped checkpoint, gravity off), EVOLVING rollout (state advances every step, "
                                        "migration between slabs, re-planning on overflow)",
                            "parallelism": f"{world} spatial slabs along x, halos per scale and layer over NCCL" if world > 1 else "single GPU",
                            "step_mode": sim.step_mode, "step_stats_timed_region": d, "particles_after": n_now,

@@ -4,14 +4,15 @@ from __future__ import annotations
 import numpy as np
 
 
-def _walls(lo, hi, dx, dims, open_top=False):
-    """One layer of wall particles (pitch dx) half a pitch outside the axis-aligned block [lo,hi], inward normals.
-    Only the axes listed in ``dims`` get walls (2-D scenes live in the xy-plane, 1-D ones on y)."""
+def _walls(lo, hi, dx, dims, open_top=False, gap=None):
+    """One layer of wall particles (pitch dx) ``gap`` (default half a pitch) outside the axis-aligned block [lo,hi], inward
+    normals.  Only the axes listed in ``dims`` get walls (2-D scenes live in the xy-plane, 1-D ones on y)."""
     pts, nrm = [], []
     axes = list(dims)
-    rng_ax = {a: np.arange(lo[a] - dx / 2, hi[a] + dx, dx) for a in axes}
+    gap = dx / 2 if gap is None else gap
+    rng_ax = {a: np.arange(lo[a] - gap, hi[a] + gap + dx / 2, dx) for a in axes}
     for a in axes:
-        for side, coord in ((+1, lo[a] - dx / 2), (-1, hi[a] + dx / 2)):
+        for side, coord in ((+1, lo[a] - gap), (-1, hi[a] + gap)):
             if open_top and a == 1 and side == -1:
                 continue
             others = [b for b in axes if b != a]
@@ -28,7 +29,8 @@ def _walls(lo, hi, dx, dims, open_top=False):
     return np.concatenate(pts).astype(np.float32), np.concatenate(nrm).astype(np.float32)
 
 
-def lattice_scene(shape, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0, origin=(0.0, 0.0, 0.0), open_top=False):
+def lattice_scene(shape, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0, origin=(0.0, 0.0, 0.0), open_top=False, wall_dx=None,
+                  wall_gap=None, headroom=0):
     """Jittered fluid lattice of ``shape`` = (nx, ny, nz) particles (entries of 1 collapse that axis) inside a box of
     wall particles.  Returns dict(pos, vel, box, box_normals) float32."""
     rng = np.random.default_rng(seed)
@@ -40,7 +42,9 @@ def lattice_scene(shape, dx=0.05, jitter=0.2, vel_sigma=0.1, seed=0, origin=(0.0
     vel = rng.normal(0.0, vel_sigma, g.shape) * mask
     lo = np.asarray(origin, dtype=np.float64)
     hi = lo + np.array([shape[a] * dx if a in dims else 0.0 for a in range(3)])
-    box, normals = _walls(lo, hi, dx, dims, open_top)
+    if headroom:  # the box is taller than the fluid block by `headroom` lattice layers (free surface under an open top)
+        hi[1] += headroom * dx
+    box, normals = _walls(lo, hi, dx if wall_dx is None else wall_dx, dims, open_top, wall_gap)
     return dict(pos=pos.astype(np.float32), vel=vel.astype(np.float32), box=box, box_normals=normals)
 
 
