@@ -740,8 +740,9 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
     if _PLAN() is not None and _PLAN().mode == "replay":
         e, slot = _PLAN().next("lattice")
         active = (v >= f32(1e-5)).astype(np.int64)
-        lo = np.asarray(e["lo"], np.int64) - 2 * active
-        dims = np.asarray(e["dims"], np.int64) + 4 * active
+        pad = (4 + np.asarray(e["dims"], np.int64) // 10) * active  # voxels of slack on every side of the measured lattice
+        lo = np.asarray(e["lo"], np.int64) - pad
+        dims = np.asarray(e["dims"], np.int64) + 2 * pad
         capacity = int(e["count"] * StepPlan.ROW_SLACK) + 64
         n_cells = int(dims[0]) * int(dims[1]) * int(dims[2])
         clo = (C.c_int32 * 3)(*[int(x) for x in lo])

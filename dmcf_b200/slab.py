@@ -289,7 +289,9 @@ class SlabContext:
         (out_l,) = self._select(go_l, packed, bounded=False)
         (out_r,) = self._select(go_r, packed, bounded=False)
         fl, fr, _ = self._exchange(out_l, out_r)
-        (kept,) = self._select(stay, packed)
+        # (unbounded: the capacity of the kept rows -- and with it the shape of the returned state -- depends on the plan only,
+        # not on how many rows the input buffer happened to have: a graph captured for that shape keeps fitting)
+        (kept,) = self._select(stay, packed, bounded=False)
         new = self._cat([kept, fl, fr])
         cnt = _count_of(new)
         outs, c = [], 0
