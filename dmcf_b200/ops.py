@@ -59,7 +59,7 @@ class StepPlan:
     """Sequence of the data-dependent size decisions of one model step, in call order (the control flow of a step is fixed by
     the model, so the i-th decision of every step is the same one)."""
 
-    PAIR_SLACK, ROW_SLACK, GRID_PAD_CELLS = 1.25, 1.25, 2
+    PAIR_SLACK, ROW_SLACK, GRID_PAD_CELLS, GRID_PAD_FRAC = 1.25, 1.25, 3, 0.08
 
     def __init__(self, device):
         self.entries = []
@@ -315,7 +315,7 @@ class CellList:
             # planned grid: the measured bounding box padded by a few cells; points that leave it are clamped into the border
             # cells (always correct) and raise the SOFT flag so that the caller re-plans after this step
             e, slot = _PLAN().next("grid")
-            pad = [StepPlan.GRID_PAD_CELLS * cell_size + 0.05 * (e["hi"][a] - e["lo"][a]) for a in range(3)]
+            pad = [StepPlan.GRID_PAD_CELLS * cell_size + StepPlan.GRID_PAD_FRAC * (e["hi"][a] - e["lo"][a]) for a in range(3)]
             origin = [e["lo"][a] - pad[a] for a in range(3)]
             while True:
                 dims = [int((e["hi"][a] + pad[a] - origin[a]) / cell_size) + 1 for a in range(3)]
