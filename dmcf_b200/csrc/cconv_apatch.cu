@@ -37,9 +37,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_apatch(const ConvParams p)
     float* fd = fh + ((half_words + 3) & ~3);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < half_words; i += NW * 32) fh[i] = __ldg(p.filters + i);
+    __shared__ uint64_t filter_bar;
     for (int i = tid; i < p.dense_cin * COUT; i += NW * 32) fd[i] = __ldg(p.filters + (size_t)p.kc_conv * COUT + i);
-    __syncthreads();
+    tma::stage_block(fh, p.filters, half_words, &filter_bar, NW * 32);  // the resident (half) filter: TMA bulk copies
 
     const bool lane_ci = lane < p.cin;
     lean::WarpCtx cx;

@@ -47,6 +47,62 @@ struct ConvParams {
 
 static constexpr int kRecordFields = 9;
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -----------------------------------------------
+// Used to stage a kernel's RESIDENT filter (k_cconv_direct, k_cconv_apatch: up to ~100 KB that stay in shared memory for the
+// lifetime of a persistent CTA) with a few bulk copies issued by one thread instead of a grid-stride loop of LDG + STS through
+// the registers of every thread.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LAB_DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "LAB_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+
+// Whole-CTA helper: `n_words` floats global -> shared.  TMA path when the block is a multiple of 16 bytes and both ends are
+// 16-byte aligned (every shipped filter), else the plain loop.  Ends with the data visible to every thread of the CTA.
+__device__ __forceinline__ void stage_block(float* dst, const float* src, int n_words, uint64_t* bar, int n_threads) {
+    const bool bulk = n_words > 0 && (n_words & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0 && n_words < (1 << 18);
+    if (!bulk) {
+        for (int i = threadIdx.x; i < n_words; i += n_threads) dst[i] = __ldg(src + i);
+        __syncthreads();
+        return;
+    }
+    const uint32_t b = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        mbar_init(b, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)n_words * 4u;
+        mbar_expect_tx(b, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+            const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+            bulk_g2s(smem_u32(dst) + off, reinterpret_cast<const char*>(src) + off, n, b);
+        }
+    }
+    mbar_wait(b, 0);
+}
+}  // namespace tma
+
 // Number of out points this launch really has: the device-side count when the caller runs capacity-sized buffers.
 __device__ __forceinline__ int64_t conv_n_out(const ConvParams& p) {
     if (p.n_out_dev == nullptr) return p.n_out;

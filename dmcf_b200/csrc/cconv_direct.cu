@@ -21,8 +21,8 @@ __global__ void __launch_bounds__(kDirWarps * 32, 1) k_cconv_direct(const ConvPa
     float* filt = smem;                                               // [kc][COUT] (conv rows, then Dense rows)
     float* scratch = filt + ((n_filter_words + 3) & ~3);             // [kDirWarps][32][kDirRecWords]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < n_filter_words; i += kDirWarps * 32) filt[i] = __ldg(p.filters + i);
-    __syncthreads();
+    __shared__ uint64_t filter_bar;
+    tma::stage_block(filt, p.filters, n_filter_words, &filter_bar, kDirWarps * 32);  // the resident filter: TMA bulk copies
     float* rec = scratch + (size_t)warp * 32 * kDirRecWords;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int kx = p.gp.kx, kyx = p.gp.ky * p.gp.kx;

@@ -32,32 +32,6 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
     return v;
 }
-// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one elected lane moves a whole filter k-quad
-// (4 rows x cout floats, contiguous in global memory) global -> shared memory; the consumers wait on the barrier's phase.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra LAB_DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "LAB_DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar) : "memory");
-}
-
 // next 128-byte slot of a 512-byte aligned ring of kGatherSlots slots
 __device__ __forceinline__ uint32_t ring_next(uint32_t saddr) {
     return (saddr & ~(kGatherSlots * 128u - 1u)) | ((saddr + 128u) & (kGatherSlots * 128u - 1u));
