@@ -147,7 +147,7 @@ static int launch_direct(const ConvParams& p, cudaStream_t st) {
     const size_t smem = ((size_t)((n_words + 3) & ~3) + (size_t)kDirWarps * 32 * kDirRecWords) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_cconv_direct<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_cconv_direct<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_direct)");
         attr_set = true;
     }
