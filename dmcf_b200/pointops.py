@@ -168,6 +168,21 @@ def approx_vel(pos_0, pos_1, n=None, m=None):
     return torch.bmm(match.transpose(1, 2), pos_1) - pos_0 * match.sum(dim=1).unsqueeze(-1)
 
 
+def nearest_distance(queries, points):
+    """For every row of ``queries`` [n, 3] the squared distance to / index of its nearest row of ``points`` [m, 3] (one
+    direction of NnDistance; the chamfer metric of utils/evaluation_helper.py:25-28 on the device)."""
+    lib = _lib.load()
+    q, p = _points(queries.unsqueeze(0), "queries")[0], _points(points.unsqueeze(0), "points")[0]
+    n, m = q.shape[0], p.shape[0]
+    d = torch.empty(n, dtype=torch.float32, device=q.device)
+    i = torch.empty(n, dtype=torch.int32, device=q.device)
+    if n and not m:
+        raise ValueError("nearest_distance: the reference point set is empty")
+    if n:
+        check(lib.dmcf_nn_distance(_p(q), n, _p(p), m, _p(d), _p(i), _stream()))
+    return d, i
+
+
 def nn_distance(xyz1, xyz2):
     """utils/tools/nn_distance.py:41-52: (dist1 [b, n], idx1 [b, n], dist2 [b, m], idx2 [b, m]); squared distances."""
     lib = _lib.load()

@@ -252,3 +252,23 @@ def test_density_loss_and_rollout_metrics(cuda):
     clipped = np.clip(pred, box.min(0), box.max(0))  # run_valid clamps the prediction into the box (pipelines/simulator.py:218-219)
     want = pointset.emd_loss(gt, clipped)
     assert abs(m["emd"] - want) <= 5e-4 * want
+
+
+def test_device_metrics_match_the_host_definitions(cuda):
+    """utils/evaluation_helper.py:25-28, 43-72 on the device (chamfer through dmcf_nn_distance, histogram KL in torch ops) against
+    the NumPy / SciPy statements of the same file."""
+    from dmcf_b200 import metrics
+    rng = np.random.default_rng(8)
+    a = rng.standard_normal((4000, 3)).astype(np.float32)
+    b = (rng.standard_normal((3500, 3)) * 1.2 + 0.1).astype(np.float32)
+    t = lambda x: torch.from_numpy(x).to(cuda)
+    got = metrics.chamfer_distance(t(a), t(b))
+    assert isinstance(got, torch.Tensor) and got.is_cuda
+    want = metrics.chamfer_distance(a, b)
+    assert np.abs(got.cpu().numpy() - want).max() <= 2e-6 * max(want.max(), 1.0)
+    va, vb = a, (a * 1.1 + rng.normal(0, 0.05, a.shape)).astype(np.float32)
+    kl_gpu, kl_cpu = metrics.compare_dist(t(va), t(vb)), metrics.compare_dist(va.astype(np.float64), vb.astype(np.float64))
+    assert abs(kl_gpu - kl_cpu) <= 1e-9 + 1e-7 * abs(kl_cpu)
+    assert metrics.compare_dist(t(va), t(va)) < 1e-12
+    v2 = rng.standard_normal((3000, 2)).astype(np.float32)  # 2-D velocities (WBC-SPH)
+    assert abs(metrics.compare_dist(t(v2), t(v2 * 0.9)) - metrics.compare_dist(v2.astype(np.float64), (v2 * 0.9).astype(np.float64))) <= 1e-7
