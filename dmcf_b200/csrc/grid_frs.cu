@@ -137,6 +137,7 @@ struct GridView {
     float ox, oy, oz, inv_cell;
     int nx, ny, nz, n_points;
     const int32_t* n_points_dev;  // optional device-side count (n_points is then the capacity)
+    const float* points;          // the array the grid was built from (set by dmcf_grid_build)
     const int32_t* cell_start;
     const int32_t* sorted_index;
     const float4* sorted_pos;
@@ -349,6 +350,107 @@ __global__ void __launch_bounds__(256) k_frs(GridView g, const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// radius queries, cell-centric variant for the common case "the queries are a prefix of the point set the grid was built from"
+// (every same-set search of a DMCF step: [fluid | boundary] rows out, the same rows plus ghost rows in).
+// k_frs above is bound by L2 traffic: every query warp streams its own ~3.4 KB of candidates (9 cell rows) although the ~8
+// queries of a cell share them.  Here ONE WARP OWNS A CELL: its points ARE its queries (position and id come with the
+// cell-major float4 list, no gather), the candidate rows of the cell's neighbourhood are loaded once, 32 candidates per batch
+// (one per lane), and every batch is tested against all queries of the cell (query position broadcast by shuffles, hits
+// compacted by ballot): 8x less candidate traffic, same row order (cell rows ascending, ascending position in the row).
+// The neighbourhood is the union of the per-query cell ranges computed exactly like k_frs does; the extra candidates a query
+// sees that way are rejected by the same exact distance test.
+// ---------------------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_frs_cell(GridView g, int64_t n_queries_cap, const int32_t* __restrict__ n_queries_dev,
+                                                    float radius, float thr, int ignore_query_point,
+                                                    const int64_t* __restrict__ row_splits, int64_t capacity,
+                                                    int32_t* __restrict__ counts, int32_t* __restrict__ nbr_index,
+                                                    float* __restrict__ nbr_dist, int32_t* __restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int64_t n_queries = n_queries_cap;
+    if (n_queries_dev != nullptr) {
+        const int64_t nd = (int64_t)__ldg(n_queries_dev);
+        n_queries = nd < n_queries_cap ? (nd < 0 ? 0 : nd) : n_queries_cap;
+    }
+    // rows that are no query of any cell (beyond the device-side count, or beyond the points the grid holds) count zero
+    if (!FILL) {
+        const int n_pts = grid_n_points(g);
+        const int64_t first_empty = n_queries < n_pts ? n_queries : (int64_t)n_pts;
+        for (int64_t q = first_empty + warp0 * 32 + lane; q < n_queries_cap; q += n_warps * 32) counts[q] = 0;
+    }
+    const int64_t n_cells = (int64_t)g.nx * g.ny * g.nz;
+    const float rp = radius * 1.0001f;
+    for (int64_t cell = warp0; cell < n_cells; cell += n_warps) {
+        const int cs = __ldg(g.cell_start + cell), ce = __ldg(g.cell_start + cell + 1);
+        for (int qb = cs; qb < ce; qb += 32) {
+            // ---- this lane's query (a point of the cell) ----
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool is_q = false;
+            if (qb + lane < ce) {
+                q = __ldg(g.sorted_pos + qb + lane);
+                is_q = (int64_t)__float_as_int(q.w) < n_queries;
+            }
+            const unsigned qmask = __ballot_sync(0xffffffffu, is_q);
+            if (qmask == 0u) continue;
+            const int qid = __float_as_int(q.w);
+            int x0 = 0x7fffffff, x1 = -1, y0 = 0x7fffffff, y1 = -1, z0 = 0x7fffffff, z1 = -1;
+            if (is_q) {
+                const float px = rp + fabsf(q.x) * 1e-6f, py = rp + fabsf(q.y) * 1e-6f, pz = rp + fabsf(q.z) * 1e-6f;
+                x0 = cell_coord(q.x - px, g.ox, g.inv_cell, g.nx); x1 = cell_coord(q.x + px, g.ox, g.inv_cell, g.nx);
+                y0 = cell_coord(q.y - py, g.oy, g.inv_cell, g.ny); y1 = cell_coord(q.y + py, g.oy, g.inv_cell, g.ny);
+                z0 = cell_coord(q.z - pz, g.oz, g.inv_cell, g.nz); z1 = cell_coord(q.z + pz, g.oz, g.inv_cell, g.nz);
+            }
+            const int X0 = __reduce_min_sync(0xffffffffu, x0), X1 = __reduce_max_sync(0xffffffffu, x1);
+            const int Y0 = __reduce_min_sync(0xffffffffu, y0), Y1 = __reduce_max_sync(0xffffffffu, y1);
+            const int Z0 = __reduce_min_sync(0xffffffffu, z0), Z1 = __reduce_max_sync(0xffffffffu, z1);
+            int count = 0;
+            int64_t base = 0;
+            if (FILL && is_q) base = row_splits[qid];
+            for (int z = Z0; z <= Z1; ++z) {
+                for (int y = Y0; y <= Y1; ++y) {
+                    const int64_t crow = ((int64_t)z * g.ny + y) * g.nx;
+                    const int s = __ldg(g.cell_start + crow + X0), e = __ldg(g.cell_start + crow + X1 + 1);
+                    for (int i0 = s; i0 < e; i0 += 32) {
+                        const bool c_ok = i0 + lane < e;
+                        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c_ok) c = __ldg(g.sorted_pos + i0 + lane);
+                        unsigned todo = qmask;
+                        while (todo) {  // warp uniform
+                            const int j = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const float qx = __shfl_sync(0xffffffffu, q.x, j), qy = __shfl_sync(0xffffffffu, q.y, j);
+                            const float qz = __shfl_sync(0xffffffffu, q.z, j);
+                            const float d2 = dist2_exact(c.x - qx, c.y - qy, c.z - qz);
+                            bool hit = c_ok && d2 <= thr;
+                            if (ignore_query_point && c.x == qx && c.y == qy && c.z == qz) hit = false;
+                            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+                            if (ballot == 0u) continue;
+                            if (FILL) {
+                                const int64_t pos0 = __shfl_sync(0xffffffffu, base + count, j);
+                                if (hit) {
+                                    const int64_t pos = pos0 + __popc(ballot & lt_mask);
+                                    if (pos < capacity) {
+                                        nbr_index[pos] = __float_as_int(c.w);
+                                        if (nbr_dist) nbr_dist[pos] = d2;
+                                    } else if (overflow) {
+                                        *overflow = 1;
+                                    }
+                                }
+                            }
+                            if (lane == j) count += __popc(ballot);
+                        }
+                    }
+                }
+            }
+            if (!FILL && is_q) counts[qid] = count;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // grid_pos (utils/tools/losses.py:136-181)
 // ---------------------------------------------------------------------------------------------------------
 struct LatticeParams {
@@ -444,6 +546,7 @@ static int make_view(const dmcf_grid* grid, GridView* v) {
     v->nx = grid->dims[0]; v->ny = grid->dims[1]; v->nz = grid->dims[2];
     v->n_points = grid->n_points;
     v->n_points_dev = grid->n_points_dev;
+    v->points = grid->points;
     v->cell_start = grid->cell_start;
     v->sorted_index = grid->sorted_index;
     v->sorted_pos = (const float4*)grid->sorted_pos;
@@ -482,6 +585,7 @@ extern "C" int dmcf_grid_build(const float* points, dmcf_grid* grid, void* works
     cudaStream_t st = (cudaStream_t)stream;
     const int n = grid->n_points;
     const int64_t n_cells = (int64_t)g.nx * g.ny * g.nz;
+    grid->points = points;
     DMCF_REQUIRE(n == 0 || points, "grid_build: points is NULL");
     DMCF_REQUIRE(workspace != nullptr, "grid_build: workspace is NULL");
     if (workspace_bytes < dmcf_grid_workspace_bytes(n, n_cells))
@@ -513,6 +617,22 @@ extern "C" int dmcf_grid_build(const float* points, dmcf_grid* grid, void* works
     return DMCF_OK;
 }
 
+namespace dmcf {
+extern std::atomic<int> g_kernel_options;  // cconv.cu; bit 6 here: keep the query-centric k_frs for prefix searches (A/B switch)
+}
+
+// queries == the points the grid was built from (a prefix of them): the cell-centric kernel applies
+static bool frs_prefix_case(const dmcf_grid* grid, const float* queries, int64_t n_queries) {
+    return grid->points != nullptr && queries == grid->points && n_queries <= (int64_t)grid->n_points &&
+           !(g_kernel_options.load(std::memory_order_relaxed) & 64);
+}
+
+static unsigned frs_cell_blocks(const GridView& g) {
+    const int64_t want = ceil_div((int64_t)g.nx * g.ny * g.nz, 8);
+    const int64_t cap = 148 * 32;
+    return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
 static unsigned frs_blocks(int64_t n_queries) {
     int64_t want = ceil_div(n_queries, 8);  // 8 warps per block
     int64_t cap = 148 * 32;                 // persistent-ish: a multiple of the SM count
@@ -527,6 +647,12 @@ extern "C" int dmcf_frs_count(const dmcf_grid* grid, const float* queries, int64
     DMCF_REQUIRE(n_queries >= 0 && (n_queries == 0 || (queries && counts)), "frs_count: NULL buffer");
     DMCF_REQUIRE(radius >= 0.0f, "frs_count: negative radius");
     if (n_queries == 0) return DMCF_OK;
+    if (frs_prefix_case(grid, queries, n_queries)) {
+        k_frs_cell<false><<<frs_cell_blocks(g), 256, 0, (cudaStream_t)stream>>>(g, n_queries, n_queries_dev, radius, radius * radius,
+                                                                                   ignore_query_point, nullptr, 0, counts, nullptr, nullptr, nullptr);
+        DMCF_LAUNCH_CHECK("k_frs_cell<count>");
+        return DMCF_OK;
+    }
     k_frs<false><<<frs_blocks(n_queries), 256, 0, (cudaStream_t)stream>>>(g, queries, n_queries, n_queries_dev, radius, radius * radius,
                                                                             ignore_query_point, nullptr, 0, counts, nullptr, nullptr, nullptr);
     DMCF_LAUNCH_CHECK("k_frs<count>");
@@ -542,6 +668,13 @@ extern "C" int dmcf_frs_fill(const dmcf_grid* grid, const float* queries, int64_
     DMCF_REQUIRE(n_queries >= 0 && (n_queries == 0 || (queries && row_splits)), "frs_fill: NULL buffer");
     DMCF_REQUIRE(capacity >= 0 && (capacity == 0 || neighbors_index), "frs_fill: NULL neighbors_index");
     if (n_queries == 0) return DMCF_OK;
+    if (frs_prefix_case(grid, queries, n_queries)) {
+        k_frs_cell<true><<<frs_cell_blocks(g), 256, 0, (cudaStream_t)stream>>>(g, n_queries, n_queries_dev, radius, radius * radius,
+                                                                                  ignore_query_point, row_splits, capacity, nullptr,
+                                                                                  neighbors_index, neighbors_distance, overflow_flag);
+        DMCF_LAUNCH_CHECK("k_frs_cell<fill>");
+        return DMCF_OK;
+    }
     k_frs<true><<<frs_blocks(n_queries), 256, 0, (cudaStream_t)stream>>>(g, queries, n_queries, n_queries_dev, radius, radius * radius,
                                                                            ignore_query_point, row_splits, capacity, nullptr,
                                                                            neighbors_index, neighbors_distance, overflow_flag);

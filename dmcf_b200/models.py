@@ -431,6 +431,14 @@ class PBFNet(BaseModel):
                 # halo width = the largest radius any conv applies to these points (coarse scales read scale 0 with it)
                 self._halo = [slab.make_halo(all_pos, max(self.particle_radii))]
                 all_in = ops.concat_rows([all_pos, self._halo[0].ghost_pos])
+                # the owned rows as a VIEW of [owned | ghost]: same values, and a search whose queries are a prefix of its points
+                # takes the cell-centric kernel (dmcf_frs_*: queries == grid->points)
+                cnt = ops.count_of(all_pos)
+                all_pos = all_in[: all_pos.shape[0]]
+                if cnt is not None:
+                    ops.with_count(all_pos, cnt)
+                self.all_pos = all_pos
+                self._pos_own = [all_pos]
                 self._pos_in = [all_in]
                 x = self._with_ghosts(0, x)
             self._pos_in = [all_in]
@@ -515,6 +523,10 @@ class PBFNet(BaseModel):
                 self._pos_own.append(None)
             self._halo[si] = plan
             self._pos_in[si] = ops.concat_rows([own, plan.ghost_pos])
+            cnt = ops.count_of(own)
+            own = self._pos_in[si][: own.shape[0]]  # view of [owned | ghost] (prefix searches, see preprocess)
+            if cnt is not None:
+                ops.with_count(own, cnt)
             self._pos_own[si] = own
             out.append(own)
         return out

@@ -74,6 +74,8 @@ typedef struct dmcf_grid {
     float* sorted_pos;     /* [n_points,4], 16-byte aligned */
     const int32_t* n_points_dev; /* optional device-side count: only rows [0, *n_points_dev) of `points` are inserted (n_points is
                                     then the capacity; sorted_index / sorted_pos entries beyond the count are not written) */
+    const float* points;   /* written by dmcf_grid_build: the array the grid was built from.  A search whose `queries` pointer
+                              equals it (queries = a prefix of the points) takes the cell-centric kernel k_frs_cell */
 } dmcf_grid;
 
 size_t dmcf_grid_workspace_bytes(int64_t n_points, int64_t n_cells);
@@ -178,7 +180,8 @@ int dmcf_cconv_patches(const dmcf_conv_desc* desc, const float* out_positions, i
  * (k_cconv_direct) and the folded half-patch kernel for antisymmetric filters (k_cconv_apatch), bit 2 = run 4x4x4 layers of
  * the legacy k_cconv_wide as two z-half launches, bit 3 = use the legacy k_cconv_wide instead of k_cconv_lean, bit 4 = do
  * not use k_cconv_apatch, bit 5 = k_cconv_lean keeps the one-pair-per-step walk for inputs with <= 8 channels instead of the
- * multi-pair phase 1 (bits 3, 4 and 5 are kept for A/B measurements); 0 forces the generic kernel.  Returns the previous
+ * multi-pair phase 1, bit 6 = searches whose queries are a prefix of the grid's points keep the query-centric k_frs instead of
+ * the cell-centric k_frs_cell (bits 3-6 are kept for A/B measurements); 0 forces the generic kernel.  Returns the previous
  * mask.  Results agree to float32 rounding. */
 int dmcf_set_kernel_options(int options);
 

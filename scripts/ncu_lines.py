@@ -1,53 +1,49 @@
-"""Joins an ncu SASS source page with nvdisasm line info: samples / instructions per CUDA source line.
-  python scripts/ncu_lines.py <report.ncu-rep> <mangled kernel substring> [topN]
-Needs the .so the report was taken from (dmcf_b200/lib/libdmcf_b200.so, built with -lineinfo)."""
-import csv, glob, os, re, subprocess, sys, tempfile
-rep, kern = sys.argv[1], sys.argv[2]
-topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "dmcf_b200/lib/libdmcf_b200.so")], cwd=tmp, capture_output=True)
-addr2line = {}
-for cub in glob.glob(os.path.join(tmp, "*.cubin")):
-    dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout
-    if kern not in dis:
-        continue
-    in_fn, cur = False, None
-    for line in dis.splitlines():
-        if line.startswith(".text.") and line.endswith(":"):
-            in_fn = kern in line
-            continue
-        if not in_fn:
-            continue
-        m = re.search(r'//## File "([^"]+)", line (\d+)', line)
-        if m:
-            cur = (os.path.basename(m.group(1)), int(m.group(2)))
-            continue
-        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", line)
-        if m and cur:
-            addr2line[int(m.group(1), 16)] = cur
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+"""Per CUDA-C source line view of an ncu report (needs -lineinfo and --import-source on):
+  python scripts/ncu_lines.py <report.ncu-rep> [N] [launch]
+prints, per source file, the top-N lines by warp instructions executed with their share of stall samples."""
+import csv
+import subprocess
+import sys
+
+path = sys.argv[1]
+topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+raw = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "cuda,sass", "--launch-skip", str(launch),
+                      "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-idx = {h: i for i, h in enumerate(rows[hi])}
-data = rows[hi + 1:]
-base = min(int(r[0], 16) for r in data if r and r[0].startswith("0x")) if data and data[0][0].startswith("0x") else 0
-agg = {}
-ts = ti = 0.0
-for n, r in enumerate(data):
-    try:
-        s = float(r[idx["# Samples"]] or 0); i = float(r[idx["Instructions Executed"]] or 0)
-    except (ValueError, IndexError):
+files, cur, hdr = {}, None, None
+for r in rows:
+    if not r:
         continue
-    off = (int(r[0], 16) - base) if r[0].startswith("0x") else n * 16
-    key = addr2line.get(off, ("?", 0))
-    a = agg.setdefault(key, [0.0, 0.0])
-    a[0] += s; a[1] += i; ts += s; ti += i
-srcs = {}
-print(f"samples {ts:.0f}  warp-instructions {ti:.3e}")
-for (f, ln), (s, i) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
-    if f not in srcs:
-        p = os.path.join(root, "dmcf_b200/csrc", f)
-        srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []
-    text = srcs[f][ln - 1].strip()[:90] if 0 < ln <= len(srcs[f]) else ""
-    print(f"{100*s/ts:5.1f}% smp {100*i/ti:5.1f}% inst  {f}:{ln:<4} {text}")
+    if r[0] == "File Path":
+        cur = r[1]
+        files.setdefault(cur, {})
+        continue
+    if r[0] == "Line No":
+        hdr = r
+        continue
+    if hdr is None or cur is None or len(r) < len(hdr) or not r[0].isdigit():
+        continue
+    # rows with Address == '-' are the per-source-line aggregates
+    if r[2] != "-":
+        continue
+    ii, si = hdr.index("Instructions Executed"), hdr.index("# Samples")
+    try:
+        inst, smp = float(r[ii] or 0), float(r[si] or 0)
+    except ValueError:
+        continue
+    d = files[cur].setdefault(int(r[0]), [r[1], 0.0, 0.0])
+    d[1] += inst
+    d[2] += smp
+tot_i = sum(v[1] for f in files.values() for v in f.values())
+tot_s = sum(v[2] for f in files.values() for v in f.values())
+print(f"total warp instructions {tot_i:.3e}  samples {tot_s:.0f}")
+for fname, lines in files.items():
+    fi, fs = sum(v[1] for v in lines.values()), sum(v[2] for v in lines.values())
+    if fi == 0:
+        continue
+    print(f"== {fname}: inst {100 * fi / tot_i:.1f}%  samples {100 * fs / max(tot_s, 1):.1f}%")
+    for ln, v in sorted(lines.items(), key=lambda kv: -kv[1][1])[:topn]:
+        if v[1] / tot_i < 0.002:
+            break
+        print(f"  {ln:4d} inst {100 * v[1] / tot_i:5.2f}%  smp {100 * v[2] / max(tot_s, 1):5.2f}%  {v[0].strip()[:110]}")

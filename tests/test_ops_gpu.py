@@ -49,9 +49,18 @@ def clouds():
     yield "large_coords", far.astype(np.float32), 0.3
 
 
+@pytest.fixture(params=[3, 67], ids=["cell-centric-search", "query-centric-search"])
+def frs_options(request):
+    """Same-set searches (queries = a prefix of the points) run k_frs_cell by default; option bit 6 keeps k_frs."""
+    from dmcf_b200 import ops
+    prev = ops.set_kernel_options(request.param)
+    yield request.param
+    ops.set_kernel_options(prev)
+
+
 @pytest.mark.parametrize("name,pts,radius", list(clouds()), ids=[c[0] for c in clouds()])
 @pytest.mark.parametrize("ignore", [False, True])
-def test_fixed_radius_search_bit_exact(cuda, name, pts, radius, ignore):
+def test_fixed_radius_search_bit_exact(cuda, name, pts, radius, ignore, frs_options):
     from dmcf_b200 import ops
     t = torch.from_numpy(pts).to(cuda)
     res = ops.fixed_radius_search(t, t, radius, ignore_query_point=ignore, return_distances=True)
@@ -87,6 +96,40 @@ def test_fixed_radius_search_distinct_sets_and_empty(cuda):
     x = ops.fixed_radius_search(t, t, 0.1)
     y = ops.fixed_radius_search(t, t, 0.1)
     assert torch.equal(x.neighbors_index, y.neighbors_index)
+
+
+def test_prefix_search_kernels_agree_row_for_row(cuda):
+    """The cell-centric kernel (queries = the first rows of the point set, as in every same-set search of a step: owned rows
+    out, owned + ghost rows in) returns the SAME arrays as the query-centric one, element for element (row order included),
+    also for a proper prefix, with crowded cells (> 32 points per cell) and with a device-side query count."""
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(9)
+    pts = np.concatenate([rng.random((6000, 3)), rng.random((3000, 3)) * 0.05 + 0.4]).astype(np.float32)  # a crowded clump
+    pts = pts[rng.permutation(len(pts))]
+    t = torch.from_numpy(pts).to(cuda)
+    for nq, radius in ((len(pts), 0.06), (5000, 0.06), (1, 0.2), (7000, 0.11)):
+        q = t[:nq]  # a view: same base pointer -> prefix case
+        out = {}
+        for opt in (3, 67):
+            prev = ops.set_kernel_options(opt)
+            try:
+                cl = ops.CellList(t, radius)
+                out[opt] = ops.fixed_radius_search(t, q, radius, cell_list=cl, return_distances=True)
+            finally:
+                ops.set_kernel_options(prev)
+        for a, b in zip(out[3], out[67]):
+            assert torch.equal(a, b), (nq, radius)
+        ri, rs, rd = o64.fixed_radius_search(pts, pts[:nq], radius)
+        assert np.array_equal(out[3].neighbors_row_splits.cpu().numpy(), rs)
+    # device-side count: rows beyond it are empty
+    cl = ops.CellList(t, 0.06)
+    nq_dev = torch.tensor([4000], dtype=torch.int32, device=cuda)
+    res = ops.fixed_radius_search(t, ops.with_count(t[:6000], nq_dev), 0.06, cell_list=cl, capacity=2_000_000)
+    ref = ops.fixed_radius_search(t, t[:4000], 0.06, cell_list=cl)
+    assert torch.equal(res.neighbors_row_splits[:4001], ref.neighbors_row_splits)
+    assert bool((res.neighbors_row_splits[4001:] == ref.neighbors_row_splits[-1]).all())
+    n = int(ref.neighbors_row_splits[-1])
+    assert torch.equal(res.neighbors_index[:n], ref.neighbors_index)
 
 
 def test_neighbor_counts_is_reduce_subarrays_sum(cuda):
