@@ -622,9 +622,13 @@ extern std::atomic<int> g_kernel_options;  // cconv.cu; bit 6 here: keep the que
 }
 
 // queries == the points the grid was built from (a prefix of them): the cell-centric kernel applies
+// ... and pays when a cell holds few points: the kernel saves candidate TRAFFIC (one load per cell instead of one per query) but
+// spends more instructions per (query, candidate batch) test, and a crowded cell is one warp's serial work.  Measured: 8 points
+// per cell (C4, r = 2 spacings) count + fill 1.51 -> 1.10 ms; ~64 per cell (the coarse scales of Liquid3d) 3.8 -> 5.4 ms.
 static bool frs_prefix_case(const dmcf_grid* grid, const float* queries, int64_t n_queries) {
+    const int64_t n_cells = (int64_t)grid->dims[0] * grid->dims[1] * grid->dims[2];
     return grid->points != nullptr && queries == grid->points && n_queries <= (int64_t)grid->n_points &&
-           !(g_kernel_options.load(std::memory_order_relaxed) & 64);
+           (int64_t)grid->n_points <= 12 * n_cells && !(g_kernel_options.load(std::memory_order_relaxed) & 64);
 }
 
 static unsigned frs_cell_blocks(const GridView& g) {

@@ -124,7 +124,7 @@ def test_prefix_search_kernels_agree_row_for_row(cuda):
     # device-side count: rows beyond it are empty
     cl = ops.CellList(t, 0.06)
     nq_dev = torch.tensor([4000], dtype=torch.int32, device=cuda)
-    res = ops.fixed_radius_search(t, ops.with_count(t[:6000], nq_dev), 0.06, cell_list=cl, capacity=2_000_000)
+    res = ops.fixed_radius_search(t, ops.with_count(t[:6000], nq_dev), 0.06, cell_list=cl, capacity=8_000_000)
     ref = ops.fixed_radius_search(t, t[:4000], 0.06, cell_list=cl)
     assert torch.equal(res.neighbors_row_splits[:4001], ref.neighbors_row_splits)
     assert bool((res.neighbors_row_splits[4001:] == ref.neighbors_row_splits[-1]).all())
