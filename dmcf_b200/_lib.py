@@ -21,7 +21,7 @@ class DmcfError(RuntimeError):
 class Grid(C.Structure):
     """struct dmcf_grid"""
     _fields_ = [("origin", c_f32 * 3), ("inv_cell", c_f32), ("dims", c_i32 * 3), ("n_points", c_i32),
-                ("cell_start", c_vp), ("sorted_index", c_vp), ("sorted_pos", c_vp), ("n_points_dev", c_vp), ("points", c_vp)]
+                ("cell_start", c_vp), ("sorted_index", c_vp), ("sorted_pos", c_vp), ("n_points_dev", c_vp), ("points", c_vp), ("mean_occupancy", c_f32)]
 
 
 class ConvDesc(C.Structure):

@@ -627,8 +627,11 @@ extern std::atomic<int> g_kernel_options;  // cconv.cu; bit 6 here: keep the que
 // per cell (C4, r = 2 spacings) count + fill 1.51 -> 1.10 ms; ~64 per cell (the coarse scales of Liquid3d) 3.8 -> 5.4 ms.
 static bool frs_prefix_case(const dmcf_grid* grid, const float* queries, int64_t n_queries) {
     const int64_t n_cells = (int64_t)grid->dims[0] * grid->dims[1] * grid->dims[2];
-    return grid->points != nullptr && queries == grid->points && n_queries <= (int64_t)grid->n_points &&
-           (int64_t)grid->n_points <= 12 * n_cells && !(g_kernel_options.load(std::memory_order_relaxed) & 64);
+    // points per OCCUPIED cell as the caller estimates it from the points' bounding box (the grid itself may be padded), else
+    // points per cell of the grid
+    const float occupancy = grid->mean_occupancy > 0.0f ? grid->mean_occupancy : (float)grid->n_points / (float)(n_cells > 0 ? n_cells : 1);
+    return grid->points != nullptr && queries == grid->points && n_queries <= (int64_t)grid->n_points && occupancy <= 12.0f &&
+           !(g_kernel_options.load(std::memory_order_relaxed) & 64);
 }
 
 static unsigned frs_cell_blocks(const GridView& g) {

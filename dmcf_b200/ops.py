@@ -311,10 +311,12 @@ class CellList:
         cell_size = float(cell_size)
         if not cell_size > 0:
             raise ValueError("cell_size must be positive")
+        box_lo = box_hi = None  # the points' true bounding box when known (occupancy hint for the search kernels)
         if (origin is None or dims is None) and _PLAN() is not None and _PLAN().mode == "replay":
             # planned grid: the measured bounding box padded by a few cells; points that leave it are clamped into the border
             # cells (always correct) and raise the SOFT flag so that the caller re-plans after this step
             e, slot = _PLAN().next("grid")
+            box_lo, box_hi = e["lo"], e["hi"]
             pad = [StepPlan.GRID_PAD_CELLS * cell_size + StepPlan.GRID_PAD_FRAC * (e["hi"][a] - e["lo"][a]) for a in range(3)]
             origin = [e["lo"][a] - pad[a] for a in range(3)]
             while True:
@@ -343,6 +345,7 @@ class CellList:
                 lo, hi = lohi[0].tolist(), lohi[1].tolist()
             else:
                 lo, hi = [0.0] * 3, [0.0] * 3
+            box_lo, box_hi = lo, hi
             if _PLAN() is not None and _PLAN().mode == "measure":
                 _PLAN().record("grid", lo=lo, hi=hi)
             while True:
@@ -369,6 +372,11 @@ class CellList:
         g.sorted_index = self.sorted_index.data_ptr()
         g.sorted_pos = self.sorted_pos.data_ptr()
         g.n_points_dev = None if n_dev is None else n_dev.data_ptr()
+        if box_lo is not None and n > 0:
+            occupied = 1.0
+            for a in range(3):
+                occupied *= max(1.0, (box_hi[a] - box_lo[a]) / cell_size)
+            g.mean_occupancy = n / occupied
         self.grid = g
         ws_bytes = lib.dmcf_grid_workspace_bytes(n, self.n_cells)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)

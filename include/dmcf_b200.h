@@ -76,6 +76,8 @@ typedef struct dmcf_grid {
                                     then the capacity; sorted_index / sorted_pos entries beyond the count are not written) */
     const float* points;   /* written by dmcf_grid_build: the array the grid was built from.  A search whose `queries` pointer
                               equals it (queries = a prefix of the points) takes the cell-centric kernel k_frs_cell */
+    float mean_occupancy;  /* optional hint: points per occupied cell (0 = unknown, the library then uses n_points / cells of the
+                              grid, which underestimates it for padded grids); k_frs_cell is used up to 12 points per cell */
 } dmcf_grid;
 
 size_t dmcf_grid_workspace_bytes(int64_t n_points, int64_t n_cells);
