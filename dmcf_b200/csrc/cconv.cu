@@ -186,6 +186,7 @@ static int launch_cconv(const ConvParams& p, cudaStream_t st) {
     }
 }
 
+int launch_cconv_ws(const ConvParams& p, cudaStream_t st, bool* handled);      // cconv_ws.cu
 int launch_cconv_lean(const ConvParams& p, cudaStream_t st, bool* handled);    // cconv_lean.cu
 int launch_cconv_apatch(const ConvParams& p, cudaStream_t st, bool* handled);  // cconv_apatch.cu
 int launch_cconv_wide(const ConvParams& p, cudaStream_t st, bool* handled);    // cconv_wide.cu
@@ -376,7 +377,12 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
         rc = launch_cconv_direct(p, st, &handled);
         if (rc || handled) return rc;
     }
-    if ((options & 1) && !(options & 8)) {  // lean register-patch kernel (production path of the wide layers)
+    if ((options & 1) && !(options & 8) && !(options & 128)) {  // warp-specialised register-patch kernel: both phases at once
+        bool handled = false;
+        rc = launch_cconv_ws(p, st, &handled);
+        if (rc || handled) return rc;
+    }
+    if ((options & 1) && !(options & 8)) {  // lean register-patch kernel (narrow inputs, patch export, A/B)
         bool handled = false;
         rc = launch_cconv_lean(p, st, &handled);
         if (rc || handled) return rc;
