@@ -32,7 +32,7 @@ static constexpr int MT = 11;    // points per half tile
 static constexpr int NPW = 12;   // producer warps (warp MT..NPW-1 have no point)
 static constexpr int NCW = 4;    // consumer warps
 static constexpr int kSlotWords = 8 * 32;  // filter ring slot: 8 rows x (cout <= 32)
-static constexpr int kSlots = 3;
+static constexpr int kSlots = 5;
 static constexpr int kRedRows = 12;        // partial-sum rows per consumer warp (row 11 is the padding point of the thread tile)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
 #pragma unroll
             for (int c = 0; c < K; ++c) acc[c] = 0.0f;
             float norm_acc = 0.0f;
-            if (o_ok) {
+            if (o_ok && !(p.debug_wrap_w & 8)) {  // (timing experiment, option bit 11: no phase 1 -> consumer-bound time)
                 float fc = 0.0f;  // centre feature of the antisymmetric layer (out point o == input row o)
                 if (p.ascc && lane_ci) {
                     fc = __ldg(p.inp_feat + o * p.inp_stride + lane);
@@ -155,18 +155,12 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
     const int groups = p.kc_conv >> 3;                          // 8-row steps over the whole filter
     const int n_it = groups > wc ? (groups - wc + NCW - 1) / NCW : 0;
     float* ring = frings + (size_t)wc * ws::kSlots * ws::kSlotWords;
-    float* const slot0 = ring, * const slot1 = ring + ws::kSlotWords, * const slot2 = ring + 2 * ws::kSlotWords;
     const int f4_per_step = 2 * cout;                           // float4s of 8 filter rows
     // lane = (q = lane / 4: k = 8 g + q, pr = (lane / 2) % 2: points 6 pr .. 6 pr + 5, cc = lane % 2: channels 16 cc .. 16 cc + 15)
     const int q = lane >> 2, pr = (lane >> 1) & 1, cc = lane & 1;
-    const float4* fw0[4]; const float4* fw1[4]; const float4* fw2[4];
+    int fw_off[4];  // this lane's four float4s of filter row q inside a ring slot (lanes beyond cout recompute the last quad)
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-        const int off = q * cout + min(cc * 16 + 4 * h, cout - 4);  // lanes beyond cout recompute the last quad
-        fw0[h] = reinterpret_cast<const float4*>(slot0 + off);
-        fw1[h] = reinterpret_cast<const float4*>(slot1 + off);
-        fw2[h] = reinterpret_cast<const float4*>(slot2 + off);
-    }
+    for (int h = 0; h < 4; ++h) fw_off[h] = q * cout + min(cc * 16 + 4 * h, cout - 4);
     // this lane's patch words: k-quad 2 g + q / 4, word q % 4, points 6 pr + i
     const int pw_off = (((2 * wc + (q >> 2)) * MT) + pr * 6) * 4 + (q & 3);
     constexpr int pw_step = 2 * NCW * MT * 4;                   // g += NCW  ->  k-quad += 2 NCW
@@ -185,8 +179,12 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
             lean::cp_commit();
             fsrc += fstep;
         };
-        issue(0, slot0);
-        issue(1, slot1);
+        int fetch_slot = 0;
+#pragma unroll
+        for (int pre = 0; pre < ws::kSlots - 1; ++pre) {
+            issue(pre, ring + fetch_slot * ws::kSlotWords);
+            ++fetch_slot;
+        }
         tma::mbar_wait(b ? bar_full0 + 8 : bar_full0, (uint32_t)((i >> 1) & 1));
         float2 acc2[6][8];
 #pragma unroll
@@ -194,37 +192,33 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
 #pragma unroll
             for (int h = 0; h < 8; ++h) acc2[a][h] = make_float2(0.0f, 0.0f);
         const float* pw = tiles + (size_t)b * tile_words + pw_off;
-#define DMCF_WS_STEP(FR, WSLOT)                                                                                  \
-        {                                                                                                        \
-            lean::cp_wait<1>();                                                                                  \
-            __syncwarp(); /* every lane's part of this slot landed; every lane is done with the previous slot */ \
-            float4 w[4];                                                                                         \
-            _Pragma("unroll") for (int h = 0; h < 4; ++h) w[h] = *FR[h];                                          \
-            float pv[6];                                                                                         \
-            _Pragma("unroll") for (int a = 0; a < 6; ++a) pv[a] = pw[a * 4];                                      \
-            issue(it + 2, WSLOT);                                                                                \
-            pw += pw_step;                                                                                       \
-            _Pragma("unroll") for (int a = 0; a < 6; ++a) {                                                      \
-                const float2 pp = make_float2(pv[a], pv[a]);                                                     \
-                _Pragma("unroll") for (int h = 0; h < 4; ++h) {                                                  \
-                    acc2[a][2 * h] = __ffma2_rn(pp, make_float2(w[h].x, w[h].y), acc2[a][2 * h]);                \
-                    acc2[a][2 * h + 1] = __ffma2_rn(pp, make_float2(w[h].z, w[h].w), acc2[a][2 * h + 1]);        \
-                }                                                                                                \
-            }                                                                                                    \
-            ++it;                                                                                                \
-        }
-        {
-            int it = 0;
+        int use_slot = 0;  // fetch_slot == kSlots - 1: the slot consumed in the previous step
+        const int n_run = (p.debug_wrap_w & 1) ? 0 : n_it;  // (timing experiment, option bit 8: no phase 2 -> producer-bound time)
 #pragma unroll 1
-            while (it + 3 <= n_it) {
-                DMCF_WS_STEP(fw0, slot2)
-                DMCF_WS_STEP(fw1, slot0)
-                DMCF_WS_STEP(fw2, slot1)
+        for (int it = 0; it < n_run; ++it) {
+            lean::cp_wait<ws::kSlots - 2>();
+            __syncwarp();  // every lane's part of this slot landed; every lane is done with the slot consumed one step ago
+            const float* sl = ring + use_slot * ws::kSlotWords;
+            float4 w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) w[h] = *reinterpret_cast<const float4*>(sl + fw_off[h]);
+            float pv[6];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) pv[a] = pw[a * 4];
+            issue(it + ws::kSlots - 1, ring + fetch_slot * ws::kSlotWords);
+            fetch_slot = fetch_slot + 1 == ws::kSlots ? 0 : fetch_slot + 1;
+            use_slot = use_slot + 1 == ws::kSlots ? 0 : use_slot + 1;
+            pw += pw_step;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const float2 pp = make_float2(pv[a], pv[a]);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    acc2[a][2 * h] = __ffma2_rn(pp, make_float2(w[h].x, w[h].y), acc2[a][2 * h]);
+                    acc2[a][2 * h + 1] = __ffma2_rn(pp, make_float2(w[h].z, w[h].w), acc2[a][2 * h + 1]);
+                }
             }
-            if (it < n_it) DMCF_WS_STEP(fw0, slot2)
-            if (it < n_it) DMCF_WS_STEP(fw1, slot0)
         }
-#undef DMCF_WS_STEP
         lean::cp_wait<0>();
         // the half tile is not read any more (its normalisers are taken along in registers): hand it back to the producers now,
         // they refill it while this tile's partial sums are reduced and stored
