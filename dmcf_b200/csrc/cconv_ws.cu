@@ -19,7 +19,8 @@
 // producers' scratch (12 x 2 KB), the consumers' filter rings (4 x 3 KB) and their partial sums.  The twelfth producer warp has
 // no point (it only keeps the barrier counts; warpgroups are the granularity of setmaxnreg).  The filter is streamed once per
 // 11 points instead of once per 24: 2.2x the L2 -> shared-memory traffic of k_cconv_lean (L2 runs at 8.5 % of its peak there).
-// The fused Dense rows are not part of the tile (they would cost a padding k-quad column): the epilogue adds x_o . Wd directly.
+// The fused Dense rows ride in the tile as one more "cell" like in k_cconv_lean (a first version added x_o . Wd in the epilogue
+// with loads from L2 -- the SM has no L1 left next to 223 KB of shared memory -- and cost 15 us per tile).
 // Same arithmetic per point as k_cconv_lean except for the summation order of the split-K partial sums (float32 rounding).
 #include <cuda_pipeline_primitives.h>
 
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
     float* rings = smem;
     float* recs = rings + (size_t)NPW * lean::kGatherSlots * 32;
     float* tiles = recs + (size_t)NPW * lean::kRecWords;
-    const int kq_total = p.kc_conv >> 2;                       // kc_conv % 8 == 0 (launcher)
+    const int kq_total = p.kc >> 2;                            // conv rows + fused Dense rows; kc % 8 == 0 (launcher)
     const size_t tile_words = (size_t)kq_total * MT * 4 + 4;   // + one float4: the thread tile's padding point reads past the last row
     float* frings = tiles + 2 * tile_words;
     float* red = frings + (size_t)NCW * ws::kSlots * ws::kSlotWords;
@@ -132,6 +133,14 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
                         for (int c = 0; c < K; ++c) tile[ws::tile_index(warp, c * p.cin + lane)] = acc[c];
                     }
                 }
+                if (p.dense_cin > 0) {  // fused Dense: the (relu'd, unscaled) centre features are one more "cell" of the patch
+                    const float* drow = p.dense_inp + o * p.dense_stride;
+                    for (int ci = lane; ci < p.dense_cin; ci += 32) {
+                        float f = __ldg(drow + ci);
+                        if (p.relu_input) f = fmaxf(f, 0.0f);
+                        tile[ws::tile_index(warp, p.kc_conv + ci)] = f;
+                    }
+                }
                 if (p.normalize) {
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) norm_acc += __shfl_xor_sync(0xffffffffu, norm_acc, off);
@@ -152,7 +161,7 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
     const int wc = warp - NPW;
     const int ctid = tid - NPW * 32;
     const int cout = p.cout;
-    const int groups = p.kc_conv >> 3;                          // 8-row steps over the whole filter
+    const int groups = p.kc >> 3;                               // 8-row steps over the whole filter (conv + Dense rows)
     const int n_it = groups > wc ? (groups - wc + NCW - 1) / NCW : 0;
     float* ring = frings + (size_t)wc * ws::kSlots * ws::kSlotWords;
     const int f4_per_step = 2 * cout;                           // float4s of 8 filter rows
@@ -294,17 +303,6 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
 #pragma unroll
                 for (int w2 = 0; w2 < NCW; ++w2) v += red[((size_t)w2 * ws::kRedRows + m) * 32 + c];
                 if (p.normalize && nvals[j] != 0.0f) v /= nvals[j];
-                if (p.dense_cin > 0) {  // fused Dense on the centre features: x_o . Wd (rows kc_conv.. of the filter)
-                    const float* drow = p.dense_inp + oo * p.dense_stride;
-                    const float* wd = p.filters + (size_t)p.kc_conv * cout + c;
-                    float d = 0.0f;
-                    for (int ci = 0; ci < p.dense_cin; ++ci) {
-                        float f = __ldg(drow + ci);
-                        if (p.relu_input) f = fmaxf(f, 0.0f);
-                        d = fmaf(f, __ldg(wd + (size_t)ci * cout), d);
-                    }
-                    v += d;
-                }
                 if (p.bias) v += __ldg(p.bias + c);
                 if (p.residual) v += __ldg(p.residual + oo * p.residual_stride + c);
                 float* dst = p.out + oo * p.out_stride + c;
@@ -316,8 +314,8 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
     }
 }
 
-static size_t ws_smem_bytes(int kc_conv) {
-    const size_t tile_words = (size_t)(kc_conv / 4) * ws::MT * 4 + 4;
+static size_t ws_smem_bytes(int kc) {
+    const size_t tile_words = (size_t)(kc / 4) * ws::MT * 4 + 4;
     const size_t words = (size_t)ws::NPW * lean::kScratchWords + 2 * tile_words + (size_t)ws::NCW * ws::kSlots * ws::kSlotWords +
                          (size_t)ws::NCW * ws::kRedRows * 32 + 2 * 12;
     return words * sizeof(float) + 4 * sizeof(uint64_t);
@@ -326,7 +324,7 @@ static size_t ws_smem_bytes(int kc_conv) {
 template <int KZ, int KY, int KX>
 static int launch_ws_grid(const ConvParams& p, cudaStream_t st, bool* handled) {
     *handled = false;
-    const size_t smem = ws_smem_bytes(p.kc_conv);
+    const size_t smem = ws_smem_bytes(p.kc);
     if (smem > 227 * 1024) return DMCF_OK;
     static bool attr_set = false;
     // [relu on the input][feature scale and/or the antisymmetric centre term]
@@ -353,7 +351,7 @@ int launch_cconv_ws(const ConvParams& p, cudaStream_t st, bool* handled) {
     *handled = false;
     if (p.gp.interp != DMCF_INTERP_LINEAR || p.cin > 32 || p.cin <= 8) return DMCF_OK;  // narrow inputs: multi-pair phase 1 of lean
     if (p.cout % 4 != 0 || p.cout > 32 || ((uintptr_t)p.filters & 15) != 0 || p.patch_out) return DMCF_OK;
-    if ((p.kc_conv & 7) != 0 || (p.kc_conv >> 3) < ws::NCW) return DMCF_OK;
+    if ((p.kc & 7) != 0 || (p.kc >> 3) < ws::NCW) return DMCF_OK;  // 8-row steps over conv + fused Dense rows
     if ((p.n_inp > 0 ? p.n_inp : 1) * p.inp_stride * 4 >= ((int64_t)1 << 31)) return DMCF_OK;  // 32-bit gather offsets
     if (p.gp.kz == 4 && p.gp.ky == 4 && p.gp.kx == 4) return launch_ws_grid<4, 4, 4>(p, st, handled);
     if (p.gp.kz == 1 && p.gp.ky == 8 && p.gp.kx == 8) return launch_ws_grid<1, 8, 8>(p, st, handled);
