@@ -32,8 +32,10 @@ namespace ws {
 static constexpr int MT = 11;    // points per half tile
 static constexpr int NPW = 12;   // producer warps (warp MT..NPW-1 have no point)
 static constexpr int NCW = 4;    // consumer warps
-static constexpr int kSlotWords = 8 * 32;  // filter ring slot: 8 rows x (cout <= 32)
-static constexpr int kSlots = 5;
+static constexpr int kRowWords = 36;       // ring slot row: cout <= 32 words + 4 of padding -- with a 32-word stride the eight rows a
+                                           // warp reads at once (one per k lane) sit in the same banks: 8-way conflicts on every LDS.128
+static constexpr int kSlotWords = 8 * kRowWords;  // filter ring slot: 8 rows
+static constexpr int kSlots = 4;
 static constexpr int kRedRows = 12;        // partial-sum rows per consumer warp (row 11 is the padding point of the thread tile)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -164,12 +166,12 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
     const int groups = p.kc >> 3;                               // 8-row steps over the whole filter (conv + Dense rows)
     const int n_it = groups > wc ? (groups - wc + NCW - 1) / NCW : 0;
     float* ring = frings + (size_t)wc * ws::kSlots * ws::kSlotWords;
-    const int f4_per_step = 2 * cout;                           // float4s of 8 filter rows
+    const int f4_per_step = 2 * cout, c4 = cout >> 2;           // float4s of 8 filter rows / of one row
     // lane = (q = lane / 4: k = 8 g + q, pr = (lane / 2) % 2: points 6 pr .. 6 pr + 5, cc = lane % 2: channels 16 cc .. 16 cc + 15)
     const int q = lane >> 2, pr = (lane >> 1) & 1, cc = lane & 1;
     int fw_off[4];  // this lane's four float4s of filter row q inside a ring slot (lanes beyond cout recompute the last quad)
 #pragma unroll
-    for (int h = 0; h < 4; ++h) fw_off[h] = q * cout + min(cc * 16 + 4 * h, cout - 4);
+    for (int h = 0; h < 4; ++h) fw_off[h] = q * ws::kRowWords + min(cc * 16 + 4 * h, cout - 4);
     // this lane's patch words: k-quad 2 g + q / 4, word q % 4, points 6 pr + i
     const int pw_off = (((2 * wc + (q >> 2)) * MT) + pr * 6) * 4 + (q & 3);
     constexpr int pw_step = 2 * NCW * MT * 4;                   // g += NCW  ->  k-quad += 2 NCW
@@ -180,8 +182,9 @@ __global__ void __launch_bounds__((ws::NPW + ws::NCW) * 32, 1) k_cconv_ws(const 
         const size_t fstep = (size_t)NCW * 8 * cout;
         auto issue = [&](int it, float* slot) {
             if (it < n_it) {
-                for (int f = lane; f < f4_per_step; f += 32) {
-                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + f * 4);
+                for (int f = lane; f < f4_per_step; f += 32) {  // float4 f of the 8 x cout block: row f / (cout / 4), quad f % (cout / 4)
+                    const int row = f / c4, col = f - row * c4;
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot + row * ws::kRowWords + col * 4);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(fsrc + f * 4));
                 }
             }

@@ -819,7 +819,7 @@ def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0, antisym
     if cout <= 4 and (kc * cout + 4 + 16 * 32 * 12) * 4 <= 200 * 1024:
         return "k_cconv_direct"
     if interpolation == "linear" and cin <= 32 and cout % 4 == 0 and (kz, ky, kx) in ((4, 4, 4), (1, 8, 8), (1, 8, 1)):
-        ws_smem = (12 * 504 + 2 * (kc // 4 * 11 * 4 + 4) + 4 * 5 * 256 + 4 * 12 * 32 + 24) * 4 + 32
+        ws_smem = (12 * 504 + 2 * (kc // 4 * 11 * 4 + 4) + 4 * 4 * 288 + 4 * 12 * 32 + 24) * 4 + 32
         if 8 < cin and cout <= 32 and kc % 8 == 0 and kc // 8 >= 4 and ws_smem <= 227 * 1024:
             return "k_cconv_ws"
         kc_pad = (kc + 3) // 4 * 4
