@@ -377,12 +377,13 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
         rc = launch_cconv_direct(p, st, &handled);
         if (rc || handled) return rc;
     }
-    if ((options & 1) && !(options & 8) && !(options & 128)) {  // warp-specialised register-patch kernel: both phases at once
+    if ((options & 1) && !(options & 8) && (options & 128)) {  // warp-specialised register-patch kernel (measured experiment, off by
+                                                               // default: slower than k_cconv_lean, see cconv_ws.cu)
         bool handled = false;
         rc = launch_cconv_ws(p, st, &handled);
         if (rc || handled) return rc;
     }
-    if ((options & 1) && !(options & 8)) {  // lean register-patch kernel (narrow inputs, patch export, A/B)
+    if ((options & 1) && !(options & 8)) {  // lean register-patch kernel (production path of the wide layers)
         bool handled = false;
         rc = launch_cconv_lean(p, st, &handled);
         if (rc || handled) return rc;

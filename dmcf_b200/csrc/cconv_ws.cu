@@ -1,5 +1,16 @@
 // continuous_conv forward, WARP-SPECIALISED register-patch kernel (round 2): the two phases of k_cconv_lean run CONCURRENTLY.
 //
+// STATUS: a measured experiment, NOT the production path (dmcf_set_kernel_options bit 7 enables it; the parity suite runs it).
+// Measured on the C4 layers (1.06 M out points, profiles/README.md): 32->32 14.5 ms against 7.08 ms for k_cconv_lean, 24->32
+// 11.4 ms against 6.24 ms.  Why, from the two timing switches (option bits 8 / 11): with the consumers' k loop switched off the
+// producers alone need 5.0 ms (11 working warps at 112 registers are slower per point than lean's 12 at 168: 7.9 us against 5.2 us);
+// with the producers switched off the consumers alone need 13.4 ms, and that time follows the DEPTH of their filter ring (5 slots
+// 6.9 ms, 4 slots 10.3 ms on the 24->32 layer), not the arithmetic: streaming the 266 KB filter once per 11 points needs
+// ~53 GB/s per SM, i.e. ~35 KB in flight at L2 latency, and next to two 90 KB half tiles there are 18 KB left for the rings
+// (k_cconv_lean amortises every filter row over 24 points and spreads the stream over 12 warps).  Overlapping the phases costs
+// more in filter streaming than it wins; cluster multicast of the filter would halve the stream but needs the CTAs of a pair in
+// lock step.  Kept as evidence and as a starting point.
+//
 // k_cconv_lean (cconv_lean.cu) owns the SM with one 24-point patch tile and moves all 12 warps through phase 1 (pair walk,
 // latency bound: 51 % issue utilisation, no FFMA2) and then phase 2 (patch x filter, FFMA2 / shared-memory operand bound, no
 // L2 traffic) in lock step: neither phase can use what the other leaves idle (profiles/r1g_cconv_lean_source.md: 3.1 ms

@@ -802,8 +802,8 @@ def grid_pos(pos, voxel, center=None, hyst=0.1):
 def set_kernel_options(options):
     """bit 0: register-patch kernels for wide layers (k_cconv_ws / k_cconv_lean, default on), bit 1: direct kernel for cout <= 4,
     bit 2: z-split launches of the legacy k_cconv_wide, bit 3: legacy k_cconv_wide instead of k_cconv_lean, bit 5: single-pair
-    walk for narrow inputs, bit 6: query-centric search for prefix searches, bit 7: k_cconv_lean instead of the warp-specialised
-    k_cconv_ws.  Returns the previous mask."""
+    walk for narrow inputs, bit 6: query-centric search for prefix searches, bit 7: the warp-specialised k_cconv_ws instead of
+    k_cconv_lean (a measured experiment, slower).  Returns the previous mask."""
     return int(_lib.load().dmcf_set_kernel_options(int(options)))
 
 
@@ -819,9 +819,6 @@ def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0, antisym
     if cout <= 4 and (kc * cout + 4 + 16 * 32 * 12) * 4 <= 200 * 1024:
         return "k_cconv_direct"
     if interpolation == "linear" and cin <= 32 and cout % 4 == 0 and (kz, ky, kx) in ((4, 4, 4), (1, 8, 8), (1, 8, 1)):
-        ws_smem = (12 * 504 + 2 * (kc // 4 * 11 * 4 + 4) + 4 * 4 * 288 + 4 * 12 * 32 + 24) * 4 + 32
-        if 8 < cin and cout <= 32 and kc % 8 == 0 and kc // 8 >= 4 and ws_smem <= 227 * 1024:
-            return "k_cconv_ws"
         kc_pad = (kc + 3) // 4 * 4
         lean_smem = (max(kc_pad // 4 * 25 * 4, 12 * 24 * 32) + 12 * 384 + 24) * 4
         return "k_cconv_lean" if cout <= 32 and lean_smem <= 227 * 1024 else "k_cconv_wide"

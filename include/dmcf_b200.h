@@ -177,14 +177,15 @@ int dmcf_cconv_patches(const dmcf_conv_desc* desc, const float* out_positions, i
                        const float* neighbors_importance, const float* pair_records, int64_t n_pairs,
                        float* patches, int64_t patch_stride, void* stream);
 
-/* Kernel selection bit mask (default 3): bit 0 = register-patch kernels for compile-time filter grids (k_cconv_ws / k_cconv_lean;
- * k_cconv_wide where neither is eligible), bit 1 = resident-filter direct kernel for cout <= 4
+/* Kernel selection bit mask (default 3): bit 0 = register-patch kernels for compile-time filter grids (k_cconv_lean;
+ * k_cconv_wide where the lean kernel is not eligible), bit 1 = resident-filter direct kernel for cout <= 4
  * (k_cconv_direct) and the folded half-patch kernel for antisymmetric filters (k_cconv_apatch), bit 2 = run 4x4x4 layers of
  * the legacy k_cconv_wide as two z-half launches, bit 3 = use the legacy k_cconv_wide instead of k_cconv_lean, bit 4 = do
  * not use k_cconv_apatch, bit 5 = k_cconv_lean keeps the one-pair-per-step walk for inputs with <= 8 channels instead of the
  * multi-pair phase 1, bit 6 = searches whose queries are a prefix of the grid's points keep the query-centric k_frs instead of
- * the cell-centric k_frs_cell, bit 7 = the wide layers run k_cconv_lean (one 24-point tile, phases in lock step) instead of the
- * warp-specialised k_cconv_ws (bits 3-7 are kept for A/B measurements); 0 forces the generic kernel.  Returns the previous
+ * the cell-centric k_frs_cell, bit 7 = the wide layers run the warp-specialised k_cconv_ws (producer / consumer warps on
+ * double-buffered half tiles; a measured experiment, slower than k_cconv_lean) (bits 3-7 are kept for A/B measurements);
+ * 0 forces the generic kernel.  Returns the previous
  * mask.  Results agree to float32 rounding. */
 int dmcf_set_kernel_options(int options);
 
