@@ -30,7 +30,8 @@ class ConvDesc(C.Structure):
                 ("interpolation", c_i32), ("align_corners", c_i32), ("normalize", c_i32), ("window", c_i32),
                 ("window_fac", c_f32), ("extent", c_f32), ("offset", c_f32 * 3), ("relu_input", c_i32),
                 ("feat_scale", c_f32), ("ascc", c_i32), ("skip_self", c_i32), ("nbr_lo", c_i32), ("nbr_hi", c_i32),
-                ("dense_cin", c_i32), ("accumulate", c_i32), ("filter_antisym", c_i32), ("n_out_dev", c_vp)]
+                ("dense_cin", c_i32), ("accumulate", c_i32), ("filter_antisym", c_i32), ("n_out_dev", c_vp),
+                ("block_cin", c_i32), ("block_cout", c_i32 * 2)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/dmcf_b200.h
@@ -87,7 +88,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.dmcf_version() < 104:
+    if lib.dmcf_version() < 105:
         raise DmcfError("libdmcf_b200.so is older than this package")
     _lib = lib
     return lib

@@ -191,6 +191,7 @@ int launch_cconv_lean(const ConvParams& p, cudaStream_t st, bool* handled);    /
 int launch_cconv_apatch(const ConvParams& p, cudaStream_t st, bool* handled);  // cconv_apatch.cu
 int launch_cconv_wide(const ConvParams& p, cudaStream_t st, bool* handled);    // cconv_wide.cu
 int launch_cconv_direct(const ConvParams& p, cudaStream_t st, bool* handled);  // cconv_direct.cu
+int launch_cconv_narrow(const ConvParams& p, cudaStream_t st, bool* handled);  // cconv_narrow.cu
 std::atomic<int> g_kernel_options{3};
 
 
@@ -228,6 +229,13 @@ static int fill_params(const dmcf_conv_desc* d, const float* filters, const floa
     p.ascc = d->ascc; p.skip_self = d->skip_self; p.nbr_lo = d->nbr_lo; p.nbr_hi = d->nbr_hi;
     p.dense_cin = d->dense_cin; p.accumulate = d->accumulate; p.filter_antisym = d->filter_antisym;
     p.n_out_dev = d->n_out_dev;
+    if (d->block_cin > 0) {
+        DMCF_REQUIRE(d->block_cin < d->cin && d->block_cout[0] >= 1 && d->block_cout[1] >= 1 &&
+                         d->block_cout[0] + d->block_cout[1] <= d->cout,
+                     "cconv: block promise (block_cin %d, block_cout %d + %d) does not fit cin %d / cout %d", d->block_cin,
+                     d->block_cout[0], d->block_cout[1], d->cin, d->cout);
+        p.blk_ca = d->block_cin; p.blk_na = d->block_cout[0]; p.blk_nb = d->block_cout[1];
+    }
     const int64_t cells = (int64_t)p.gp.kx * p.gp.ky * p.gp.kz;
     DMCF_REQUIRE(cells * d->cin + d->dense_cin < (1 << 24), "cconv: filter too large");
     p.kc_conv = (int)(cells * d->cin);
@@ -375,6 +383,11 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
     if (options & 2) {  // resident-filter direct kernel for cout <= 4
         bool handled = false;
         rc = launch_cconv_direct(p, st, &handled);
+        if (rc || handled) return rc;
+    }
+    if ((options & 2) && !(options & 4096)) {  // direct kernel for narrow (block diagonal) layers: the input conv of every net
+        bool handled = false;
+        rc = launch_cconv_narrow(p, st, &handled);
         if (rc || handled) return rc;
     }
     if ((options & 1) && !(options & 8) && (options & 128)) {  // warp-specialised register-patch kernel (measured experiment, off by

@@ -18,6 +18,7 @@ struct ConvParams {
     int use_zsplit;           // option bit 2: run 4x4x4 wide layers as two z-half launches (2 CTAs/SM)
     int no_multipair;         // option bit 5: k_cconv_lean keeps the one-pair-per-step walk for narrow inputs (A/B switch)
     int cip, cp;              // pow2 lane groupings for input / output channels
+    int blk_ca, blk_na, blk_nb;  // block-diagonal promise (dmcf_conv_desc::block_cin / block_cout), 0 = none
     const float* filters;
     const float* out_pos;
     const float* inp_pos;

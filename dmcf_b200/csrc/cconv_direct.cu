@@ -13,7 +13,7 @@
 namespace dmcf {
 
 static constexpr int kDirWarps = 16;
-static constexpr int kDirRecWords = 12;  // {row, c000, dx | dy<<10 | dz<<20, pad, w0..w3, w4..w7}
+static constexpr int kDirRecWords = 12;  // {row, base offset, dx | dy << 16, dz (filter words), w0..w3, w4..w7}
 
 template <int COUT>
 __global__ void __launch_bounds__(kDirWarps * 32, 1) k_cconv_direct(const ConvParams p, int n_filter_words) {
@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(kDirWarps * 32, 1) k_cconv_direct(const ConvPa
     float* rec = scratch + (size_t)warp * 32 * kDirRecWords;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int kx = p.gp.kx, kyx = p.gp.ky * p.gp.kx;
+    const int cell_stride = p.cin * COUT;
 
     const int64_t n_warps = (int64_t)gridDim.x * kDirWarps;
     const int64_t n_out = conv_n_out(p);
@@ -41,14 +42,17 @@ __global__ void __launch_bounds__(kDirWarps * 32, 1) k_cconv_direct(const ConvPa
             const PairRec pr = pair_record(p, n, n < re, ox, oy, oz);
             const int row = pr.row;
             norm_acc += pr.norm;
-            int c000 = 0, dpack = 0;
+            // Parked record: {row, base cell offset, dx | dy << 16, dz} in filter WORDS (cell stride folded in once per pair by the
+            // lane that owns the pair instead of once per corner by every lane), then the eight corner weights.
+            int base = 0, dxy = 0, dzo = 0;
             float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
             if (row >= 0) {
                 const PairGeom& g = pr.g;
                 const int x0 = g.i0 & 0xff, y0 = (g.i0 >> 8) & 0xff, z0 = (g.i0 >> 16) & 0xff;
                 const int x1 = g.i1 & 0xff, y1 = (g.i1 >> 8) & 0xff, z1 = (g.i1 >> 16) & 0xff;
-                c000 = z0 * kyx + y0 * kx + x0;
-                dpack = (x1 - x0) | ((y1 - y0) << 10) | ((z1 - z0) << 20);  // each difference is 0 or 1
+                base = (z0 * kyx + y0 * kx + x0) * cell_stride;
+                dxy = ((x1 - x0) * cell_stride) | (((y1 - y0) * kx * cell_stride) << 16);  // each difference is 0 or 1
+                dzo = (z1 - z0) * kyx * cell_stride;
                 wa = make_float4(g.wx0 * g.wy0 * g.wz0, g.wx1 * g.wy0 * g.wz0, g.wx0 * g.wy1 * g.wz0, g.wx1 * g.wy1 * g.wz0);
                 wb = make_float4(g.wx0 * g.wy0 * g.wz1, g.wx1 * g.wy0 * g.wz1, g.wx0 * g.wy1 * g.wz1, g.wx1 * g.wy1 * g.wz1);
             }
@@ -57,51 +61,53 @@ __global__ void __launch_bounds__(kDirWarps * 32, 1) k_cconv_direct(const ConvPa
             __syncwarp();
             if (row >= 0) {
                 float* r = rec + __popc(active & lt_mask) * kDirRecWords;
-                *reinterpret_cast<int4*>(r) = make_int4(row, c000, dpack, 0);
+                *reinterpret_cast<int4*>(r) = make_int4(row, base, dxy, dzo);
                 *reinterpret_cast<float4*>(r + 4) = wa;
                 *reinterpret_cast<float4*>(r + 8) = wb;
+            }
+            if (lane < 3 && cnt + lane < ((cnt + 3) & ~3)) {  // pad the list to whole groups of four: no tail tests in the pair loop
+                float* r = rec + (cnt + lane) * kDirRecWords;
+                *reinterpret_cast<int4*>(r) = make_int4(-1, 0, 0, 0);
+                *reinterpret_cast<float4*>(r + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(r + 8) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             __syncwarp();
             for (int cb0 = 0; cb0 < p.cin; cb0 += 32) {
                 const int ci = cb0 + lane;
                 const bool ci_ok = ci < p.cin;
+                const int cic = ci_ok ? ci : p.cin - 1;  // lanes beyond cin read a valid address and contribute f = 0
                 float fc = 0.0f;
                 if (p.ascc && ci_ok) {
                     fc = __ldg(p.inp_feat + o * p.inp_stride + ci);
                     if (p.relu_input) fc = fmaxf(fc, 0.0f);
                     fc *= p.feat_scale;
                 }
-                const float* fl = filt + (size_t)ci * COUT;  // + cell * cin * COUT
-                const int cell_stride = p.cin * COUT;
+                const float* fl = filt + (size_t)cic * COUT;  // + cell * cin * COUT
                 for (int j = 0; j < cnt; j += 4) {
                     int4 hd[4];
                     float fv[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        if (j + u < cnt) {
-                            hd[u] = *reinterpret_cast<const int4*>(rec + (j + u) * kDirRecWords);
-                            fv[u] = ci_ok ? __ldg(p.inp_feat + (int64_t)hd[u].x * p.inp_stride + ci) : 0.0f;
-                        }
+                        hd[u] = *reinterpret_cast<const int4*>(rec + (j + u) * kDirRecWords);
+                        fv[u] = hd[u].x >= 0 ? __ldg(p.inp_feat + (int64_t)hd[u].x * p.inp_stride + cic) : 0.0f;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        if (j + u < cnt) {
-                            const float4 wa2 = *reinterpret_cast<const float4*>(rec + (j + u) * kDirRecWords + 4);
-                            const float4 wb2 = *reinterpret_cast<const float4*>(rec + (j + u) * kDirRecWords + 8);
-                            float f = fv[u];
-                            if (p.relu_input) f = fmaxf(f, 0.0f);
-                            f = fmaf(f, p.feat_scale, fc);
-                            if (!ci_ok) f = 0.0f;
-                            const int dxo = hd[u].z & 0x3ff, dyo = ((hd[u].z >> 10) & 0x3ff) * kx, dzo = ((hd[u].z >> 20) & 0x3ff) * kyx;
-                            const float w[8] = {wa2.x, wa2.y, wa2.z, wa2.w, wb2.x, wb2.y, wb2.z, wb2.w};
+                        const float4 wa2 = *reinterpret_cast<const float4*>(rec + (j + u) * kDirRecWords + 4);
+                        const float4 wb2 = *reinterpret_cast<const float4*>(rec + (j + u) * kDirRecWords + 8);
+                        float f = fv[u];
+                        if (p.relu_input) f = fmaxf(f, 0.0f);
+                        f = fmaf(f, p.feat_scale, fc);
+                        if (!ci_ok || hd[u].x < 0) f = 0.0f;
+                        const int dxo = hd[u].z & 0xffff, dyo = hd[u].z >> 16, dzo2 = hd[u].w;
+                        const float* fb = fl + hd[u].y;
+                        const float w[8] = {wa2.x, wa2.y, wa2.z, wa2.w, wb2.x, wb2.y, wb2.z, wb2.w};
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const int cell = hd[u].y + ((c & 1) ? dxo : 0) + ((c & 2) ? dyo : 0) + ((c & 4) ? dzo : 0);
-                                const float wf = w[c] * f;
-                                const float* fp = ci_ok ? fl + (size_t)cell * cell_stride : filt;
+                        for (int c = 0; c < 8; ++c) {
+                            const float* fp = fb + ((c & 1) ? dxo : 0) + ((c & 2) ? dyo : 0) + ((c & 4) ? dzo2 : 0);
+                            const float wf = w[c] * f;
 #pragma unroll
-                                for (int co = 0; co < COUT; ++co) acc[co] = fmaf(wf, fp[co], acc[co]);
-                            }
+                            for (int co = 0; co < COUT; ++co) acc[co] = fmaf(wf, fp[co], acc[co]);
                         }
                     }
                 }
@@ -165,6 +171,7 @@ int launch_cconv_direct(const ConvParams& p, cudaStream_t st, bool* handled) {
     if (p.cout > 4) return DMCF_OK;
     const size_t smem = ((size_t)p.kc * p.cout + 4 + (size_t)kDirWarps * 32 * kDirRecWords) * sizeof(float);
     if (smem > 200 * 1024) return DMCF_OK;
+    if ((int64_t)p.gp.kx * p.cin * p.cout >= 32768) return DMCF_OK;  // corner offsets travel as 16-bit fields of the parked record
     *handled = true;
     switch (p.cout) {
         case 1: return launch_direct<1>(p, st);

@@ -452,7 +452,8 @@ class PBFNet(BaseModel):
                 align_corners=True, coordinate_mapping=self.coordinate_mapping, normalize=False,
                 interpolation=self.interpolation, window=win.typ if win else None, window_fac=win.fac if win else 1.0,
                 feat_scale=self.part_scale, skip_self=self.ignore_query_points, bias=b, dense_inp=x,
-                dense_cin=cf + cb, kernel_size=self.kernel_size, pair_records=recs, out=own_rows)
+                dense_cin=cf + cb, kernel_size=self.kernel_size, pair_records=recs, out=own_rows,
+                block_diagonal=(cf, ch, ch))  # rows are [fluid | 0] or [0 | box], the filter is built block diagonal
         src = all_pos if self.use_bnds else pos
         if slab is not None and self.fused:
             dilated_pos, idx = self._slab_dilated_pos(slab, all_pos, all_in), [None] * len(self.strides)

@@ -477,9 +477,10 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
                     max_temp_mem_MB=64, *, window=None, window_fac=1.0, relu_input=False, feat_scale=1.0,
                     ascc=False, skip_self=False, nbr_range=None, bias=None, dense_inp=None, dense_cin=0,
                     residual=None, out=None, accumulate=False, kernel_size=None, pair_records=None,
-                    antisymmetric_filter=False):
+                    antisymmetric_filter=False, block_diagonal=None):
     """``ml3d.ops.continuous_conv`` (kwargs as assembled at utils/convolutions.py:414-429) plus keyword-only fused
-    extras (see include/dmcf_b200.h).  ``filters`` is [kz,ky,kx,Cin,Cout] or, with a fused Dense, the flattened
+    extras (see include/dmcf_b200.h).  ``block_diagonal=(cin_a, cout_a, cout_b)`` is the caller's promise of
+    ``dmcf_conv_desc::block_cin`` (two convs over zero-padded channel groups fused into one call).  ``filters`` is [kz,ky,kx,Cin,Cout] or, with a fused Dense, the flattened
     [(kz*ky*kx*Cin + dense_cin), Cout] matrix together with ``kernel_size``."""
     lib = _lib.load()
     n_out_dev = count_of(out_positions)
@@ -542,6 +543,9 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     d.accumulate = int(bool(accumulate))
     d.filter_antisym = int(bool(antisymmetric_filter))  # promise: filters[rev(cell)] == -filters[cell] exactly
     d.n_out_dev = None if n_out_dev is None else n_out_dev.data_ptr()
+    if block_diagonal is not None:
+        d.block_cin = int(block_diagonal[0])
+        d.block_cout[:] = [int(block_diagonal[1]), int(block_diagonal[2])]
     dense_stride = 0
     if dense_cin:
         dense_inp, dense_stride = _rows(dense_inp, "dense_inp")
@@ -565,7 +569,8 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
         neighbors_index = torch.zeros(1, dtype=torch.int32, device=out_positions.device)
     rec = None
     if PROFILE is not None:
-        rec = dict(kernel=conv_kernel_name((kz, ky, kx), cin, cout, interpolation, int(dense_cin), bool(antisymmetric_filter)),
+        rec = dict(kernel=conv_kernel_name((kz, ky, kx), cin, cout, interpolation, int(dense_cin), bool(antisymmetric_filter),
+                                           block_diagonal, bool(ascc or normalize or nbr_range)),
                    kernel_size=(kz, ky, kx), cin=cin, cout=cout, ascc=bool(ascc), n_inp=n_inp, n_out=n_out,
                    rows=kz * ky * kx * cin + int(dense_cin),
                    pairs=int(getattr(neighbors_index, "_dmcf_true_pairs", neighbors_index.shape[0])),
@@ -803,14 +808,18 @@ def set_kernel_options(options):
     """bit 0: register-patch kernels for wide layers (k_cconv_ws / k_cconv_lean, default on), bit 1: direct kernel for cout <= 4,
     bit 2: z-split launches of the legacy k_cconv_wide, bit 3: legacy k_cconv_wide instead of k_cconv_lean, bit 5: single-pair
     walk for narrow inputs, bit 6: query-centric search for prefix searches, bit 7: the warp-specialised k_cconv_ws instead of
-    k_cconv_lean (a measured experiment, slower).  Returns the previous mask."""
+    k_cconv_lean (a measured experiment, slower), bit 12: no narrow direct kernel (k_cconv_narrow).  Returns the previous mask."""
     return int(_lib.load().dmcf_set_kernel_options(int(options)))
 
 
-def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0, antisymmetric_filter=False):
+def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0, antisymmetric_filter=False, block_diagonal=None,
+                     not_narrow=False):
     """Which kernel dmcf_cconv_forward dispatches to with the default options (mirrors csrc/cconv.cu)."""
     kz, ky, kx = (int(k) for k in kernel_size)
     kc = kz * ky * kx * cin + dense_cin
+    if (block_diagonal is not None and not not_narrow and cout <= 32 and dense_cin <= 32 and kz * ky * kx < 512
+            and block_diagonal[0] <= 4 and 1 <= cin - block_diagonal[0] <= 4 and max(block_diagonal[1:]) <= 8):
+        return "k_cconv_narrow"
     if (antisymmetric_filter and interpolation == "linear" and cin <= 32
             and ((kz, ky, kx), cout) == ((1, 8, 8), 2)):
         return "k_cconv_apatch"

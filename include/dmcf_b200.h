@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define DMCF_B200_VERSION 104
+#define DMCF_B200_VERSION 105
 
 enum dmcf_status {
     DMCF_OK = 0,
@@ -141,6 +141,14 @@ typedef struct dmcf_conv_desc {
                                allows the folded half-patch kernel k_cconv_apatch.  0 is always safe */
     const int32_t* n_out_dev; /* optional device-side number of out points (<= n_out, which is then the capacity the kernels
                                  are launched for); rows >= *n_out_dev of `out` are not written */
+    int32_t block_cin;      /* > 0: the caller guarantees a BLOCK DIAGONAL layer, as the fused input layer of the DMCF nets is built
+                               (fluid_convs + obs_convs over zero-padded [fluid | box] features, models/pbf_model.py:375-411):
+                               input channels [0, block_cin) reach outputs [0, block_cout[0]) only, input channels
+                               [block_cin, cin) reach outputs [block_cout[0], block_cout[0] + block_cout[1]) only (every other
+                               conv filter entry is zero; fused Dense rows are not restricted), and every input feature row is
+                               all zero in one of the two channel groups.  Allows the narrow direct kernel k_cconv_narrow.
+                               0 is always safe */
+    int32_t block_cout[2];
 } dmcf_conv_desc;
 
 int dmcf_cconv_forward(const dmcf_conv_desc* desc, const float* filters,
@@ -184,7 +192,8 @@ int dmcf_cconv_patches(const dmcf_conv_desc* desc, const float* out_positions, i
  * not use k_cconv_apatch, bit 5 = k_cconv_lean keeps the one-pair-per-step walk for inputs with <= 8 channels instead of the
  * multi-pair phase 1, bit 6 = searches whose queries are a prefix of the grid's points keep the query-centric k_frs instead of
  * the cell-centric k_frs_cell, bit 7 = the wide layers run the warp-specialised k_cconv_ws (producer / consumer warps on
- * double-buffered half tiles; a measured experiment, slower than k_cconv_lean) (bits 3-7 are kept for A/B measurements);
+ * double-buffered half tiles; a measured experiment, slower than k_cconv_lean), bit 12 = do not use the narrow direct kernel
+ * k_cconv_narrow (bits 3-7 and 12 are kept for A/B measurements);
  * 0 forces the generic kernel.  Returns the previous
  * mask.  Results agree to float32 rounding. */
 int dmcf_set_kernel_options(int options);

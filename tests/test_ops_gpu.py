@@ -243,6 +243,68 @@ def test_continuous_conv_fused_extras(cuda, kernel_options, cin):
     assert float(out_wide[:, :3].abs().sum()) == 0 and float(out_wide[:, 3 + cout:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("shape", [(4, 4, 8, 8, 8), (3, 2, 5, 7, 4), (1, 4, 8, 3, 0), (4, 1, 2, 8, 8)],
+                         ids=["c4-input-layer", "ragged-groups", "one-channel-group", "one-box-channel"])
+@pytest.mark.parametrize("with_records", [False, True])
+def test_block_diagonal_input_layer(cuda, shape, with_records):
+    """The fused input layer of the DMCF nets (models/pbf_model.py:375-411: fluid_convs + obs_convs + two Dense over zero-padded
+    [fluid | box] rows, one block diagonal filter): the narrow direct kernel (k_cconv_narrow, takes the block promise of
+    dmcf_conv_desc::block_cin) against the O64 oracle of the zero-padded conv, and against the register-patch route (option bit 12)
+    which ignores the promise.  Rows of the two kinds are interleaved (ghost rows arrive in any order)."""
+    from dmcf_b200 import ops
+    ca, cb, na, nb, n_dense = shape
+    rng = np.random.default_rng(sum(shape))
+    n, ks = 900, (4, 4, 4)
+    cin, cout = ca + cb, na + nb + n_dense
+    pts = rng.random((n, 3)).astype(np.float32)
+    kind_b = rng.random(n) < 0.3
+    feats = rng.standard_normal((n, cin)).astype(np.float32)
+    feats[kind_b, :ca] = 0
+    feats[~kind_b, ca:] = 0
+    feats[~kind_b, 0] = 1
+    feats[kind_b, ca] = 1
+    filt = np.zeros(ks + (cin, cout), np.float32)
+    filt[..., :ca, :na] = rng.uniform(-0.5, 0.5, ks + (ca, na))
+    filt[..., ca:, na:na + nb] = rng.uniform(-0.5, 0.5, ks + (cb, nb))
+    dk = np.zeros((cin, cout), np.float32)
+    dk[:, na + nb:] = rng.uniform(-0.5, 0.5, (cin, n_dense))
+    bias = rng.standard_normal(cout).astype(np.float32)
+    extent = np.float32(0.3)
+    radius = np.float32(0.5) * extent
+    idx, splits, d2 = o64.fixed_radius_search(pts, pts, radius, ignore_query_point=True)
+    imp = o64.window("poly6", d2.astype(np.float64) / np.float64(radius) ** 2)
+    ref = o64.continuous_conv(filt, pts, extent, (0, 0, 0), pts, feats * np.float32(0.25), None, idx, imp, splits,
+                              align_corners=True, coordinate_mapping="ball_to_cube_volume_preserving", normalize=False,
+                              interpolation="linear")
+    ref = ref + feats.astype(np.float64) @ dk + bias
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    w_ext = torch.cat([t(filt).reshape(-1, cout), t(dk)], dim=0)
+    recs = None
+    if with_records:
+        recs = ops.prepare_pair_records(ks, t(pts), float(extent), None, t(pts), None, t(idx), None, t(splits), align_corners=True,
+                                        coordinate_mapping="ball_to_cube_volume_preserving", interpolation="linear", window="poly6")
+    got = {}
+    for opt in (3, 3 | 4096):
+        prev = ops.set_kernel_options(opt)
+        try:
+            launches = ops.launch_count()
+            got[opt] = ops.continuous_conv(
+                w_ext, t(pts), float(extent), None, t(pts), t(feats), None, t(idx), None, t(splits), align_corners=True,
+                coordinate_mapping="ball_to_cube_volume_preserving", normalize=False, interpolation="linear", window="poly6",
+                feat_scale=0.25, bias=t(bias), dense_inp=t(feats), dense_cin=cin, kernel_size=ks, pair_records=recs,
+                block_diagonal=(ca, na, nb)).cpu().numpy()
+            assert ops.launch_count() == launches + 1
+        finally:
+            ops.set_kernel_options(prev)
+        feat_close(got[opt], ref)
+    feat_close(got[3], got[3 | 4096], 0.5)
+    # a promise that does not fit the layer is refused
+    with pytest.raises(Exception):
+        ops.continuous_conv(w_ext, t(pts), float(extent), None, t(pts), t(feats), None, t(idx), None, t(splits), align_corners=True,
+                            coordinate_mapping="ball_to_cube_volume_preserving", window="poly6", dense_inp=t(feats), dense_cin=cin,
+                            kernel_size=ks, block_diagonal=(cin, na, nb))
+
+
 def test_ascc_fused_matches_reference_form_and_conserves(cuda, kernel_options):
     """Antisymmetric layer: fused (f_j + f_i) kernel vs the reference's two-pass form (utils/convolutions.py:433-458)
     and momentum conservation sum_i out_i = 0."""

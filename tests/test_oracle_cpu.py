@@ -262,7 +262,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dmcf_version() == 104
+    assert lib.dmcf_version() == 105
     # error path without a GPU: invalid arguments are rejected before any CUDA call
     import ctypes as C
     rc = lib.dmcf_cconv_forward(None, None, None, 0, None, None, 0, 0, None, None, None, None, None, None, 0, None, 0, None, 0, None, 0, None)
