@@ -119,8 +119,10 @@ struct PairRec {
     float norm;   // contribution to the normaliser (sum of neighbour importances / neighbour count)
 };
 
-// Evaluates pair `n` of the CSR list for the out point at (ox,oy,oz).
-__device__ __forceinline__ PairRec eval_pair(const ConvParams& p, int64_t n, bool in_range, float ox, float oy, float oz) {
+// Evaluates pair `n` of the CSR list for the out point at (ox,oy,oz); `idx` = nbr_index[n], loaded by the caller (a kernel
+// that evaluates the geometry itself fetches the indices of the NEXT chunk while it works on this one, so that the dependent
+// position gather is the only exposed round trip).
+__device__ __forceinline__ PairRec eval_pair_idx(const ConvParams& p, int64_t n, bool in_range, int idx, float ox, float oy, float oz) {
     PairRec r;
     r.row = -1;
     r.norm = 0.0f;
@@ -128,7 +130,6 @@ __device__ __forceinline__ PairRec eval_pair(const ConvParams& p, int64_t n, boo
     r.g.wx0 = r.g.wx1 = r.g.wy0 = r.g.wy1 = r.g.wz0 = r.g.wz1 = 0.0f;
     if (!in_range) return r;
     const bool filter_nbr = p.nbr_hi > p.nbr_lo;
-    const int idx = __ldg(p.nbr_index + n);
     if (filter_nbr && (idx < p.nbr_lo || idx >= p.nbr_hi)) return r;
     const int row = filter_nbr ? idx - p.nbr_lo : idx;
     const float dx = __ldg(p.inp_pos + 3 * (int64_t)row) - ox;
@@ -149,6 +150,10 @@ __device__ __forceinline__ PairRec eval_pair(const ConvParams& p, int64_t n, boo
     r.g.wz1 *= a;
     r.row = row;
     return r;
+}
+
+__device__ __forceinline__ PairRec eval_pair(const ConvParams& p, int64_t n, bool in_range, float ox, float oy, float oz) {
+    return eval_pair_idx(p, n, in_range, in_range ? __ldg(p.nbr_index + n) : 0, ox, oy, oz);
 }
 
 // Same pair from the precomputed record arrays (normaliser not stored: prepare refuses `normalize`).

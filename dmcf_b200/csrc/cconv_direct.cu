@@ -30,16 +30,36 @@ __global__ void __launch_bounds__(kDirWarps * 32, 1) k_cconv_direct(const ConvPa
 
     const int64_t n_warps = (int64_t)gridDim.x * kDirWarps;
     const int64_t n_out = conv_n_out(p);
-    for (int64_t o = (int64_t)blockIdx.x * kDirWarps + warp; o < n_out; o += n_warps) {
+    // the next point's row bounds and position are fetched while this point is worked on, its first neighbour indices once
+    // the bounds have arrived (end of this point): a point starts with its operands in flight instead of three dependent trips
+    int64_t o = (int64_t)blockIdx.x * kDirWarps + warp;
+    int64_t rs_n = 0, re_n = 0;
+    float ox_n = 0.f, oy_n = 0.f, oz_n = 0.f;
+    int idx_first = 0;
+    if (o < n_out) {
+        rs_n = p.row_splits[o]; re_n = p.row_splits[o + 1];
+        ox_n = __ldg(p.out_pos + 3 * o); oy_n = __ldg(p.out_pos + 3 * o + 1); oz_n = __ldg(p.out_pos + 3 * o + 2);
+        if (!p.records && rs_n + lane < re_n) idx_first = __ldg(p.nbr_index + rs_n + lane);
+    }
+    for (; o < n_out; o += n_warps) {
         float acc[COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
-        const float ox = __ldg(p.out_pos + 3 * o), oy = __ldg(p.out_pos + 3 * o + 1), oz = __ldg(p.out_pos + 3 * o + 2);
-        const int64_t rs = p.row_splits[o], re = p.row_splits[o + 1];
+        const float ox = ox_n, oy = oy_n, oz = oz_n;
+        const int64_t rs = rs_n, re = re_n;
+        const int64_t o2 = o + n_warps;
+        if (o2 < n_out) {
+            rs_n = p.row_splits[o2]; re_n = p.row_splits[o2 + 1];
+            ox_n = __ldg(p.out_pos + 3 * o2); oy_n = __ldg(p.out_pos + 3 * o2 + 1); oz_n = __ldg(p.out_pos + 3 * o2 + 2);
+        }
         float norm_acc = 0.0f;
+        // without precomputed records the neighbour indices run one chunk ahead of the geometry that gathers their positions
+        int idx_next = idx_first;
         for (int64_t c0 = rs; c0 < re; c0 += 32) {
             const int64_t n = c0 + lane;
-            const PairRec pr = pair_record(p, n, n < re, ox, oy, oz);
+            const int idx_cur = idx_next;
+            if (!p.records && n + 32 < re) idx_next = __ldg(p.nbr_index + n + 32);
+            const PairRec pr = p.records ? load_pair(p, n, n < re) : eval_pair_idx(p, n, n < re, idx_cur, ox, oy, oz);
             const int row = pr.row;
             norm_acc += pr.norm;
             // Parked record: {row, base cell offset, dx | dy << 16, dz} in filter WORDS (cell stride folded in once per pair by the
@@ -113,6 +133,7 @@ __global__ void __launch_bounds__(kDirWarps * 32, 1) k_cconv_direct(const ConvPa
                 }
             }
         }
+        if (!p.records && o2 < n_out && rs_n + lane < re_n) idx_first = __ldg(p.nbr_index + rs_n + lane);
         if (p.normalize) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) norm_acc += __shfl_xor_sync(0xffffffffu, norm_acc, off);

@@ -64,6 +64,12 @@ __global__ void __launch_bounds__(256) k_correct(const float* __restrict__ pos, 
 
 }  // namespace dmcf
 
+namespace dmcf {
+int launch_dense_umma(const float* x, int64_t n, int cin, int64_t x_stride, const float* w, const float* b, int cout, int relu_input,
+                      float* out, int64_t out_stride, cudaStream_t st, bool* handled);  // dense_umma.cu
+extern std::atomic<int> g_kernel_options;                                               // cconv.cu
+}  // namespace dmcf
+
 using namespace dmcf;
 
 extern "C" int dmcf_dense_forward(const float* x, int64_t n, int32_t cin, int64_t x_stride, const float* w, const float* b,
@@ -73,6 +79,11 @@ extern "C" int dmcf_dense_forward(const float* x, int64_t n, int32_t cin, int64_
     if (n == 0) return DMCF_OK;
     DMCF_REQUIRE(x && w && out, "dense: NULL buffer");
     DMCF_REQUIRE(x_stride >= cin && out_stride >= cout, "dense: row stride smaller than channel count");
+    if (!(g_kernel_options.load(std::memory_order_relaxed) & 8192)) {  // tensor-core kernel (tcgen05, 3xTF32) for large batches
+        bool handled = false;
+        const int rc = launch_dense_umma(x, n, cin, x_stride, w, b, cout, relu_input, out, out_stride, (cudaStream_t)stream, &handled);
+        if (rc || handled) return rc;
+    }
     const size_t smem = (size_t)(cin * cout + 8 * cin) * 4;
     static bool attr_set = false;
     if (!attr_set) {

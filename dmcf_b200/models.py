@@ -105,10 +105,15 @@ class _StepCache:
                                                   return_distances=False, cell_list=self.cells[ck])
         return self.nns[k]
 
-    def records(self, key, nns, kernel_size, inp_pos, out_pos, extent, mapping, interpolation, window, skip_self):
-        """Pair geometry shared by every conv on the same (neighbour list, filter grid, window)."""
+    def records(self, key, nns, kernel_size, inp_pos, out_pos, extent, mapping, interpolation, window, skip_self,
+                only_if_shared=False):
+        """Pair geometry shared by every conv on the same (neighbour list, filter grid, window).  ``only_if_shared``: a conv whose
+        kernel does not need sorted records (k_cconv_direct) and that is the only user of its filter grid evaluates the geometry in
+        the kernel instead (no 20 B / pair written and read back); it still takes records another conv has already made."""
         k = (key, tuple(kernel_size), float(extent), mapping, interpolation, window.typ if window else None,
              window.fac if window else 1.0, bool(skip_self))
+        if k not in self.recs and only_if_shared:
+            return None
         if k not in self.recs:
             self.recs[k] = ops.prepare_pair_records(
                 kernel_size, out_pos, extent, None, inp_pos, None, nns.neighbors_index, None, nns.neighbors_row_splits,
@@ -604,8 +609,10 @@ class PBFNet(BaseModel):
         nns = self._step.search(key, inp_pos, out_pos, 0.5 * float(extent))
         win = conv.window_function
         skip = bool(conv.radius_search_ignore_query_points and same_set)
+        direct = ops.conv_kernel_name(conv.kernel_size, x.shape[1], w.shape[1], self.interpolation,
+                                      x.shape[1] if dense is not None else 0) == "k_cconv_direct"
         recs = self._step.records(key, nns, conv.kernel_size, inp_pos, out_pos, float(extent), self.coordinate_mapping,
-                                  self.interpolation, win, skip)
+                                  self.interpolation, win, skip, only_if_shared=direct)
         return ops.continuous_conv(
             w, out_pos, float(extent), None, inp_pos, x, None, nns.neighbors_index, None, nns.neighbors_row_splits,
             align_corners=True, coordinate_mapping=self.coordinate_mapping, normalize=False,

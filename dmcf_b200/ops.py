@@ -581,8 +581,8 @@ def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_
     if pair_records is not None:
         _req(pair_records, "pair_records", dim=2)
         n_pairs = int(neighbors_index.shape[0])
-        if tuple(pair_records.shape) != (9, n_pairs) or not pair_records.is_contiguous():
-            raise ValueError("pair_records must be a contiguous [9, n_pairs] tensor from prepare_pair_records")
+        if tuple(pair_records.shape) != (RECORD_FIELDS, n_pairs) or not pair_records.is_contiguous():
+            raise ValueError(f"pair_records must be a contiguous [{RECORD_FIELDS}, n_pairs] tensor from prepare_pair_records")
     check(lib.dmcf_cconv_forward(C.byref(d), _p(filters), _p(out_positions), n_out, _p(inp_positions),
                                  _p(inp_features), inp_stride, n_inp, _p(inp_importance),
                                  _p(neighbors_index), _p(neighbors_row_splits),
@@ -678,7 +678,7 @@ def prepare_pair_records(kernel_size, out_positions, extents, offset, inp_positi
     d.nbr_lo, d.nbr_hi = (0, 0) if nbr_range is None else (int(nbr_range[0]), int(nbr_range[1]))
     d.n_out_dev = None if n_out_dev is None else n_out_dev.data_ptr()
     n_pairs = int(neighbors_index.shape[0])
-    records = torch.empty((9, n_pairs), dtype=torch.float32, device=out_positions.device)
+    records = torch.empty((RECORD_FIELDS, n_pairs), dtype=torch.float32, device=out_positions.device)
     rec = _prof_begin("pair_records", n_inp=inp_positions.shape[0], n_out=out_positions.shape[0],
                       pairs=int(getattr(neighbors_index, "_dmcf_true_pairs", n_pairs)))
     check(lib.dmcf_cconv_prepare(C.byref(d), _p(out_positions), out_positions.shape[0], _p(inp_positions),
@@ -810,6 +810,9 @@ def set_kernel_options(options):
     walk for narrow inputs, bit 6: query-centric search for prefix searches, bit 7: the warp-specialised k_cconv_ws instead of
     k_cconv_lean (a measured experiment, slower), bit 12: no narrow direct kernel (k_cconv_narrow).  Returns the previous mask."""
     return int(_lib.load().dmcf_set_kernel_options(int(options)))
+
+
+RECORD_FIELDS = 9  # dmcf_cconv_prepare: {row, i0, i1, wx0, wx1, wy0, wy1, wz0*a, wz1*a} per pair
 
 
 def conv_kernel_name(kernel_size, cin, cout, interpolation, dense_cin=0, antisymmetric_filter=False, block_diagonal=None,

@@ -404,6 +404,37 @@ def test_dense_and_elementwise(cuda):
         assert np.allclose(vn.cpu().numpy(), (pr - pos) / dt, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,cin,cout", [(10_000, 32, 32), (4096, 4, 8), (70_001, 96, 64), (5000, 24, 3), (33_333, 7, 20),
+                                        (200_000, 32, 32)])
+def test_dense_tensor_core_kernel(cuda, n, cin, cout):
+    """k_dense_umma (tcgen05.mma kind::tf32 as 3xTF32, accumulator in tensor memory) against the float64 oracle and against the
+    SIMT kernel k_dense (option bit 13), with relu, strided input / output rows and a ragged last tile."""
+    from dmcf_b200 import ops
+    rng = np.random.default_rng(n + cin)
+    x_wide = rng.standard_normal((n, cin + 8)).astype(np.float32)
+    x = x_wide[:, 4:4 + cin]
+    w = rng.standard_normal((cin, cout)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    ref = o64.dense(np.maximum(x, 0), w, b)
+    xw = t(x_wide)
+    got = {}
+    for opt in (3, 3 | 8192):
+        prev = ops.set_kernel_options(opt)
+        try:
+            out_wide = torch.full((n, cout + 4), -7.0, device=cuda)
+            ops.dense(xw[:, 4:4 + cin], t(w), t(b), relu_input=True, out=out_wide[:, 4:])
+            got[opt] = out_wide[:, 4:].cpu().numpy()
+            assert float((out_wide[:, :4] + 7.0).abs().sum()) == 0
+        finally:
+            ops.set_kernel_options(prev)
+        feat_close(got[opt], ref)
+    feat_close(got[3], got[3 | 8192], 0.5)
+    # contiguous rows, no relu, no bias
+    plain = ops.dense(t(x), t(w), None).cpu().numpy()
+    feat_close(plain, o64.dense(x, w, np.zeros(cout, np.float32)))
+
+
 def test_no_cpu_fallback(cuda):
     from dmcf_b200 import ops
     from dmcf_b200._lib import DmcfError
