@@ -51,6 +51,7 @@ SIGNATURES = {
     "dmcf_cconv_patches": (c_i32, [C.POINTER(ConvDesc), c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
                                    c_i64, c_vp, c_i64, c_vp]),
     "dmcf_cconv_records_bytes": (c_sz, [c_i64]),
+    "dmcf_umma_probe": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "dmcf_cconv_prepare": (c_i32, [C.POINTER(ConvDesc), c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
                                    c_vp]),
     "dmcf_set_kernel_options": (c_i32, [c_i32]),

@@ -223,4 +223,134 @@ int launch_dense_umma(const float* x, int64_t n, int cin, int64_t x_stride, cons
     return DMCF_OK;
 }
 
+
+// ---- measured experiment (dmcf_umma_probe): the tensor-core shape a conv's patch x filter product would have -------------------
+// D[64 x N] (+)= A_s[64 x 16] . B_s[N x 16]^T, kind::f16, for s = 0 .. ks-1 and `n_tiles` tiles per CTA: the A operand
+// (filter rows: [F_hi ; F_lo] of 32 output channels, 2 KB per k-step) STREAMS from global memory / L2 through a ring of
+// `stages` bulk copies (cp.async.bulk completing on mbarriers, slots released by tcgen05.commit), the B operand (the patch
+// tile: N points x K, hi and lo halves) is resident in shared memory.  One thread issues the copies, one the MMAs; the other
+// warps only read the accumulator of the last tile (which lets the host check the numerics and the M = 64 lane layout).
+// Timed from the host over all 148 SMs streaming the same filter: the L2 -> shared-memory stream is what bounds it.
+namespace umma {
+__host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+}  // namespace umma
+
+__global__ void __launch_bounds__(128, 1) k_umma_probe(const uint16_t* __restrict__ a_stream, const uint16_t* __restrict__ b_tile,
+                                                        int ks, int n, int n_tiles, int stages, int passes,
+                                                        float* __restrict__ d_out, long long* __restrict__ stats) {
+    extern __shared__ __align__(128) unsigned char psm[];
+    __shared__ __align__(8) uint64_t bars[2 * 64 + 1];  // full[stages], empty[stages], done
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ng = n >> 3;                           // row groups of the B operand
+    const uint32_t b_lbo = (uint32_t)ng * 128 + 16;  // K-chunk stride, padded by 16 bytes (bank spread of the patch stores)
+    unsigned char* ring = psm;                       // [stages][2048]
+    unsigned char* btile = psm + (size_t)stages * 2048;  // [passes][ks * 2 chunks][b_lbo]
+    const size_t b_bytes = (size_t)ks * 2 * b_lbo;
+    if (warp == 0) umma::tmem_alloc(tma::smem_u32(&tmem_base_slot), 32);
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) {
+            tma::mbar_init(tma::smem_u32(&bars[i]), 1);
+            tma::mbar_init(tma::smem_u32(&bars[64 + i]), 1);
+        }
+        tma::mbar_init(tma::smem_u32(&bars[128]), 1);
+        tma::mbar_fence_init();
+    }
+    for (size_t i = tid; i < (size_t)passes * b_bytes / 4; i += 128)
+        reinterpret_cast<uint32_t*>(btile)[i] = __ldg(reinterpret_cast<const uint32_t*>(b_tile) + i);
+    umma::fence_async_smem();
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+    if (warp == 0 && lane == 0) {  // producer: the filter stream
+        uint32_t it = 0;
+        long long t_wait = 0, t_copy = 0;
+        for (int t = 0; t < n_tiles; ++t)
+            for (int s = 0; s < ks; ++s, ++it) {
+                const int st = it % stages;
+                const uint32_t ph = (it / stages) & 1;
+                const long long c0 = clock64();
+                if (it >= (uint32_t)stages && !umma::mbar_wait_bounded(tma::smem_u32(&bars[64 + st]), ph ^ 1)) __trap();
+                const long long c1 = clock64();
+                tma::mbar_expect_tx(tma::smem_u32(&bars[st]), 2048);
+                tma::bulk_g2s(tma::smem_u32(ring + (size_t)st * 2048), a_stream + (size_t)s * 1024, 2048, tma::smem_u32(&bars[st]));
+                const long long c2 = clock64();
+                t_wait += c1 - c0; t_copy += c2 - c1;
+            }
+        if (stats && blockIdx.x == 0) { stats[0] = t_wait; stats[1] = t_copy; }
+    } else if (warp == 1 && lane == 0) {  // MMA issuer
+        long long t_wait = 0, t_mma = 0, t_commit = 0;
+        const uint32_t idesc = umma::instr_desc_f16(64, n);
+        uint32_t it = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            for (int s = 0; s < ks; ++s, ++it) {
+                const int st = it % stages;
+                const uint32_t ph = (it / stages) & 1;
+                const long long c0 = clock64();
+                if (!umma::mbar_wait_bounded(tma::smem_u32(&bars[st]), ph)) __trap();
+                umma::fence_after();
+                const long long c1 = clock64();
+                const uint64_t da = umma::smem_desc(tma::smem_u32(ring + (size_t)st * 2048), 1024, 128);
+                for (int q = 0; q < passes; ++q) {
+                    const uint64_t db = umma::smem_desc(tma::smem_u32(btile + q * b_bytes + (size_t)s * 2 * b_lbo), b_lbo, 128);
+                    umma::mma_f16(tmem_d, da, db, idesc, (s > 0 || q > 0) ? 1u : 0u);
+                }
+                const long long c2 = clock64();
+                umma::commit(tma::smem_u32(&bars[64 + st]));  // the slot is free once these MMAs have read it
+                const long long c3 = clock64();
+                t_wait += c1 - c0; t_mma += c2 - c1; t_commit += c3 - c2;
+            }
+        }
+        umma::commit(tma::smem_u32(&bars[128]));
+        if (stats && blockIdx.x == 0) { stats[2] = t_wait; stats[3] = t_mma; stats[4] = t_commit; }
+    }
+    // the idle lanes of the two role warps park HERE: a lane spinning in mbarrier.try_wait suspends its whole warp for the wait's
+    // time limit and would stall the issuing lane of the same warp on every iteration (measured: 1.7 us per k-step)
+    __syncwarp();
+    if (!umma::mbar_wait_bounded(tma::smem_u32(&bars[128]), 0)) __trap();
+    umma::fence_after();
+    __syncwarp();
+    if (d_out && blockIdx.x == 0) {  // all 128 accumulator lanes x n columns, raw (the host maps rows to lanes)
+        for (int c0 = 0; c0 < n; c0 += 8) {
+            float v[8];
+            umma::tmem_ld8(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            for (int i = 0; i < 8; ++i) d_out[(size_t)tid * n + c0 + i] = v[i];
+        }
+    }
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_d, 32);
+}
+
 }  // namespace dmcf
+
+extern "C" int dmcf_umma_probe(const void* a_stream, const void* b_tile, int32_t ks, int32_t n, int32_t n_tiles, int32_t stages,
+                               int32_t passes, int32_t n_ctas, float* d_out, long long* stats, void* stream) {
+    using namespace dmcf;
+    DMCF_REQUIRE(a_stream && b_tile && ks >= 1 && n >= 8 && n <= 32 && (n & 7) == 0 && n_tiles >= 1 && stages >= 1 && stages <= 64 &&
+                     passes >= 1 && passes <= 2 && n_ctas >= 1,
+                 "umma_probe: bad arguments");
+    const size_t smem = (size_t)stages * 2048 + (size_t)passes * ks * 2 * ((n >> 3) * 128 + 16);
+    DMCF_REQUIRE(smem <= 220 * 1024, "umma_probe: %zu bytes of shared memory", smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_umma_probe)");
+        attr_set = true;
+    }
+    k_umma_probe<<<(unsigned)n_ctas, 128, smem, (cudaStream_t)stream>>>((const uint16_t*)a_stream, (const uint16_t*)b_tile, ks, n,
+                                                                         n_tiles, stages, passes, d_out, stats);
+    DMCF_LAUNCH_CHECK("k_umma_probe");
+    return DMCF_OK;
+}

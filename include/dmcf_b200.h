@@ -205,6 +205,16 @@ int dmcf_set_kernel_options(int options);
 int dmcf_dense_forward(const float* x, int64_t n, int32_t cin, int64_t x_stride, const float* w, const float* b,
                        int32_t cout, int32_t relu_input, float* out, int64_t out_stride, void* stream);
 
+/* Measured experiment, not a product path (profiles/README.md, "tensor cores for the conv"): the tcgen05 shape a conv's
+ * patch x filter product would have.  Every CTA runs n_tiles x ks k-steps of  D[64 x n] += A_s[64 x 16] B_s[n x 16]^T
+ * (kind::f16, `passes` B operands per step) with the A operand (2 KB per k-step, UMMA K-major no-swizzle core-matrix order)
+ * streamed from `a_stream` through a ring of `stages` cp.async.bulk copies and the B operand (`passes` x ks x 2 chunks of
+ * (n / 8) x 128 + 16 bytes) resident in shared memory; d_out (may be NULL) receives the 128 x n accumulator lanes of CTA 0,
+ * stats (may be NULL) five cycle counters of CTA 0: producer {wait for a free slot, issue the copy}, MMA thread {wait for the
+ * data, issue the MMAs, commit}. */
+int dmcf_umma_probe(const void* a_stream, const void* b_tile, int32_t ks, int32_t n, int32_t n_tiles, int32_t stages,
+                    int32_t passes, int32_t n_ctas, float* d_out, long long* stats, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * elementwise step pieces (models/pbf_model.py:234-250, 466-487)
  *   integrate: vel2 = vel + dt*acc (acc == NULL -> gravity vector), pos2 = pos + dt*vel2
