@@ -36,7 +36,15 @@ namespace dmcf {
 
 // SL = 1: the register-patch walk above.  SL = 4 / 8 (cin <= 8 / 4): the multi-pair phase 1 of cconv_walk.cuh
 // (lean::point_patch_mp; relu / scale are run-time flags there, so those instances use RELU = FX = false).
-template <int KZ, int KY, int KX, int MT, int NW, bool RELU, bool FX, int SL>
+// TC = true (round 2, cout == 32, cin % 8 == 0, dense_cin % 8 == 0): phase 2 on the tensor cores through the warp-level path
+// (mma.sync m16n8k8 tf32, SASS HMMA.1688: 511 MAC per clock and SM measured, scripts/mma_sync_probe.cu, against 128 for FFMA2) as
+// 3xTF32 -- operands are split into hi / lo IN REGISTERS after the fragment loads, so the split costs no shared memory (what
+// rules tcgen05 out here): D[co][pt] += F_hi P_hi + F_lo P_hi + F_hi P_lo, float32 accumulators.  A warp
+// owns k-OCTETS w, w + NW, ... and the whole 32 x 24 output tile: 2 x 3 MMA tiles, 14 conflict-free LDS (8 filter words from a
+// swizzled 1 KB ring slot, 6 patch words) and 18 HMMA per octet instead of 2 x (28 wavefronts + 48 FFMA2).  The fused Dense rows
+// are not tile columns in this mode (the tile holds kc_conv columns, which makes room for two octet slots per warp): their B
+// fragments are read from the out points' own feature rows in global memory by the (at most one per warp) octet that needs them.
+template <int KZ, int KY, int KX, int MT, int NW, bool RELU, bool FX, int SL, bool TC = false>
 __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     using G = FilterGrid<KZ, KY, KX>;
     constexpr int K = G::K;
@@ -45,21 +53,27 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     constexpr int MTP = MT + 1;
     extern __shared__ __align__(1024) float smem[];
     // [NW gather rings of 512 B][patch tile, k-quad major [kc_pad/4][MT+1][4]; later [NW][MT][32]][NW record blocks][norm]
+    // TC: [NW scratch blocks of 2 KB = gather ring + record block, later two filter octet slots][patch tile of kc_conv columns][norm]
+    const int tile_cols = TC ? p.kc_conv : p.kc_pad;
+    constexpr int TCS = lean::tc_slots(MT);          // filter octet slots per warp (tensor-core phase 2)
+    constexpr int TCW = TCS * 256;                   // words of a warp's scratch block in that mode
+    static_assert(!TC || TCW >= lean::kScratchWords, "the octet slots reuse the phase-1 scratch");
     float* rings = smem;
-    float* patch = rings + (size_t)NW * lean::kGatherSlots * 32;
-    const size_t tile_words = (size_t)(p.kc_pad / 4) * MTP * 4, red_words = (size_t)NW * MT * 32;
+    float* patch = rings + (size_t)NW * (TC ? TCW : lean::kGatherSlots * 32);
+    const size_t tile_words = (size_t)(tile_cols / 4) * MTP * 4, red_words = (size_t)NW * MT * 32;
     float* recs = patch + (tile_words > red_words ? tile_words : red_words);
-    float* norm = recs + (size_t)NW * lean::kRecWords;  // [MT]
-    float* accs = norm + MT;                             // SL > 1: [NW][K][32] per-warp slot patches
+    float* norm = TC ? recs : recs + (size_t)NW * lean::kRecWords;  // [MT]
+    float* accs = norm + MT;                                         // SL > 1: [NW][K][32] per-warp slot patches
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile_base = (int64_t)blockIdx.x * MT;
     const int64_t n_out = conv_n_out(p);
     if (tile_base >= n_out) return;  // capacity-sized launch: tiles beyond the device-side count have nothing to do
-    float* wrec = recs + (size_t)warp * lean::kRecWords;
+    float* wring = TC ? rings + (size_t)warp * TCW : rings + (size_t)warp * lean::kGatherSlots * 32;
+    float* wrec = TC ? wring + lean::kGatherSlots * 32 : recs + (size_t)warp * lean::kRecWords;
     const bool lane_ci = lane < p.cin;
     lean::WarpCtx cx;
-    cx.init(rings + (size_t)warp * lean::kGatherSlots * 32, wrec, p, lane);
+    cx.init(wring, wrec, p, lane);
 
     // ================= phase 1: patch rows of this warp's points =================
     int64_t o = tile_base + warp;
@@ -130,7 +144,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         }
         // ---- Dense columns, padding ----
         if (!o_ok) {
-            for (int k = lane; k < p.kc_pad; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
+            for (int k = lane; k < tile_cols; k += 32) patch[patchq_index<MT>(m, k)] = 0.0f;
+        } else if (TC) {
+            if (p.normalize) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) norm_acc += __shfl_xor_sync(0xffffffffu, norm_acc, off);
+                if (lane == 0) norm[m] = norm_acc;
+            }
         } else {
             if (p.dense_cin > 0) {
                 const float* drow = p.dense_inp + o * p.dense_stride;
@@ -152,6 +172,144 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     }
     lean::cp_wait<0>();
 
+    if constexpr (TC) {
+        // ================= phase 2 on the tensor cores: D[co][pt] = sum_k F[k][co] P[pt][k], split-K over the warps =================
+        static_assert(MT % 8 == 0 && SL == 1, "tensor-core phase 2: whole 8-point MMA tiles, register-patch phase 1");
+        constexpr int NT = MT / 8;  // MMA tiles along the points
+        const int g = lane >> 2, t = lane & 3;
+        const int n_oct_conv = p.kc_conv >> 3, n_oct = (p.kc_conv + p.dense_cin) >> 3;
+        const int n_it = n_oct > warp ? (n_oct - warp + NW - 1) / NW : 0;
+        // lane L moves float4 L and L + 32 of an octet (8 filter rows x 32 channels, contiguous); row r is rotated by 8 (r % 4)
+        // words so that the fragment loads below (lanes = 8 channels x 4 rows) hit 32 different banks
+        uint32_t dst_off[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int f4 = lane + 32 * h, row = f4 >> 3, c4 = f4 & 7;
+            dst_off[h] = (uint32_t)(row * 32 + ((c4 * 4 + 8 * (row & 3)) & 31)) * 4u;
+        }
+        const float* fsrc = p.filters + (size_t)warp * 256 + lane * 4;
+        auto issue = [&](int it, float* sl) {
+            const uint32_t base = (uint32_t)__cvta_generic_to_shared(sl);
+            const int pred = it < n_it;
+            asm volatile("{ .reg .pred q; setp.ne.b32 q, %3, 0; @q cp.async.cg.shared.global [%0], [%2], 16; "
+                         "@q cp.async.cg.shared.global [%1], [%2 + 512], 16; }"
+                         ::"r"(base + dst_off[0]), "r"(base + dst_off[1]), "l"(fsrc), "r"(pred));
+            lean::cp_commit();
+            fsrc += (size_t)NW * 256;
+        };
+        __syncwarp();  // this warp's phase-1 scratch is dead
+#pragma unroll
+        for (int i = 0; i < TCS; ++i) issue(i, wring + i * 256);
+        // B fragments of this warp's Dense octet (at most one: dense_cin <= 8 NW): the out points' own feature rows
+        float bd[NT][2];
+        {
+            const int first_d = n_oct_conv + ((warp - n_oct_conv % NW) + NW) % NW;  // first octet >= n_oct_conv of this warp
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                bd[n][0] = bd[n][1] = 0.0f;
+                const int64_t oo = tile_base + 8 * n + g;
+                if (first_d < n_oct && oo < n_out) {
+                    const float* drow = p.dense_inp + oo * p.dense_stride + 8 * (first_d - n_oct_conv) + t;
+                    bd[n][0] = __ldg(drow); bd[n][1] = __ldg(drow + 4);
+                    if (p.relu_input) { bd[n][0] = fmaxf(bd[n][0], 0.0f); bd[n][1] = fmaxf(bd[n][1], 0.0f); }
+                }
+            }
+        }
+        __syncthreads();  // patch tile complete
+        float c[2][NT][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c[m][n][i] = 0.0f;
+        // fragment word offsets inside a slot: rows t and t + 4 share the rotation 8 t
+        int aoff[2][2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            aoff[m][0] = t * 32 + ((16 * m + g + 8 * t) & 31);
+            aoff[m][1] = t * 32 + ((16 * m + 8 + g + 8 * t) & 31);
+        }
+        const float* pb = patch + (size_t)(2 * warp) * MTP * 4 + g * 4 + t;  // word t of point g of the octet's first k-quad
+#pragma unroll 1
+        for (int it = 0; it < n_it; ++it) {
+            float* sl = wring + (it % TCS) * 256;
+            lean::cp_wait<TCS - 1>();
+            __syncwarp();  // every lane's part of this slot has landed
+            uint32_t ah[2][4], al[2][4], bh[NT][2], bl[NT][2];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const float a[4] = {sl[aoff[m][0]], sl[aoff[m][1]], sl[aoff[m][0] + 128], sl[aoff[m][1] + 128]};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ah[m][i] = __float_as_uint(a[i]) & 0xffffe000u;
+                    al[m][i] = __float_as_uint(a[i] - __uint_as_float(ah[m][i]));
+                }
+            }
+            const bool dense_oct = warp + it * NW >= n_oct_conv;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                float b0, b1;
+                if (dense_oct) {
+                    b0 = bd[n][0]; b1 = bd[n][1];
+                } else {
+                    b0 = pb[n * 32]; b1 = pb[n * 32 + MTP * 4];
+                }
+                bh[n][0] = __float_as_uint(b0) & 0xffffe000u; bl[n][0] = __float_as_uint(b0 - __uint_as_float(bh[n][0]));
+                bh[n][1] = __float_as_uint(b1) & 0xffffe000u; bl[n][1] = __float_as_uint(b1 - __uint_as_float(bh[n][1]));
+            }
+            __syncwarp();  // every lane has read this slot
+            issue(it + TCS, sl);
+            pb += (size_t)2 * NW * MTP * 4;
+#define DMCF_MMA_TF32(C, A, B)                                                                                              \
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+                 : "+f"(C[0]), "+f"(C[1]), "+f"(C[2]), "+f"(C[3])                                                           \
+                 : "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(B[0]), "r"(B[1]))
+            // three passes over the six accumulator tiles: consecutive MMAs on one accumulator are six instructions apart
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) DMCF_MMA_TF32(c[m][n], al[m], bh[n]);
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) DMCF_MMA_TF32(c[m][n], ah[m], bl[n]);
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) DMCF_MMA_TF32(c[m][n], ah[m], bh[n]);
+#undef DMCF_MMA_TF32
+        }
+        lean::cp_wait<0>();
+        __syncthreads();  // the patch is dead: partial sums reuse its storage
+        float* red = patch;  // [NW][MT][32]
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                float* r = red + ((size_t)warp * MT + 8 * n + 2 * t) * 32 + 16 * m + g;
+                r[0] = c[m][n][0]; r[32] = c[m][n][1]; r[8] = c[m][n][2]; r[40] = c[m][n][3];
+            }
+        __syncthreads();
+        for (int tt = tid; tt < MT * 32; tt += NW * 32) {
+            const int m = tt >> 5, cc2 = tt & 31;
+            const int64_t oo = tile_base + m;
+            if (oo < n_out && cc2 < p.cout) {
+                float v = 0.0f;
+#pragma unroll
+                for (int w2 = 0; w2 < NW; ++w2) v += red[((size_t)w2 * MT + m) * 32 + cc2];
+                if (p.normalize) {
+                    const float nv = norm[m];
+                    if (nv != 0.0f) v /= nv;
+                }
+                if (p.bias) v += __ldg(p.bias + cc2);
+                if (p.residual) v += __ldg(p.residual + oo * p.residual_stride + cc2);
+                float* dst = p.out + oo * p.out_stride + cc2;
+                if (p.accumulate) v += *dst;
+                *dst = v;
+            }
+        }
+    } else {
     // ================= phase 2: [MT x kc] x [kc x cout], split-K over the warps and over the quarter-warps =================
     // lane = (q = lane / 8: k = 4*kq + q, pr = (lane / 2) % 4: points 6*pr..6*pr+5, cc = lane % 2: channels 16*cc..16*cc+15)
     static_assert(MT == 24, "phase 2 thread tile assumes 24 points per CTA");
@@ -320,6 +478,36 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
             *dst = v;
         }
     }
+    }  // FFMA2 phase 2
+}
+
+static size_t lean_tc_smem_bytes(int mt, int nw, int kc_conv) {
+    const size_t tile = (size_t)(kc_conv / 4) * (mt + 1) * 4, red = (size_t)nw * mt * 32;
+    return ((tile > red ? tile : red) + (size_t)nw * lean::tc_slots(mt) * 256 + mt) * sizeof(float);
+}
+
+// Tensor-core phase 2 (mma.sync 3xTF32), two tile shapes: the FFMA2 kernel's 24 points x 12 warps (default), or 16 points x
+// 16 warps at 128 registers (option bit 16; one point per warp in phase 1, four octet slots per warp -- the 24 accumulators of
+// this phase 2 leave the registers for it).  Measured on the C4 32->32 layer: 6.52 ms against 6.70 ms (FFMA2 phase 2: 7.08 ms):
+// sixteen warps do not make phase 1 faster, and the filter is streamed 1.5 x as often.
+template <int KZ, int KY, int KX, int MT, int NW>
+static int launch_lean_tc(const ConvParams& p, cudaStream_t st) {
+    const bool fx = p.ascc || p.feat_scale != 1.0f;
+    void (*kerns_tc[2][2])(const ConvParams) = {
+        {k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 1, true>, k_cconv_lean<KZ, KY, KX, MT, NW, false, true, 1, true>},
+        {k_cconv_lean<KZ, KY, KX, MT, NW, true, false, 1, true>, k_cconv_lean<KZ, KY, KX, MT, NW, true, true, 1, true>}};
+    static bool tc_attr_set = false;
+    if (!tc_attr_set) {
+        for (int i = 0; i < 4; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kerns_tc[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(k_cconv_lean, tensor-core phase 2)");
+        }
+        tc_attr_set = true;
+    }
+    const int64_t tiles = ceil_div(p.n_out, MT);
+    kerns_tc[p.relu_input ? 1 : 0][fx ? 1 : 0]<<<(unsigned)tiles, NW * 32, lean_tc_smem_bytes(MT, NW, p.kc_conv), st>>>(p);
+    DMCF_LAUNCH_CHECK("k_cconv_lean (tensor-core phase 2)");
+    return DMCF_OK;
 }
 
 static size_t lean_smem_bytes(int mt, int nw, int kc_pad, int slot_patch_cells = 0) {
@@ -362,6 +550,11 @@ static int launch_lean_grid(const ConvParams& p, cudaStream_t st, bool* handled)
         return DMCF_OK;
     }
     const bool fx = p.ascc || p.feat_scale != 1.0f;
+    // tensor-core phase 2 (mma.sync 3xTF32): 32 output channels, whole k-octets, room for two octet slots per warp
+    if (!p.no_lean_tc && !p.patch_out && p.cout == 32 && p.cin % 8 == 0 && p.dense_cin % 8 == 0 && p.dense_cin <= 8 * NW) {
+        if (p.lean_tc_16 && lean_tc_smem_bytes(16, 16, p.kc_conv) <= 227 * 1024) return launch_lean_tc<KZ, KY, KX, 16, 16>(p, st);
+        if (lean_tc_smem_bytes(MT, NW, p.kc_conv) <= 227 * 1024) return launch_lean_tc<KZ, KY, KX, MT, NW>(p, st);
+    }
     kerns[p.relu_input ? 1 : 0][fx ? 1 : 0]<<<(unsigned)tiles, NW * 32, lean_smem_bytes(MT, NW, p.kc_pad), st>>>(p);
     DMCF_LAUNCH_CHECK("k_cconv_lean");
     return DMCF_OK;

@@ -155,8 +155,9 @@ def test_exclusive_scan_large(cuda):
 from conv_cases import CONV_CASES, conv_case_inputs  # noqa: E402
 
 
-@pytest.fixture(params=[3, 35, 131, 27, 31, 0], ids=["fast-kernels", "fast-kernels-single-pair-walk", "warp-specialised-experiment",
-                                                     "legacy-wide-direct", "legacy-wide-zsplit-direct", "generic-kernel"])
+@pytest.fixture(params=[3, 35, 131, 27, 31, 0, 3 | 32768, 3 | 65536],
+                ids=["fast-kernels", "fast-kernels-single-pair-walk", "warp-specialised-experiment", "legacy-wide-direct",
+                     "legacy-wide-zsplit-direct", "generic-kernel", "fast-kernels-ffma2-phase2", "fast-kernels-tc-16x16"])
 def kernel_options(request):
     from dmcf_b200 import ops
     prev = ops.set_kernel_options(request.param)
