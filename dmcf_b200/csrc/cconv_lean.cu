@@ -25,8 +25,8 @@
 //       the quarter-warp partial sums meet in a two-step shuffle reduce-scatter, the warps' in shared memory;
 //     * the filter streams L2 -> shared memory through a per-warp cp.async ring, two k-quads ahead
 //       (one LDGSTS per k-quad per warp, no registers held by the prefetch).
-// Tensor cores are deliberately not used: with N = cout <= 32 a tcgen05 tile would be bound by the same shared-memory
-// operand reads, and float32 accuracy needs 3xTF32.
+// Round 2: for cout == 32 phase 2 runs on the tensor cores through the warp-level path (mma.sync, 3xTF32 split in registers;
+// template parameter TC below).  tcgen05 was measured and ruled out for this shape (dense_umma.cu).
 #include <cuda_pipeline_primitives.h>
 
 #include "cconv_walk.cuh"
