@@ -377,6 +377,7 @@ extern "C" int dmcf_cconv_forward(const dmcf_conv_desc* d, const float* filters,
     p.no_multipair = (options >> 5) & 1;
     p.no_lean_tc = (options >> 15) & 1;
     p.lean_tc_16 = (options >> 16) & 1;
+    p.lean_cta_per_tile = (options >> 14) & 1;
     if ((options & 2) && !(options & 16)) {  // folded half-patch kernel for the antisymmetric output layer
         bool handled = false;
         rc = launch_cconv_apatch(p, st, &handled);

@@ -16,6 +16,7 @@ struct ConvParams {
     int debug_wrap_w;         // timing experiment switches (dmcf_set_kernel_options bits 8+), never set in production
     int filter_antisym;       // desc flag: filters[rev(cell)] == -filters[cell]
     int use_zsplit;           // option bit 2: run 4x4x4 wide layers as two z-half launches (2 CTAs/SM)
+    int lean_cta_per_tile;    // option bit 14: the tensor-core k_cconv_lean launches one CTA per tile instead of persistent CTAs (A/B)
     int lean_tc_16;           // option bit 16: tensor-core phase 2 on a 16-point / 16-warp tile instead of 24 points / 12 warps (A/B)
     int no_lean_tc;           // option bit 15: k_cconv_lean keeps the FFMA2 phase 2 (A/B switch for the tensor-core phase 2)
     int no_multipair;         // option bit 5: k_cconv_lean keeps the one-pair-per-step walk for narrow inputs (A/B switch)

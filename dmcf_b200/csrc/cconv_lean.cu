@@ -66,25 +66,62 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     float* accs = norm + MT;                                         // SL > 1: [NW][K][32] per-warp slot patches
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t tile_base = (int64_t)blockIdx.x * MT;
     const int64_t n_out = conv_n_out(p);
-    if (tile_base >= n_out) return;  // capacity-sized launch: tiles beyond the device-side count have nothing to do
+    const int64_t n_tiles = (n_out + MT - 1) / MT;  // capacity-sized launch: tiles beyond the device-side count do not exist
     float* wring = TC ? rings + (size_t)warp * TCW : rings + (size_t)warp * lean::kGatherSlots * 32;
     float* wrec = TC ? wring + lean::kGatherSlots * 32 : recs + (size_t)warp * lean::kRecWords;
     const bool lane_ci = lane < p.cin;
     lean::WarpCtx cx;
     cx.init(wring, wrec, p, lane);
 
+    // The grid may be smaller than the number of tiles (persistent CTAs, tensor-core variant): a CTA then walks tiles blockIdx.x,
+    // blockIdx.x + gridDim.x, ... and the first point of this warp in the NEXT tile is fetched during the current one -- its row
+    // bounds and position at the start of phase 1, its first chunk of pair records at the end of phase 1 (in flight during phase
+    // 2) -- so a tile starts with its operands at hand instead of two dependent round trips after a CTA launch.
+    // (The FFMA2 variants are launched with one CTA per tile and carry nothing across tiles: their 96 accumulators leave no
+    // registers for it -- measured: 7.08 -> 7.20 ms with the carried values spilled.)
+    int64_t tile = blockIdx.x;
+    int64_t t_rs = 0, t_re = 0;
+    float t_ox = 0.f, t_oy = 0.f, t_oz = 0.f;
+    PairRec t_cur;
+    if constexpr (TC) {
+        const int64_t o0 = tile * MT + warp;
+        if (tile < n_tiles && o0 < n_out) {
+            t_rs = p.row_splits[o0]; t_re = p.row_splits[o0 + 1];
+            t_ox = __ldg(p.out_pos + 3 * o0); t_oy = __ldg(p.out_pos + 3 * o0 + 1); t_oz = __ldg(p.out_pos + 3 * o0 + 2);
+        }
+        t_cur = pair_record(p, t_rs + lane, t_rs + lane < t_re, t_ox, t_oy, t_oz);
+    }
+    if (tile >= n_tiles) return;
+#pragma unroll 1
+    do {  // one pass for the FFMA2 variants (compile-time false loop condition), a tile loop for the tensor-core variant
+    const int64_t tile_base = tile * MT;
+
     // ================= phase 1: patch rows of this warp's points =================
     int64_t o = tile_base + warp;
     bool o_ok = o < n_out;
     int64_t rs = 0, re = 0;
     float ox = 0.f, oy = 0.f, oz = 0.f;
-    if (o_ok) {
-        rs = p.row_splits[o]; re = p.row_splits[o + 1];
-        ox = __ldg(p.out_pos + 3 * o); oy = __ldg(p.out_pos + 3 * o + 1); oz = __ldg(p.out_pos + 3 * o + 2);
+    PairRec cur;
+    bool t_ok = false;
+    if constexpr (TC) {
+        rs = t_rs; re = t_re; ox = t_ox; oy = t_oy; oz = t_oz;
+        cur = t_cur;
+        const int64_t tile_n = tile + gridDim.x;
+        const int64_t o_t = tile_n * MT + warp;
+        t_ok = tile_n < n_tiles && o_t < n_out;
+        t_rs = 0; t_re = 0;
+        if (t_ok) {
+            t_rs = p.row_splits[o_t]; t_re = p.row_splits[o_t + 1];
+            t_ox = __ldg(p.out_pos + 3 * o_t); t_oy = __ldg(p.out_pos + 3 * o_t + 1); t_oz = __ldg(p.out_pos + 3 * o_t + 2);
+        }
+    } else {
+        if (o_ok) {
+            rs = p.row_splits[o]; re = p.row_splits[o + 1];
+            ox = __ldg(p.out_pos + 3 * o); oy = __ldg(p.out_pos + 3 * o + 1); oz = __ldg(p.out_pos + 3 * o + 2);
+        }
+        cur = pair_record(p, rs + lane, rs + lane < re, ox, oy, oz);
     }
-    PairRec cur = pair_record(p, rs + lane, rs + lane < re, ox, oy, oz);
     if constexpr (SL > 1) {
         float* a = accs + (size_t)warp * K * 32 + lane;
 #pragma unroll 8
@@ -170,6 +207,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         o = o_n; o_ok = n_ok; rs = rs_n; re = re_n; ox = ox_n; oy = oy_n; oz = oz_n;
         cur = first_n;
     }
+    if constexpr (TC) t_cur = pair_record(p, t_rs + lane, t_ok && t_rs + lane < t_re, t_ox, t_oy, t_oz);  // in flight during phase 2
     lean::cp_wait<0>();
 
     if constexpr (TC) {
@@ -309,6 +347,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
                 *dst = v;
             }
         }
+        __syncthreads();  // partial sums read: the storage is the next tile's patch, the ring slots its scratch
     } else {
     // ================= phase 2: [MT x kc] x [kc x cout], split-K over the warps and over the quarter-warps =================
     // lane = (q = lane / 8: k = 4*kq + q, pr = (lane / 2) % 4: points 6*pr..6*pr+5, cc = lane % 2: channels 16*cc..16*cc+15)
@@ -479,6 +518,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
         }
     }
     }  // FFMA2 phase 2
+    } while (TC && (tile += gridDim.x) < n_tiles);
 }
 
 static size_t lean_tc_smem_bytes(int mt, int nw, int kc_conv) {
@@ -504,7 +544,8 @@ static int launch_lean_tc(const ConvParams& p, cudaStream_t st) {
         }
         tc_attr_set = true;
     }
-    const int64_t tiles = ceil_div(p.n_out, MT);
+    int64_t tiles = ceil_div(p.n_out, MT);
+    if (!p.lean_cta_per_tile && tiles > 148) tiles = 148;  // persistent CTAs, one per SM (option bit 14: one CTA per tile)
     kerns_tc[p.relu_input ? 1 : 0][fx ? 1 : 0]<<<(unsigned)tiles, NW * 32, lean_tc_smem_bytes(MT, NW, p.kc_conv), st>>>(p);
     DMCF_LAUNCH_CHECK("k_cconv_lean (tensor-core phase 2)");
     return DMCF_OK;
