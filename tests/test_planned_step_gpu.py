@@ -133,3 +133,22 @@ def test_graph_rollout_tracks_the_eager_rollout_with_evolving_state(cuda):
             a, b = eager.step(a), graph.step(b)
             assert float((a[0] - b[0]).abs().max()) <= 1e-5 * (i + 1), i
     assert graph.stats["graph_replays"] >= 5, graph.stats
+
+
+def test_bench_end_to_end_loop_returns_the_step_result(cuda):
+    """bench.py's `e2e` loop moves the inputs and results of neighbouring steps on side streams while a step computes: what
+    arrives in the pinned host buffers must be the result of Simulator.step on the same inputs."""
+    import bench
+    from dmcf_b200 import scenes
+    from dmcf_b200.simulator import Simulator
+    cfg, scene = scenes.c4_model_cfg(), scenes.lattice_scene((20, 16, 12), dx=0.05, seed=4)
+    model = build(cfg, cuda)
+    sample = sample_of(scene, cuda)
+    sim = Simulator(model, device="cuda", step_mode="graph")
+    with torch.no_grad():
+        for _ in range(3):
+            ref = sim.step(sample)
+    _, nbytes, o_pos, o_vel = bench.e2e_steps_timed(sim, scene, sample[4], sample[5], 4, lambda: torch.cuda.synchronize(), cuda,
+                                                    return_host_results=True)
+    assert nbytes == scene["pos"].size * 4 * 2
+    assert torch.equal(o_pos, ref[0].cpu()) and torch.equal(o_vel, ref[1].cpu())
