@@ -596,6 +596,16 @@ def main():
                     else "per-launch CUDA events inside the headline timed region",
                     "note": "wide CConv layers are fp32-FLOP bound (SURVEY 8d): HBM fraction reported as BASELINE asks, "
                             "fp32 TFLOP/s beside it" + ("; rank 0's launches (its slab)" if world > 1 else "")}
+        rec0 = next(g["rec"] for g in groups.values() if g["rec"]["kernel"] == top["kernel"] and g["rec"]["cin"] == top["cin"]
+                    and g["rec"]["cout"] == top["cout"])
+        if top["kernel"] == "k_cconv_lean" and top["cout"] == 32 and top["cin"] % 8 == 0 and top["cin"] > 8:
+            # phase 2 of this kernel runs on the tensor cores (mma.sync m16n8k8 tf32, three passes for float32 parity): its floor
+            # at the measured peak of that path (scripts/mma_sync_probe.cu: 511 MAC per clock and SM) against the launch
+            macs = 3.0 * rec0["n_out"] * rec0["rows"] * rec0["cout"]
+            floor_ms = macs / (511.0 * 148 * 1.965e9) * 1e3
+            roofline["tensor_pipe"] = {"path": "mma.sync m16n8k8 tf32 x3 (HMMA.1688.F32.TF32)", "mac_per_launch": macs,
+                                       "peak_mac_per_clk_sm": 511, "floor_ms": round(floor_ms, 3),
+                                       "frac_of_launch": round(floor_ms / top["avg_ms"], 4)}
 
     hbm_kernels = hbm_op_breakdown(hbm_ops, prof_region_ms, peak)
 
