@@ -44,7 +44,7 @@ namespace dmcf {
 // swizzled 1 KB ring slot, 6 patch words) and 18 HMMA per octet instead of 2 x (28 wavefronts + 48 FFMA2).  The fused Dense rows
 // are not tile columns in this mode (the tile holds kc_conv columns, which makes room for two octet slots per warp): their B
 // fragments are read from the out points' own feature rows in global memory by the (at most one per warp) octet that needs them.
-template <int KZ, int KY, int KX, int MT, int NW, bool RELU, bool FX, int SL, bool TC = false>
+template <int KZ, int KY, int KX, int MT, int NW, bool RELU, bool FX, int SL, int TC = 0>  // TC = filter octet slots per warp, 0 = FFMA2
 __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     using G = FilterGrid<KZ, KY, KX>;
     constexpr int K = G::K;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     // [NW gather rings of 512 B][patch tile, k-quad major [kc_pad/4][MT+1][4]; later [NW][MT][32]][NW record blocks][norm]
     // TC: [NW scratch blocks of 2 KB = gather ring + record block, later two filter octet slots][patch tile of kc_conv columns][norm]
     const int tile_cols = TC ? p.kc_conv : p.kc_pad;
-    constexpr int TCS = lean::tc_slots(MT);          // filter octet slots per warp (tensor-core phase 2)
+    constexpr int TCS = TC > 0 ? TC : 2;              // filter octet slots per warp (tensor-core phase 2)
     constexpr int TCW = TCS * 256;                   // words of a warp's scratch block in that mode
     static_assert(!TC || TCW >= lean::kScratchWords, "the octet slots reuse the phase-1 scratch");
     float* rings = smem;
@@ -521,21 +521,21 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
     } while (TC && (tile += gridDim.x) < n_tiles);
 }
 
-static size_t lean_tc_smem_bytes(int mt, int nw, int kc_conv) {
+static size_t lean_tc_smem_bytes(int mt, int nw, int kc_conv, int slots) {
     const size_t tile = (size_t)(kc_conv / 4) * (mt + 1) * 4, red = (size_t)nw * mt * 32;
-    return ((tile > red ? tile : red) + (size_t)nw * lean::tc_slots(mt) * 256 + mt) * sizeof(float);
+    return ((tile > red ? tile : red) + (size_t)nw * slots * 256 + mt) * sizeof(float);
 }
 
 // Tensor-core phase 2 (mma.sync 3xTF32), two tile shapes: the FFMA2 kernel's 24 points x 12 warps (default), or 16 points x
 // 16 warps at 128 registers (option bit 16; one point per warp in phase 1, four octet slots per warp -- the 24 accumulators of
 // this phase 2 leave the registers for it).  Measured on the C4 32->32 layer: 6.52 ms against 6.70 ms (FFMA2 phase 2: 7.08 ms):
 // sixteen warps do not make phase 1 faster, and the filter is streamed 1.5 x as often.
-template <int KZ, int KY, int KX, int MT, int NW>
+template <int KZ, int KY, int KX, int MT, int NW, int SLOTS>
 static int launch_lean_tc(const ConvParams& p, cudaStream_t st) {
     const bool fx = p.ascc || p.feat_scale != 1.0f;
     void (*kerns_tc[2][2])(const ConvParams) = {
-        {k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 1, true>, k_cconv_lean<KZ, KY, KX, MT, NW, false, true, 1, true>},
-        {k_cconv_lean<KZ, KY, KX, MT, NW, true, false, 1, true>, k_cconv_lean<KZ, KY, KX, MT, NW, true, true, 1, true>}};
+        {k_cconv_lean<KZ, KY, KX, MT, NW, false, false, 1, SLOTS>, k_cconv_lean<KZ, KY, KX, MT, NW, false, true, 1, SLOTS>},
+        {k_cconv_lean<KZ, KY, KX, MT, NW, true, false, 1, SLOTS>, k_cconv_lean<KZ, KY, KX, MT, NW, true, true, 1, SLOTS>}};
     static bool tc_attr_set = false;
     if (!tc_attr_set) {
         for (int i = 0; i < 4; ++i) {
@@ -546,7 +546,7 @@ static int launch_lean_tc(const ConvParams& p, cudaStream_t st) {
     }
     int64_t tiles = ceil_div(p.n_out, MT);
     if (!p.lean_cta_per_tile && tiles > 148) tiles = 148;  // persistent CTAs, one per SM (option bit 14: one CTA per tile)
-    kerns_tc[p.relu_input ? 1 : 0][fx ? 1 : 0]<<<(unsigned)tiles, NW * 32, lean_tc_smem_bytes(MT, NW, p.kc_conv), st>>>(p);
+    kerns_tc[p.relu_input ? 1 : 0][fx ? 1 : 0]<<<(unsigned)tiles, NW * 32, lean_tc_smem_bytes(MT, NW, p.kc_conv, SLOTS), st>>>(p);
     DMCF_LAUNCH_CHECK("k_cconv_lean (tensor-core phase 2)");
     return DMCF_OK;
 }
@@ -593,8 +593,9 @@ static int launch_lean_grid(const ConvParams& p, cudaStream_t st, bool* handled)
     const bool fx = p.ascc || p.feat_scale != 1.0f;
     // tensor-core phase 2 (mma.sync 3xTF32): 32 output channels, whole k-octets, room for two octet slots per warp
     if (!p.no_lean_tc && !p.patch_out && p.cout == 32 && p.cin % 8 == 0 && p.dense_cin % 8 == 0 && p.dense_cin <= 8 * NW) {
-        if (p.lean_tc_16 && lean_tc_smem_bytes(16, 16, p.kc_conv) <= 227 * 1024) return launch_lean_tc<KZ, KY, KX, 16, 16>(p, st);
-        if (lean_tc_smem_bytes(MT, NW, p.kc_conv) <= 227 * 1024) return launch_lean_tc<KZ, KY, KX, MT, NW>(p, st);
+        if (p.lean_tc_16 && lean_tc_smem_bytes(16, 16, p.kc_conv, 4) <= 227 * 1024) return launch_lean_tc<KZ, KY, KX, 16, 16, 4>(p, st);
+        // two octet slots per warp (four, where the 154 KB tile of 24 input channels leaves room, measured slower: 5.66 vs 5.58 ms)
+        if (lean_tc_smem_bytes(MT, NW, p.kc_conv, 2) <= 227 * 1024) return launch_lean_tc<KZ, KY, KX, MT, NW, 2>(p, st);
     }
     kerns[p.relu_input ? 1 : 0][fx ? 1 : 0]<<<(unsigned)tiles, NW * 32, lean_smem_bytes(MT, NW, p.kc_pad), st>>>(p);
     DMCF_LAUNCH_CHECK("k_cconv_lean");

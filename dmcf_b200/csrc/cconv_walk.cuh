@@ -17,9 +17,6 @@ static constexpr int kRecWords = 2 * kMetaSlots + kHeadWords + 8 * kWgtSlots;  /
 static constexpr int kFilterSlots = 3;    // phase 2: filter k-quads in flight per warp (slots of 128 words): slot 0 is the
                                           // warp's gather ring, slots 1..2 the head of its record block
 static constexpr int kScratchWords = kGatherSlots * 32 + kRecWords;            // per warp, both phases
-// tensor-core phase 2: the warp's gather ring + record block live in ONE block of tc_slots x 1 KB, reused as filter octet slots
-__host__ __device__ constexpr int tc_slots(int mt) { return mt == 16 ? 4 : 2; }
-
 __device__ __forceinline__ void cp_async4(uint32_t saddr, const void* gptr) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gptr));
 }
