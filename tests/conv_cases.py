@@ -34,6 +34,10 @@ CONV_CASES = [
     ("wide444_cin7_cout12", (4, 4, 4), 7, 12, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False, 0.4),
     # lattice without jitter: neighbours exactly on the filter border (g == fs-1), ties in the cell order
     ("wide444_lattice", (4, 4, 4), 8, 8, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", False, "lattice"),
+    # tensor-core phase 2 of k_cconv_lean (cout == 32, cin % 8 == 0) with the normaliser, and on the thin grids
+    ("tc444_norm", (4, 4, 4), 16, 32, "ball_to_cube_radial", "linear", True, True, "cubic", False),
+    ("tc181", (1, 8, 1), 16, 32, "ball_to_cube_volume_preserving", "linear", True, False, "poly6", True),
+    ("tc444_long_rows_cin24", (4, 4, 4), 24, 32, "ball_to_cube_volume_preserving", "linear", True, False, "peak", True, 0.45),
 ]
 
 
