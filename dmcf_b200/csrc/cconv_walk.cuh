@@ -65,11 +65,11 @@ __device__ __forceinline__ void merge_case(Walk& wk, float (&acc)[S::NACC], cons
         if (RELU) f = fmaxf(f, 0.0f);
         if (FX) f = fmaf(f, scale, fc);
         S::template scatter<C>(acc, wk.wa, wk.wb, f);
+        if ((mj.x | gate) >= 0) cp_async4(sj, fbase + (unsigned)mj.x);
+        cp_commit();
         wk.w += 8;
         wk.wa = *reinterpret_cast<const float4*>(wk.w);
         wk.wb = *reinterpret_cast<const float4*>(wk.w + 4);
-        if ((mj.x | gate) >= 0) cp_async4(sj, fbase + (unsigned)mj.x);
-        cp_commit();
         b_next = mj.y;
     } while (b_next == C);
 }
