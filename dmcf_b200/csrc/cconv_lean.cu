@@ -170,9 +170,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_cconv_lean(const ConvParams p) {
             if (o_ok && lane_ci) {
                 if ((p.cin & 3) == 0) {  // k = c*cin + lane: the k-quad advances by cin/4 per cell -> one running pointer
                     float* pp = patch + patchq_index<MT>(m, lane);
-                    const int step = p.cin * MTP;
+                    // the shipped widths get compile-time offsets: 64 STS with immediates instead of 64 x (address + STS)
+                    if (p.cin == 32) lean::store_patch_row<32 * MTP, K>(pp, acc);
+                    else if (p.cin == 24) lean::store_patch_row<24 * MTP, K>(pp, acc);
+                    else if (p.cin == 16) lean::store_patch_row<16 * MTP, K>(pp, acc);
+                    else {
+                        const int step = p.cin * MTP;
 #pragma unroll
-                    for (int c = 0; c < K; ++c) pp[c * step] = acc[c];
+                        for (int c = 0; c < K; ++c) pp[c * step] = acc[c];
+                    }
                 } else {
 #pragma unroll
                     for (int c = 0; c < K; ++c) patch[patchq_index<MT>(m, c * p.cin + lane)] = acc[c];

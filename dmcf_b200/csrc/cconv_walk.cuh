@@ -30,6 +30,13 @@ __device__ __forceinline__ float lds_f32(uint32_t saddr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
     return v;
 }
+// patch row of one point: cell c goes STEP words further (STEP = cin x (points per tile + 1), a compile-time constant here)
+template <int STEP, int K>
+__device__ __forceinline__ void store_patch_row(float* pp, const float (&acc)[K]) {
+#pragma unroll
+    for (int c = 0; c < K; ++c) pp[c * STEP] = acc[c];
+}
+
 // next 128-byte slot of a 512-byte aligned ring of kGatherSlots slots
 __device__ __forceinline__ uint32_t ring_next(uint32_t saddr) {
     return (saddr & ~(kGatherSlots * 128u - 1u)) | ((saddr + 128u) & (kGatherSlots * 128u - 1u));
