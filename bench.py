@@ -275,27 +275,35 @@ def e2e_steps_timed(sim, scene, box_d, bn_d, steps, barrier, dev, return_host_re
     main = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
-    def fetch():
+    # two device input buffers: the copy for step k + 1 runs while step k computes, into the buffer step k - 1 has finished with
+    # (no allocations on the side streams: a block freed there would wait for cross-stream events in the caching allocator)
+    d_pos = [torch.empty(h_pos.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+    d_vel = [torch.empty(h_vel.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+    read_done = [None, None]
+
+    def fetch(k):
+        b = k & 1
         with torch.cuda.stream(s_in):
-            p = h_pos.to(dev, non_blocking=True)
-            v = h_vel.to(dev, non_blocking=True)
+            if read_done[b] is not None:
+                s_in.wait_event(read_done[b])
+            d_pos[b].copy_(h_pos, non_blocking=True)
+            d_vel[b].copy_(h_vel, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(s_in)
-        return p, v, ev
+        return b, ev
 
     with torch.no_grad():
         def run(k_steps):
-            nxt = fetch()
+            nxt = fetch(0)
             for k in range(k_steps):
-                p, v, ev = nxt
+                b, ev = nxt
                 main.wait_event(ev)
-                p.record_stream(main)
-                v.record_stream(main)
                 if k + 1 < k_steps:
-                    nxt = fetch()
-                res = sim.step([p, v, None, None, box_d, bn_d])
+                    nxt = fetch(k + 1)
+                res = sim.step([d_pos[b], d_vel[b], None, None, box_d, bn_d])
                 done = torch.cuda.Event()
                 done.record(main)
+                read_done[b] = done
                 n = min(res[0].shape[0], o_pos.shape[0])  # slabs: migration may change the row count by a few
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(done)
