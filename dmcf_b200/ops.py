@@ -808,8 +808,8 @@ def set_kernel_options(options):
     """bit 0: register-patch kernels for wide layers (k_cconv_ws / k_cconv_lean, default on), bit 1: direct kernel for cout <= 4,
     bit 2: z-split launches of the legacy k_cconv_wide, bit 3: legacy k_cconv_wide instead of k_cconv_lean, bit 5: single-pair
     walk for narrow inputs, bit 6: query-centric search for prefix searches, bit 7: the warp-specialised k_cconv_ws instead of
-    k_cconv_lean (a measured experiment, slower), bit 12: no narrow direct kernel (k_cconv_narrow), bit 13: SIMT Dense, bit 15: FFMA2 instead of tensor-core phase 2 in
-    k_cconv_lean, bit 16: its 16-point / 16-warp tile.  Returns the previous mask."""
+    k_cconv_lean (a measured experiment, slower), bit 12: no narrow direct kernel (k_cconv_narrow), bit 13: SIMT Dense, bit 14: one CTA per tile in the tensor-core
+    k_cconv_lean, bit 15: FFMA2 instead of its tensor-core phase 2, bit 16: its 16-point / 16-warp tile.  Returns the previous mask."""
     return int(_lib.load().dmcf_set_kernel_options(int(options)))
 
 

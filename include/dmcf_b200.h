@@ -195,8 +195,8 @@ int dmcf_cconv_patches(const dmcf_conv_desc* desc, const float* out_positions, i
  * double-buffered half tiles; a measured experiment, slower than k_cconv_lean), bit 12 = do not use the narrow direct kernel
  * k_cconv_narrow, bit 13 = dmcf_dense_forward keeps the SIMT kernel k_dense instead of the tensor-core kernel k_dense_umma,
  * bit 15 = k_cconv_lean keeps its FFMA2 patch x filter product instead of the tensor-core one (mma.sync, 3xTF32),
- * bit 16 = the tensor-core product runs on 16-point / 16-warp tiles instead of 24 points / 12 warps
- * (bits 3-7, 12, 13, 15 and 16 are kept for A/B measurements);
+ * bit 14 = the tensor-core k_cconv_lean launches one CTA per tile instead of persistent CTAs, bit 16 = its product runs on
+ * 16-point / 16-warp tiles instead of 24 points / 12 warps (bits 3-7 and 12-16 are kept for A/B measurements);
  * 0 forces the generic kernel.  Returns the previous
  * mask.  Results agree to float32 rounding. */
 int dmcf_set_kernel_options(int options);
